@@ -1,0 +1,113 @@
+"""Pins the CPU oracle (oracle/oracle.py) to golden vectors produced by the unmodified
+reference (oracle/make_golden.py), and live to the reference when /root/reference exists."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle, ref_shim
+from helpers import STEP_TAGS, rel_err, rel_err_norm, step_inputs, well_separated
+
+
+def test_nn_matches_reference_golden(golden):
+    g = golden('nn')
+    p = torch.as_tensor(g['points'].astype(np.float64))
+    for key, kw in (('radius_r0.4', dict(r=0.4)), ('radius_r0.15', dict(r=0.15)), ('knn8', dict(k=8)),
+                    ('knn16_r0.3', dict(k=16, r=0.3)), ('knn32_r0.1', dict(k=32, r=0.1))):
+        dist, idx = oracle.nearest_neighbors(p, k=kw.get('k'), r=kw.get('r'))
+        assert idx.dtype == torch.int64
+        assert np.array_equal(idx.numpy(), g[key]), key
+        if key + '_dist' in g.files:
+            assert np.array_equal(dist.numpy(), g[key + '_dist']), key
+        else:
+            assert dist is None
+    q = torch.as_tensor(g['query'].astype(np.float64))
+    dist, idx = oracle.nearest_neighbors(p, q, k=4)
+    assert np.array_equal(idx.numpy(), g['cross_knn4']) and np.array_equal(dist.numpy(), g['cross_knn4_dist'])
+
+
+def test_nn_boundary_semantics(golden):
+    """ball query includes d == r; kNN distance_upper_bound is strict (nearest_neighbors.py:48-51)."""
+    g = golden('nn')
+    lat = torch.as_tensor(g['lattice'].astype(np.float64))
+    _, idx = oracle.nearest_neighbors(lat, r=0.5)
+    assert np.array_equal(idx.numpy(), g['lattice_radius_r0.5'])
+    assert set(idx[0].tolist()) == {0, 1, 2, 3, 4, 6}
+    dist, idx = oracle.nearest_neighbors(lat, k=3, r=0.5)
+    assert np.array_equal(idx.numpy()[:, :2], g['lattice_knn3_r0.5'][:, :2])
+    assert idx[0].tolist() == [0, 6, -1] and np.isinf(dist[0, 2].item())
+
+
+@pytest.mark.parametrize('tag', ['r', 'kr'])
+def test_features_match_reference_golden(golden, tag):
+    g = golden('features_' + tag)
+    pts = torch.as_tensor(g['points'].astype(np.float64))
+    vps, dirs, depth = oracle.from_points(pts)
+    assert np.array_equal(dirs.numpy(), g['dirs']) and np.array_equal(depth.numpy(), g['depth'])
+    nb = torch.as_tensor(g['neighbors'].astype(np.int64))
+    f = oracle.neighborhood_features(pts, nb, dirs=dirs)
+    for k in ('mean', 'cov', 'eigvals'):
+        assert np.max(np.abs(f[k].numpy() - g[k])) < 1e-14, k
+    # eigenvectors are only defined up to sign, and only for separated eigenvalues
+    ok = well_separated(g['eigvals'])
+    assert ok.mean() > 0.5
+    dots = np.abs(np.einsum('nij,nij->nj', f['eigvecs'].numpy(), g['eigvecs']))
+    assert np.all(np.abs(dots[ok] - 1) < 1e-9)
+    assert np.max(np.abs(f['normals'].numpy()[ok] - g['normals'][ok])) < 1e-9
+    assert np.max(np.abs(f['inc_angles'].numpy()[ok] - g['inc_angles'][ok])) < 1e-7
+    cfg_ratio = [[0, 1, 0, 0.25], [1, 2, 0.25, 1.0]]
+    gev = torch.as_tensor(g['eigvals'])   # mask logic on identical eigenvalues (bounds are knife-edge)
+    assert np.array_equal(oracle.eigenvalue_masks(gev, (), cfg_ratio).numpy(), g['mask_ratio'])
+    assert np.array_equal(oracle.eigenvalue_masks(gev, [[0, None, 0.01], [1, 0.0025, None]]).numpy(), g['mask_eig'])
+    assert np.array_equal(oracle.valid_neighbor_mask(nb, 5).numpy(), g['mask_valid'])
+
+
+@pytest.mark.parametrize('tag', STEP_TAGS)
+def test_step_matches_reference_golden(golden, tag):
+    g = golden('step_' + tag)
+    inp = step_inputs(g)
+    for sc in inp['scans']:
+        sc.pop('points32')
+    out = oracle.map_consistency_step(**inp)
+    assert rel_err(out['loss'], g['loss']) < 1e-12
+    assert rel_err_norm(out['per_point'], g['per_point']) < 1e-12
+    assert rel_err_norm(out['eigvals'], g['eigvals']) < 1e-12
+    assert rel_err_norm(out['w_grad'], g['w_grad']) < 1e-9
+    assert rel_err_norm(out['poses_grad'], g['poses_grad']) < 1e-9
+    if inp['pose_deltas'] is not None:
+        assert rel_err_norm(out['pose_deltas_grad'], g['pose_deltas_grad']) < 1e-9
+
+
+def test_model_and_transform_golden(golden):
+    g = golden('misc')
+    ang = torch.as_tensor(g['angles'])[:, None]
+    d = torch.full((10, 1), 20.0, dtype=torch.float64)
+    w, e = torch.tensor([[-0.06, -0.06]], dtype=torch.float64), torch.tensor([[2.0, 4.0]], dtype=torch.float64)
+    assert np.array_equal(oracle.correct_depth(d, ang, None, w, e, True).numpy(), g['d_scaled'])
+    assert np.array_equal(oracle.correct_depth(d, ang, None, w, e, False).numpy(), g['d_poly'])
+    m = torch.tensor([True, False] * 5)
+    assert np.array_equal(oracle.correct_depth(d, ang, m, w, e, True).numpy(), g['d_masked'])
+    mats = oracle.xyz_axis_angle_to_matrix(torch.as_tensor(g['xyz_axis_angle'])).numpy()
+    assert np.array_equal(mats, g['matrices'])
+
+
+def test_axis_angle_pinned_to_scipy(golden):
+    """pytorch3d is absent: pin our restatement of its axis-angle map to scipy's rotvec map."""
+    from scipy.spatial.transform import Rotation
+    g = golden('misc')
+    aa = g['xyz_axis_angle'][:, 3:]
+    ours = oracle.axis_angle_to_matrix(torch.as_tensor(aa)).numpy()
+    assert np.max(np.abs(ours - Rotation.from_rotvec(aa).as_matrix())) < 1e-14
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='reference tree only exists in the build container')
+def test_oracle_live_against_reference():
+    import warnings
+    warnings.simplefilter('ignore')
+    ref = ref_shim.load()
+    rng = np.random.default_rng(5)
+    pts = torch.as_tensor(rng.uniform(0, 2, (800, 3)).astype(np.float32).astype(np.float64))
+    for kw in (dict(r=0.3), dict(k=9), dict(k=9, r=0.25)):
+        d0, i0 = ref.nearest_neighbors(pts, pts, **kw)
+        d1, i1 = oracle.nearest_neighbors(pts, **kw)
+        assert torch.equal(i0, i1)
+        assert (d0 is None and d1 is None) or torch.equal(d0, d1)
