@@ -1,0 +1,427 @@
+// Kernel 1: radius / kNN / kNN-within-r neighbour search on the cell-sorted map, plus graph
+// format conversions (sliced-ELL <-> the reference's padded int64 [N,K]) and the transposed graph.
+// Replaces cKDTree.query / query_ball_point and the Python padding loop of
+// nearest_neighbors.py:46-73.
+#include <cub/cub.cuh>
+#include "dc_common.cuh"
+#include "dc_grid.cuh"
+
+#define NN_THREADS 128
+
+// ---------------------------------------------------------------------------------------------
+// Radius mode.  One thread per query (queries are cell-sorted, so a warp shares its candidate rows
+// and the candidate records stay in L1).  FILL=false counts, FILL=true writes sorted-space indices
+// in ascending order (rows of cells are visited in increasing key order).
+// ---------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(NN_THREADS)
+radius_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
+              const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
+              const int32_t* __restrict__ cell_start, double r2, int rings, int32_t* __restrict__ counts,
+              int32_t* __restrict__ slice_width, const int64_t* __restrict__ slice_ptr, int32_t* __restrict__ ell_idx) {
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int cnt = 0;
+  int64_t base = 0;
+  int width = 0;
+  if (FILL && q < nq) {
+    base = slice_ptr[q >> 5];
+    width = (int)((slice_ptr[(q >> 5) + 1] - base) >> 5);
+  }
+  if (q < nq) {
+    const dc_point pq = dc_ld_point(Q + q);
+    int c0, c1, c2;
+    dc_key_coords(g, qkeys[q], c0, c1, c2);
+    for (int e2 = -rings; e2 <= rings; ++e2) {
+      for (int e1 = -rings; e1 <= rings; ++e1) {
+        int lo, hi;
+        dc_row_range(g, pkeys, n, cell_start, c0 - rings, c0 + rings, c1 + e1, c2 + e2, lo, hi);
+        for (int j = lo; j < hi; ++j) {
+          const dc_point pj = dc_ld_point(P + j);
+          if (dc_dist2(pj, pq) <= r2) {
+            if (FILL) ell_idx[base + (int64_t)cnt * DC_SLICE + lane] = j;
+            ++cnt;
+          }
+        }
+      }
+    }
+    if (!FILL) counts[q] = cnt;
+  }
+  if (!FILL) {
+    int m = cnt;
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && q < nq) slice_width[q >> 5] = m;
+  } else if (q < nq) {
+    for (int c = cnt; c < width; ++c) ell_idx[base + (int64_t)c * DC_SLICE + lane] = -1;
+  } else if ((q >> 5) <= ((nq - 1) >> 5) && nq > 0) {
+    // tail lanes of the last (partial) slice: pad the whole column
+    base = slice_ptr[q >> 5];
+    width = (int)((slice_ptr[(q >> 5) + 1] - base) >> 5);
+    for (int c = 0; c < width; ++c) ell_idx[base + (int64_t)c * DC_SLICE + lane] = -1;
+  }
+}
+
+static int radius_launch(bool fill, const void* P, const uint64_t* pkeys, int64_t n, const void* Q,
+                         const uint64_t* qkeys, int64_t nq, const dc_grid_spec* spec, const int32_t* cell_start,
+                         double r, int32_t* counts, int32_t* slice_width, const int64_t* slice_ptr, int32_t* ell_idx,
+                         void* stream) {
+  if (nq <= 0) return DC_OK;
+  if (!(r > 0.0)) return dc_set_error(DC_ERR_ARG, "radius search: r must be positive");
+  dc_grid g;
+  int rc = dc_make_grid(spec, &g);
+  if (rc) return rc;
+  const int rings = (int)ceil(r / g.cell);
+  // cKDTree compares the squared distance against r*r (distance_upper_bound ** p)
+  const double r2 = r * r;
+  const int blocks = dc_blocks(((nq + 31) / 32) * 32, NN_THREADS);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fill)
+    radius_kernel<true><<<blocks, NN_THREADS, 0, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq, g,
+                                                        cell_start, r2, rings, counts, slice_width, slice_ptr, ell_idx);
+  else
+    radius_kernel<false><<<blocks, NN_THREADS, 0, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq, g,
+                                                         cell_start, r2, rings, counts, slice_width, slice_ptr, ell_idx);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+extern "C" int dc_radius_count(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys,
+                               int64_t nq, const dc_grid_spec* spec, const int32_t* cell_start, double r,
+                               int32_t* counts, int32_t* slice_width, void* stream) {
+  return radius_launch(false, P, pkeys, n, Q, qkeys, nq, spec, cell_start, r, counts, slice_width, nullptr, nullptr, stream);
+}
+
+extern "C" int dc_radius_fill(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys,
+                              int64_t nq, const dc_grid_spec* spec, const int32_t* cell_start, double r,
+                              const int64_t* slice_ptr, int32_t* ell_idx, void* stream) {
+  return radius_launch(true, P, pkeys, n, Q, qkeys, nq, spec, cell_start, r, nullptr, nullptr, slice_ptr, ell_idx, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kNN / kNN within r.  Shells of cells at Chebyshev distance rho = 0, 1, 2 ... are scanned until
+// the k-th best distance is provably final: every unscanned point is farther than rho * cell.
+// The k best (d2, original index) pairs live in a per-thread sorted list in local memory
+// (L1-resident); candidates that lose against the current k-th are rejected with one compare.
+// ---------------------------------------------------------------------------------------------
+template <int KMAX>
+struct TopK {
+  double d[KMAX];
+  int j[KMAX];       // sorted-space index
+  int cnt;
+};
+
+template <int KMAX>
+__device__ __forceinline__ void topk_insert(TopK<KMAX>& t, int k, double d2, int j, long long tag,
+                                            const dc_point* __restrict__ P) {
+  if (t.cnt == k) {
+    const double dw = t.d[k - 1];
+    if (d2 > dw) return;
+    if (d2 == dw && tag > P[t.j[k - 1]].tag) return;
+  }
+  int pos = (t.cnt < k) ? t.cnt++ : k - 1;
+  while (pos > 0) {
+    const double dp = t.d[pos - 1];
+    if (dp < d2) break;
+    if (dp == d2 && P[t.j[pos - 1]].tag < tag) break;
+    t.d[pos] = dp;
+    t.j[pos] = t.j[pos - 1];
+    --pos;
+  }
+  t.d[pos] = d2;
+  t.j[pos] = j;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(NN_THREADS)
+knn_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
+           const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
+           const int32_t* __restrict__ cell_start, int k, double r2, int max_ring, int32_t* __restrict__ ell_idx,
+           double* __restrict__ ell_d2) {
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t base = (q >> 5) * (int64_t)k * DC_SLICE;
+  if (q >= nq) {
+    if (nq > 0 && (q >> 5) <= ((nq - 1) >> 5))
+      for (int c = 0; c < k; ++c) {
+        ell_idx[base + (int64_t)c * DC_SLICE + lane] = -1;
+        if (ell_d2) ell_d2[base + (int64_t)c * DC_SLICE + lane] = INFINITY;
+      }
+    return;
+  }
+  TopK<KMAX> t;
+  t.cnt = 0;
+  const dc_point pq = dc_ld_point(Q + q);
+  int c0, c1, c2;
+  dc_key_coords(g, qkeys[q], c0, c1, c2);
+  // a query outside the grid box is clamped into a border cell; its distance to the box adds to the bound
+  const double slack_cell = g.cell * (1.0 - 1e-9);
+  for (int rho = 0; rho <= max_ring; ++rho) {
+    for (int e2 = -rho; e2 <= rho; ++e2) {
+      for (int e1 = -rho; e1 <= rho; ++e1) {
+        const bool full_row = (e2 == -rho || e2 == rho || e1 == -rho || e1 == rho);
+        const int nseg = full_row ? 1 : 2;   // interior rows only contribute their two end cells
+        for (int sgm = 0; sgm < nseg; ++sgm) {
+          int a, b;
+          if (full_row) { a = c0 - rho; b = c0 + rho; }
+          else if (sgm == 0) { a = b = c0 - rho; }
+          else { a = b = c0 + rho; }
+          int lo, hi;
+          dc_row_range(g, pkeys, n, cell_start, a, b, c1 + e1, c2 + e2, lo, hi);
+          for (int j = lo; j < hi; ++j) {
+            const dc_point pj = dc_ld_point(P + j);
+            const double d2 = dc_dist2(pj, pq);
+            if (d2 < r2) topk_insert<KMAX>(t, k, d2, j, pj.tag, P);
+          }
+        }
+      }
+    }
+    if (t.cnt == k) {
+      const double reach = rho * slack_cell;
+      if (t.d[k - 1] < reach * reach) break;
+    }
+  }
+  for (int c = 0; c < k; ++c) {
+    const bool ok = c < t.cnt;
+    ell_idx[base + (int64_t)c * DC_SLICE + lane] = ok ? t.j[c] : -1;
+    if (ell_d2) ell_d2[base + (int64_t)c * DC_SLICE + lane] = ok ? t.d[c] : INFINITY;
+  }
+}
+
+extern "C" int dc_knn(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
+                      const dc_grid_spec* spec, const int32_t* cell_start, int k, double r, int32_t* ell_idx,
+                      double* ell_d2, void* stream) {
+  if (nq <= 0) return DC_OK;
+  if (k < 1 || k > 256) return dc_set_error(DC_ERR_ARG, "dc_knn: k must be in [1, 256]");
+  dc_grid g;
+  int rc = dc_make_grid(spec, &g);
+  if (rc) return rc;
+  int max_ring = g.d[0] > g.d[1] ? g.d[0] : g.d[1];
+  max_ring = max_ring > g.d[2] ? max_ring : g.d[2];
+  double r2 = INFINITY;
+  if (r > 0.0) {
+    r2 = r * r;
+    const int rr = (int)ceil(r / g.cell);
+    if (rr < max_ring) max_ring = rr;
+  }
+  const int blocks = dc_blocks(((nq + 31) / 32) * 32, NN_THREADS);
+  cudaStream_t st = (cudaStream_t)stream;
+#define DC_KNN_CASE(KM)                                                                                          \
+  knn_kernel<KM><<<blocks, NN_THREADS, 0, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq, g, \
+                                                 cell_start, k, r2, max_ring, ell_idx, ell_d2)
+  if (k <= 8) DC_KNN_CASE(8);
+  else if (k <= 16) DC_KNN_CASE(16);
+  else if (k <= 32) DC_KNN_CASE(32);
+  else if (k <= 64) DC_KNN_CASE(64);
+  else if (k <= 128) DC_KNN_CASE(128);
+  else DC_KNN_CASE(256);
+#undef DC_KNN_CASE
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Export / import between sliced-ELL (sorted space, int32) and the reference layout
+// (original order, padded int64 [N,K], -1 = missing; nearest_neighbors.py:69-78).
+// ---------------------------------------------------------------------------------------------
+__global__ void ell_to_padded_kernel(const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ ell_idx,
+                                     int64_t nq, const int32_t* __restrict__ order_p,
+                                     const int32_t* __restrict__ order_q, int K, int64_t* __restrict__ out) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= nq) return;
+  const int lane = (int)(row & 31);
+  const int64_t base = slice_ptr[row >> 5];
+  const int width = (int)((slice_ptr[(row >> 5) + 1] - base) >> 5);
+  int64_t* o = out + (int64_t)order_q[row] * K;
+  for (int c = 0; c < K; ++c) {
+    int64_t v = -1;
+    if (c < width) {
+      const int j = ell_idx[base + (int64_t)c * DC_SLICE + lane];
+      if (j >= 0) v = order_p[j];
+    }
+    o[c] = v;
+  }
+}
+
+extern "C" int dc_ell_to_padded(const int64_t* slice_ptr, const int32_t* ell_idx, int64_t nq, const int32_t* order_p,
+                                const int32_t* order_q, int K, int64_t* out, void* stream) {
+  if (nq <= 0 || K <= 0) return DC_OK;
+  ell_to_padded_kernel<<<dc_blocks(nq, 128), 128, 0, (cudaStream_t)stream>>>(slice_ptr, ell_idx, nq, order_p, order_q, K, out);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+__global__ void ell_to_dist_kernel(int k, const double* __restrict__ ell_d2, const int32_t* __restrict__ ell_idx,
+                                   int64_t nq, const int32_t* __restrict__ order_q, double* __restrict__ out) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= nq) return;
+  const int lane = (int)(row & 31);
+  const int64_t base = (row >> 5) * (int64_t)k * DC_SLICE;
+  double* o = out + (int64_t)order_q[row] * k;
+  for (int c = 0; c < k; ++c) {
+    const int64_t e = base + (int64_t)c * DC_SLICE + lane;
+    o[c] = ell_idx[e] >= 0 ? sqrt(ell_d2[e]) : INFINITY;
+  }
+}
+
+extern "C" int dc_ell_to_dist(int k, const double* ell_d2, const int32_t* ell_idx, int64_t nq, const int32_t* order_q,
+                              double* out, void* stream) {
+  if (nq <= 0) return DC_OK;
+  ell_to_dist_kernel<<<dc_blocks(nq, 128), 128, 0, (cudaStream_t)stream>>>(k, ell_d2, ell_idx, nq, order_q, out);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+struct dc_row_offset {
+  int64_t K;
+  __host__ __device__ int64_t operator()(int64_t i) const { return i * K; }
+};
+
+extern "C" int dc_sort_rows(int64_t* rows, int64_t n, int K, void* temp, size_t* temp_bytes, void* stream) {
+  // -1 reinterpreted as uint64 is the maximum key, so padding stays at the end of every row
+  typedef dc_row_offset Off;
+  if ((double)n * (double)K > 2.0e9) return dc_set_error(DC_ERR_OVERFLOW, "dc_sort_rows: more than 2^31 entries");
+  cub::CountingInputIterator<int64_t> cnt(0);
+  cub::TransformInputIterator<int64_t, Off, cub::CountingInputIterator<int64_t>> begin(cnt, Off{K});
+  cub::TransformInputIterator<int64_t, Off, cub::CountingInputIterator<int64_t>> end(cnt + 1, Off{K});
+  uint64_t* keys = (uint64_t*)rows;
+  // in-place through the double-buffer-free API needs a second buffer: temp holds [cub temp | copy]
+  size_t cub_bytes = 0;
+  DC_CUDA_CHECK(cub::DeviceSegmentedSort::SortKeys(nullptr, cub_bytes, keys, keys, (int)(n * K), (int)n, begin, end,
+                                                   (cudaStream_t)stream));
+  cub_bytes = (cub_bytes + 255) & ~(size_t)255;
+  const size_t copy_bytes = (size_t)n * K * sizeof(uint64_t);
+  if (!temp) { *temp_bytes = cub_bytes + copy_bytes + 256; return DC_OK; }
+  if (*temp_bytes < cub_bytes + copy_bytes) return dc_set_error(DC_ERR_ARG, "dc_sort_rows: temp too small");
+  uint64_t* copy = (uint64_t*)((char*)temp + cub_bytes);
+  DC_CUDA_CHECK(cudaMemcpyAsync(copy, keys, copy_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  DC_CUDA_CHECK(cub::DeviceSegmentedSort::SortKeys(temp, cub_bytes, copy, keys, (int)(n * K), (int)n, begin, end,
+                                                   (cudaStream_t)stream));
+  return DC_OK;
+}
+
+// pass 1 (ell_idx == NULL): slice widths; pass 2: fill.  Rows of `neighbors` are in original order.
+__global__ void padded_to_ell_kernel(const int64_t* __restrict__ neighbors, int64_t n, int K,
+                                     const int32_t* __restrict__ order, const int32_t* __restrict__ inv_order,
+                                     int32_t* __restrict__ slice_width, const int64_t* __restrict__ slice_ptr,
+                                     int32_t* __restrict__ ell_idx) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // sorted-space row
+  const int lane = threadIdx.x & 31;
+  const bool live = row < n;
+  const int64_t* src = live ? neighbors + (int64_t)order[row] * K : nullptr;
+  if (!ell_idx) {
+    int cnt = 0;
+    if (live) for (int c = 0; c < K; ++c) cnt += (src[c] >= 0 && src[c] < n);
+    for (int o = 16; o > 0; o >>= 1) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o));
+    if (lane == 0 && live) slice_width[row >> 5] = cnt;
+    return;
+  }
+  if ((row >> 5) > ((n - 1) >> 5)) return;
+  const int64_t base = slice_ptr[row >> 5];
+  const int width = (int)((slice_ptr[(row >> 5) + 1] - base) >> 5);
+  int cnt = 0;
+  if (live)
+    for (int c = 0; c < K; ++c) {
+      const int64_t v = src[c];
+      if (v >= 0 && v < n) ell_idx[base + (int64_t)(cnt++) * DC_SLICE + lane] = inv_order[v];
+    }
+  for (int c = cnt; c < width; ++c) ell_idx[base + (int64_t)c * DC_SLICE + lane] = -1;
+}
+
+extern "C" int dc_padded_to_ell(const int64_t* neighbors, int64_t n, int K, const int32_t* order,
+                                const int32_t* inv_order, int32_t* slice_width, const int64_t* slice_ptr,
+                                int32_t* ell_idx, void* stream) {
+  if (n <= 0) return DC_OK;
+  const int blocks = dc_blocks(((n + 31) / 32) * 32, 128);
+  padded_to_ell_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(neighbors, n, K, order, inv_order, slice_width, slice_ptr, ell_idx);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Transposed graph: row j of the transpose lists every i with j in N(i) (ascending i).
+// ---------------------------------------------------------------------------------------------
+__global__ void graph_degrees_kernel(const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ ell_idx,
+                                     int64_t n_rows, int32_t* __restrict__ out_degree) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const int lane = (int)(row & 31);
+  const int64_t base = slice_ptr[row >> 5];
+  const int width = (int)((slice_ptr[(row >> 5) + 1] - base) >> 5);
+  int cnt = 0;
+  for (int c = 0; c < width; ++c) cnt += ell_idx[base + (int64_t)c * DC_SLICE + lane] >= 0;
+  out_degree[row] = cnt;
+}
+
+extern "C" int dc_graph_degrees(const int64_t* slice_ptr, const int32_t* ell_idx, int64_t n_rows, int32_t* out_degree,
+                                void* stream) {
+  if (n_rows <= 0) return DC_OK;
+  graph_degrees_kernel<<<dc_blocks(n_rows, 128), 128, 0, (cudaStream_t)stream>>>(slice_ptr, ell_idx, n_rows, out_degree);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+__global__ void graph_edges_kernel(const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ ell_idx,
+                                   int64_t n_rows, const int64_t* __restrict__ edge_offset, uint64_t* __restrict__ pairs) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const int lane = (int)(row & 31);
+  const int64_t base = slice_ptr[row >> 5];
+  const int width = (int)((slice_ptr[(row >> 5) + 1] - base) >> 5);
+  int64_t e = edge_offset[row];
+  for (int c = 0; c < width; ++c) {
+    const int j = ell_idx[base + (int64_t)c * DC_SLICE + lane];
+    if (j >= 0) pairs[e++] = ((uint64_t)(uint32_t)j << 32) | (uint64_t)(uint32_t)row;
+  }
+}
+
+extern "C" int dc_graph_edges(const int64_t* slice_ptr, const int32_t* ell_idx, int64_t n_rows,
+                              const int64_t* edge_offset, uint64_t* pairs, void* stream) {
+  if (n_rows <= 0) return DC_OK;
+  graph_edges_kernel<<<dc_blocks(n_rows, 128), 128, 0, (cudaStream_t)stream>>>(slice_ptr, ell_idx, n_rows, edge_offset, pairs);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+__global__ void transpose_kernel(const uint64_t* __restrict__ pairs, int64_t n_edges, int64_t n_cols,
+                                 int32_t* __restrict__ in_degree, int32_t* __restrict__ slice_width,
+                                 const int64_t* __restrict__ slice_ptr_t, int32_t* __restrict__ ell_idx_t) {
+  const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool live = col < n_cols;
+  int64_t lo = 0, hi = 0;
+  if (live) {
+    lo = dc_lower_bound(pairs, n_edges, (uint64_t)col << 32);
+    hi = dc_lower_bound(pairs, n_edges, (uint64_t)(col + 1) << 32);
+  }
+  const int deg = (int)(hi - lo);
+  if (!ell_idx_t) {
+    if (live) in_degree[col] = deg;
+    int m = deg;
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && live) slice_width[col >> 5] = m;
+    return;
+  }
+  if (n_cols <= 0 || (col >> 5) > ((n_cols - 1) >> 5)) return;
+  const int64_t base = slice_ptr_t[col >> 5];
+  const int width = (int)((slice_ptr_t[(col >> 5) + 1] - base) >> 5);
+  for (int c = 0; c < width; ++c)
+    ell_idx_t[base + (int64_t)c * DC_SLICE + lane] = c < deg ? (int32_t)(uint32_t)(pairs[lo + c] & 0xffffffffu) : -1;
+}
+
+extern "C" int dc_transpose_widths(const uint64_t* pairs_sorted, int64_t n_edges, int64_t n_cols, int32_t* in_degree,
+                                   int32_t* slice_width, void* stream) {
+  if (n_cols <= 0) return DC_OK;
+  const int blocks = dc_blocks(((n_cols + 31) / 32) * 32, 128);
+  transpose_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(pairs_sorted, n_edges, n_cols, in_degree, slice_width, nullptr, nullptr);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+extern "C" int dc_transpose_fill(const uint64_t* pairs_sorted, int64_t n_edges, int64_t n_cols,
+                                 const int64_t* slice_ptr_t, int32_t* ell_idx_t, void* stream) {
+  if (n_cols <= 0) return DC_OK;
+  const int blocks = dc_blocks(((n_cols + 31) / 32) * 32, 128);
+  transpose_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(pairs_sorted, n_edges, n_cols, nullptr, nullptr, slice_ptr_t, ell_idx_t);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}

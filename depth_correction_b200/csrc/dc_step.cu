@@ -1,0 +1,504 @@
+// Kernels 2 and 3: the fused fixed-graph map-consistency step (forward A: corrected world points,
+// forward B: neighbourhood covariance / eigen / loss, backward C: gather-form gradient down to the
+// model weights, exponents and per-scan poses).  See include/dc_b200.h for the reference mapping.
+//
+// HBM layout (sorted space): packed scan records 2 x vec4 + u32 per point, one 32-byte fp64 point
+// record per point (written by A, gathered by B and C), one 64-byte fp64 stash per point (written
+// by B, gathered by C), sliced-ELL int32 neighbour indices (read once per pass, coalesced).
+#include <cub/cub.cuh>
+#include "dc_common.cuh"
+#include "dc_math.cuh"
+
+#define STEP_THREADS 128
+
+template <typename T> struct vec4_of;
+template <> struct vec4_of<float> { typedef float4 type; };
+template <> struct vec4_of<double> { typedef double4 type; };
+
+struct dc_model {
+  int kind, n_terms;
+  const double* w;
+  const double* e;
+};
+
+// depth correction d' and (optionally) the powers g^e_k
+__device__ __forceinline__ double dc_correct_depth(const dc_model& m, bool masked, double d, double g, double* pw) {
+  if (m.kind == DC_MODEL_NONE || !masked) return d;
+  double bias = 0.0;
+#pragma unroll 1
+  for (int k = 0; k < m.n_terms; ++k) {
+    const double p = dc_pow_exp(g, m.e[k]);
+    if (pw) pw[k] = p;
+    bias += m.w[k] * p;
+  }
+  return m.kind == DC_MODEL_SCALED_POLYNOMIAL ? d * (1.0 - bias) : d - bias;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack scan rows into sorted space (one-time, per scan)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_records_kernel(const T* __restrict__ vps, const T* __restrict__ dirs, const T* __restrict__ depth,
+                                    const T* __restrict__ inc, const uint8_t* __restrict__ model_mask,
+                                    const uint8_t* __restrict__ loss_mask, int64_t first, int64_t count, int scan_id,
+                                    const int32_t* __restrict__ inv_order, typename vec4_of<T>::type* __restrict__ rec_dir,
+                                    typename vec4_of<T>::type* __restrict__ rec_vp, uint32_t* __restrict__ rec_meta) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t s = inv_order[first + i];
+  typename vec4_of<T>::type a, b;
+  a.x = dirs[3 * i]; a.y = dirs[3 * i + 1]; a.z = dirs[3 * i + 2]; a.w = depth[i];
+  if (vps) { b.x = vps[3 * i]; b.y = vps[3 * i + 1]; b.z = vps[3 * i + 2]; }
+  else { b.x = 0; b.y = 0; b.z = 0; }
+  b.w = inc ? inc[i] : (T)0;
+  uint32_t f = 0;
+  if (!model_mask || model_mask[i]) f |= DC_PT_MODEL_MASK;
+  if (!loss_mask || loss_mask[first + i]) f |= DC_PT_LOSS_MASK;
+  rec_dir[s] = a;
+  rec_vp[s] = b;
+  rec_meta[s] = ((uint32_t)scan_id << 2) | f;
+}
+
+extern "C" int dc_pack_records(const void* vps, const void* dirs, const void* depth, const void* inc_angles,
+                               const uint8_t* model_mask, const uint8_t* loss_mask, int dtype, int64_t first,
+                               int64_t count, int scan_id, const int32_t* inv_order, void* rec_dir, void* rec_vp,
+                               uint32_t* rec_meta, void* stream) {
+  if (count <= 0) return DC_OK;
+  if (scan_id < 0 || scan_id >= (1 << 30)) return dc_set_error(DC_ERR_ARG, "dc_pack_records: scan id out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = dc_blocks(count, 256);
+  if (dtype == DC_F32)
+    pack_records_kernel<float><<<blocks, 256, 0, st>>>((const float*)vps, (const float*)dirs, (const float*)depth,
+                                                       (const float*)inc_angles, model_mask, loss_mask, first, count,
+                                                       scan_id, inv_order, (float4*)rec_dir, (float4*)rec_vp, rec_meta);
+  else
+    pack_records_kernel<double><<<blocks, 256, 0, st>>>((const double*)vps, (const double*)dirs, (const double*)depth,
+                                                        (const double*)inc_angles, model_mask, loss_mask, first, count,
+                                                        scan_id, inv_order, (double4*)rec_dir, (double4*)rec_vp, rec_meta);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+__global__ void set_loss_mask_kernel(const uint8_t* __restrict__ loss_mask, int64_t n, const int32_t* __restrict__ order,
+                                     uint32_t* __restrict__ rec_meta) {
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  uint32_t m = rec_meta[s] & ~DC_PT_LOSS_MASK;
+  if (!loss_mask || loss_mask[order[s]]) m |= DC_PT_LOSS_MASK;
+  rec_meta[s] = m;
+}
+
+extern "C" int dc_set_loss_mask(const uint8_t* loss_mask, int64_t n, const int32_t* order, uint32_t* rec_meta, void* stream) {
+  if (n <= 0) return DC_OK;
+  set_loss_mask_kernel<<<dc_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(loss_mask, n, order, rec_meta);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass A: p = R_s (vp + d' dir) + t_s     (model.py:250-261, depth_cloud.py:122-152)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+step_points_kernel(const typename vec4_of<T>::type* __restrict__ rec_dir, const typename vec4_of<T>::type* __restrict__ rec_vp,
+                   const uint32_t* __restrict__ rec_meta, int64_t n, const double* __restrict__ poses, dc_model model,
+                   dc_point* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const typename vec4_of<T>::type a = rec_dir[i], b = rec_vp[i];
+  const uint32_t meta = rec_meta[i];
+  const double* Tm = poses + 12 * (size_t)(meta >> 2);
+  const double d = dc_correct_depth(model, meta & DC_PT_MODEL_MASK, (double)a.w, (double)b.w, nullptr);
+  const double x = (double)b.x + d * (double)a.x, y = (double)b.y + d * (double)a.y, z = (double)b.z + d * (double)a.z;
+  dc_point p;
+  p.x = Tm[0] * x + Tm[1] * y + Tm[2] * z + Tm[3];
+  p.y = Tm[4] * x + Tm[5] * y + Tm[6] * z + Tm[7];
+  p.z = Tm[8] * x + Tm[9] * y + Tm[10] * z + Tm[11];
+  p.tag = 0;
+  out[i] = p;
+}
+
+extern "C" int dc_step_points(const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta, int dtype, int64_t n,
+                              const double* poses, int n_scans, int model_kind, const double* w, const double* exponent,
+                              int n_terms, void* points_out, void* stream) {
+  if (n <= 0) return DC_OK;
+  if (n_terms < 0 || n_terms > DC_MAX_TERMS) return dc_set_error(DC_ERR_ARG, "dc_step_points: too many polynomial terms");
+  (void)n_scans;
+  dc_model m = {model_kind, n_terms, w, exponent};
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = dc_blocks(n, 256);
+  if (dtype == DC_F32)
+    step_points_kernel<float><<<blocks, 256, 0, st>>>((const float4*)rec_dir, (const float4*)rec_vp, rec_meta, n, poses, m, (dc_point*)points_out);
+  else
+    step_points_kernel<double><<<blocks, 256, 0, st>>>((const double4*)rec_dir, (const double4*)rec_vp, rec_meta, n, poses, m, (dc_point*)points_out);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass B: per point, gather the neighbourhood (coalesced index columns, 256-bit point records),
+// accumulate first and second moments relative to the query point in fp64, then
+// mean / covariance (utils.py:109-149) / eigen (depth_cloud.py:376-399) / loss (loss.py:216-370).
+// ---------------------------------------------------------------------------------------------
+struct dc_stash {   // 64 bytes
+  double mx, my, mz;   // neighbourhood mean (world)
+  double vx, vy, vz;   // eigenvector of the smallest eigenvalue
+  double alpha, beta;  // dl/dp_j = (alpha v v^T + beta I)(p_j - m)
+};
+
+__device__ __forceinline__ void dc_store_stash(dc_stash* dst, const dc_stash& s) {
+  double4* d4 = reinterpret_cast<double4*>(dst);
+  d4[0] = make_double4(s.mx, s.my, s.mz, s.vx);
+  d4[1] = make_double4(s.vy, s.vz, s.alpha, s.beta);
+}
+
+template <int LOSS>
+__global__ void __launch_bounds__(STEP_THREADS)
+step_forward_kernel(const dc_point* __restrict__ P, const uint32_t* __restrict__ rec_meta, int64_t n,
+                    const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ ell_idx, int flags,
+                    double* __restrict__ loss_pp, dc_stash* __restrict__ stash, double* __restrict__ eigvals,
+                    double* __restrict__ loss_sum, double* __restrict__ partials, unsigned int* __restrict__ done) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool live = row < n;
+  double l_acc = 0.0, c_acc = 0.0;
+  if (live) {
+    const int64_t base = slice_ptr[row >> 5];
+    const int width = (int)((slice_ptr[(row >> 5) + 1] - base) >> 5);
+    const int32_t* col = ell_idx + base + lane;
+    const dc_point pi = dc_ld_point(P + row);
+    const int self = (int)row;
+    int W = 0;
+    double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    int c = 0;
+    // 4 independent gathers in flight per thread; a missing neighbour (-1) is replaced by the query
+    // itself, whose offset is exactly zero, so the accumulators need no predication.
+    for (; c + 4 <= width; c += 4) {
+      const int j0 = __ldg(col + (c + 0) * DC_SLICE), j1 = __ldg(col + (c + 1) * DC_SLICE);
+      const int j2 = __ldg(col + (c + 2) * DC_SLICE), j3 = __ldg(col + (c + 3) * DC_SLICE);
+      const dc_point p0 = dc_ld_point(P + (j0 >= 0 ? j0 : self));
+      const dc_point p1 = dc_ld_point(P + (j1 >= 0 ? j1 : self));
+      const dc_point p2 = dc_ld_point(P + (j2 >= 0 ? j2 : self));
+      const dc_point p3 = dc_ld_point(P + (j3 >= 0 ? j3 : self));
+      W += (j0 >= 0) + (j1 >= 0) + (j2 >= 0) + (j3 >= 0);
+#define DC_ACC(p)                                                   \
+  {                                                                 \
+    const double dx = p.x - pi.x, dy = p.y - pi.y, dz = p.z - pi.z; \
+    sx += dx; sy += dy; sz += dz;                                   \
+    sxx = fma(dx, dx, sxx); sxy = fma(dx, dy, sxy); sxz = fma(dx, dz, sxz); \
+    syy = fma(dy, dy, syy); syz = fma(dy, dz, syz); szz = fma(dz, dz, szz); \
+  }
+      DC_ACC(p0) DC_ACC(p1) DC_ACC(p2) DC_ACC(p3)
+    }
+    for (; c < width; ++c) {
+      const int j0 = __ldg(col + c * DC_SLICE);
+      const dc_point p0 = dc_ld_point(P + (j0 >= 0 ? j0 : self));
+      W += (j0 >= 0);
+      DC_ACC(p0)
+    }
+#undef DC_ACC
+    const double Wd = (double)W;
+    const double iw = 1.0 / Wd;                       // W == 0 -> inf -> NaN features, like the reference's 0/0
+    const double cw = fmax(Wd - 1.0, 1e-6);           // utils.py:143-146
+    const double icw = 1.0 / cw;
+    dc_sym3 C;
+    C.xx = (sxx - sx * sx * iw) * icw; C.xy = (sxy - sx * sy * iw) * icw; C.xz = (sxz - sx * sz * iw) * icw;
+    C.yy = (syy - sy * sy * iw) * icw; C.yz = (syz - sy * sz * iw) * icw; C.zz = (szz - sz * sz * iw) * icw;
+    const double tr = C.xx + C.yy + C.zz;
+    double raw, alpha = 0.0, beta = 0.0;
+    double v0[3] = {0.0, 0.0, 0.0};
+    if (LOSS == DC_LOSS_TRACE) {
+      raw = tr;                                        // loss.py:329-330
+      beta = 1.0;
+      if (eigvals) {
+        double lam[3];
+        dc_sym3_eig(C, lam, nullptr, 0);
+        eigvals[3 * row] = lam[0]; eigvals[3 * row + 1] = lam[1]; eigvals[3 * row + 2] = lam[2];
+      }
+    } else {
+      double lam[3];
+      dc_sym3_eig(C, lam, v0, 1);
+      if (eigvals) { eigvals[3 * row] = lam[0]; eigvals[3 * row + 1] = lam[1]; eigvals[3 * row + 2] = lam[2]; }
+      if (flags & DC_FLAG_NORMALIZATION) {             // loss.py:253-254
+        const double tc = fmax(tr, 1e-6);
+        raw = lam[0] / tc;
+        alpha = 1.0 / tc;
+        beta = tr > 1e-6 ? -lam[0] / (tc * tc) : 0.0;
+      } else {
+        raw = lam[0];
+        alpha = 1.0;
+      }
+    }
+    const bool masked = rec_meta[row] & DC_PT_LOSS_MASK;
+    double val = raw, dfac = 1.0;
+    if (!(flags & DC_FLAG_RAW)) {
+      // relu (loss.py:284) then optional sqrt (:286-287); relu'(x <= 0) = 0 also kills sqrt'(0) = inf
+      if (raw > 0.0) {
+        if (flags & DC_FLAG_SQRT) { val = sqrt(raw); dfac = 0.5 / val; }
+      } else if (raw <= 0.0) {
+        val = 0.0; dfac = 0.0;
+      }                                                // NaN falls through unchanged
+      if (!masked) { val = 0.0; dfac = 0.0; }
+    }
+    if (loss_pp) loss_pp[row] = val;
+    if (masked) { l_acc = val; c_acc = 1.0; }
+    if (stash) {
+      const double f = 2.0 * icw * dfac;
+      dc_stash s;
+      s.mx = pi.x + sx * iw; s.my = pi.y + sy * iw; s.mz = pi.z + sz * iw;
+      s.vx = v0[0]; s.vy = v0[1]; s.vz = v0[2];
+      s.alpha = f * alpha; s.beta = f * beta;
+      dc_store_stash(stash + row, s);
+    }
+  }
+  if (!loss_sum) return;
+  // deterministic two-level reduction: per-block partials, last block adds them in index order
+  typedef cub::BlockReduce<double, STEP_THREADS> BR;
+  __shared__ typename BR::TempStorage tmp;
+  __shared__ bool is_last;
+  const double bl = BR(tmp).Sum(l_acc);
+  __syncthreads();
+  const double bc = BR(tmp).Sum(c_acc);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = bl;
+    partials[2 * blockIdx.x + 1] = bc;
+    __threadfence();
+    const unsigned int t = atomicAdd(done, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += STEP_THREADS) {
+      a += ((volatile double*)partials)[2 * i];
+      b += ((volatile double*)partials)[2 * i + 1];
+    }
+    __syncthreads();
+    const double ta = BR(tmp).Sum(a);
+    __syncthreads();
+    const double tb = BR(tmp).Sum(b);
+    if (threadIdx.x == 0) {
+      loss_sum[0] = ta;
+      loss_sum[1] = tb;
+      *done = 0;   // re-arm for the next launch
+    }
+  }
+}
+
+extern "C" int dc_step_forward(const void* points, const uint32_t* rec_meta, int64_t n, const int64_t* slice_ptr,
+                               const int32_t* ell_idx, int loss_kind, int flags, double* loss_pp, double* stash,
+                               double* eigvals, double* loss_sum, void* partials, size_t partials_bytes, void* stream) {
+  if (n <= 0) return DC_OK;
+  const int blocks = dc_blocks(((n + 31) / 32) * 32, STEP_THREADS);
+  if (loss_sum && partials_bytes < (size_t)blocks * 16 + 16)
+    return dc_set_error(DC_ERR_ARG, "dc_step_forward: partials buffer too small (need 16*blocks+16 bytes)");
+  double* part = (double*)partials;
+  unsigned int* done = loss_sum ? (unsigned int*)((char*)partials + (size_t)blocks * 16) : nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (loss_kind == DC_LOSS_TRACE)
+    step_forward_kernel<DC_LOSS_TRACE><<<blocks, STEP_THREADS, 0, st>>>((const dc_point*)points, rec_meta, n, slice_ptr, ell_idx, flags,
+                                                                         loss_pp, (dc_stash*)stash, eigvals, loss_sum, part, done);
+  else if (loss_kind == DC_LOSS_MIN_EIGVAL)
+    step_forward_kernel<DC_LOSS_MIN_EIGVAL><<<blocks, STEP_THREADS, 0, st>>>((const dc_point*)points, rec_meta, n, slice_ptr, ell_idx, flags,
+                                                                              loss_pp, (dc_stash*)stash, eigvals, loss_sum, part, done);
+  else
+    return dc_set_error(DC_ERR_ARG, "dc_step_forward: unknown loss kind");
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass C: gather-form backward.  Row j of the TRANSPOSED graph lists every i with j in N(i), so
+//   g_j = sum_i u_i (alpha_i v_i v_i^T + beta_i I)(p_j - m_i)
+// needs no atomics on per-point data.  g_j is chained in registers through p_j = R_s (vp + d' dir) + t_s:
+//   dL/dw_k, dL/de_k   block reduction -> one atomic per block and term
+//   dL/dT_s (3x4)      warp-segmented reduction over the scan ids present in the warp -> atomics
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dc_warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(STEP_THREADS)
+step_backward_kernel(const dc_point* __restrict__ P, const typename vec4_of<T>::type* __restrict__ rec_dir,
+                     const typename vec4_of<T>::type* __restrict__ rec_vp, const uint32_t* __restrict__ rec_meta, int64_t n,
+                     const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ ell_idx,
+                     const dc_stash* __restrict__ stash, const double* __restrict__ upstream,
+                     const double* __restrict__ poses, dc_model model, double* __restrict__ dw,
+                     double* __restrict__ dexp, double* __restrict__ dposes) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool live = row < n;
+  double gx = 0, gy = 0, gz = 0;
+  dc_point pj;
+  pj.x = pj.y = pj.z = 0.0;
+  if (live) {
+    const int64_t base = slice_ptr[row >> 5];
+    const int width = (int)((slice_ptr[(row >> 5) + 1] - base) >> 5);
+    const int32_t* col = ell_idx + base + lane;
+    pj = dc_ld_point(P + row);
+    const int self = (int)row;
+#define DC_BWD(i_)                                                                       \
+  {                                                                                      \
+    const int ii = (i_) >= 0 ? (i_) : self;                                              \
+    double4 s0, s1;                                                                      \
+    dc_ld256(stash + ii, s0.x, s0.y, s0.z, s0.w);                                        \
+    dc_ld256(reinterpret_cast<const char*>(stash + ii) + 32, s1.x, s1.y, s1.z, s1.w);    \
+    double u = (i_) >= 0 ? 1.0 : 0.0;                                                    \
+    if (upstream) u *= __ldg(upstream + ii);                                             \
+    const double ex = pj.x - s0.x, ey = pj.y - s0.y, ez = pj.z - s0.z;                   \
+    const double a = u * s1.z * (s0.w * ex + s1.x * ey + s1.y * ez), b = u * s1.w;       \
+    gx += a * s0.w + b * ex; gy += a * s1.x + b * ey; gz += a * s1.y + b * ez;           \
+  }
+    int c = 0;
+    for (; c + 2 <= width; c += 2) {
+      const int i0 = __ldg(col + (c + 0) * DC_SLICE), i1 = __ldg(col + (c + 1) * DC_SLICE);
+      DC_BWD(i0) DC_BWD(i1)
+    }
+    for (; c < width; ++c) {
+      const int i0 = __ldg(col + c * DC_SLICE);
+      DC_BWD(i0)
+    }
+#undef DC_BWD
+  }
+  // ---- chain rule through the point's own record
+  double gw[DC_MAX_TERMS], ge[DC_MAX_TERMS];
+#pragma unroll
+  for (int k = 0; k < DC_MAX_TERMS; ++k) { gw[k] = 0.0; ge[k] = 0.0; }
+  double gT[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) gT[k] = 0.0;
+  int scan = -1;
+  if (live) {
+    const typename vec4_of<T>::type a = rec_dir[row], b = rec_vp[row];
+    const uint32_t meta = rec_meta[row];
+    scan = (int)(meta >> 2);
+    const double* Tm = poses + 12 * (size_t)scan;
+    const bool mm = (model.kind != DC_MODEL_NONE) && (meta & DC_PT_MODEL_MASK);
+    double pw[DC_MAX_TERMS];
+    const double d0 = (double)a.w, gam = (double)b.w;
+    const double d = dc_correct_depth(model, mm, d0, gam, pw);
+    const double dx = (double)a.x, dy = (double)a.y, dz = (double)a.z;
+    // d L / d d' = (R dir) . g
+    const double gd = (Tm[0] * dx + Tm[1] * dy + Tm[2] * dz) * gx + (Tm[4] * dx + Tm[5] * dy + Tm[6] * dz) * gy +
+                      (Tm[8] * dx + Tm[9] * dy + Tm[10] * dz) * gz;
+    if (mm) {
+      const double f = (model.kind == DC_MODEL_SCALED_POLYNOMIAL ? -d0 : -1.0) * gd;
+      for (int k = 0; k < model.n_terms; ++k) {
+        gw[k] = f * pw[k];
+        if (dexp) ge[k] = f * model.w[k] * dc_pow_exp_dlog(gam, model.e[k], pw[k]);
+      }
+    }
+    const double x = (double)b.x + d * dx, y = (double)b.y + d * dy, z = (double)b.z + d * dz;
+    gT[0] = gx * x; gT[1] = gx * y; gT[2] = gx * z; gT[3] = gx;
+    gT[4] = gy * x; gT[5] = gy * y; gT[6] = gy * z; gT[7] = gy;
+    gT[8] = gz * x; gT[9] = gz * y; gT[10] = gz * z; gT[11] = gz;
+  }
+  // ---- model gradients: warp shuffle -> shared -> one atomic per block and term
+  if (model.kind != DC_MODEL_NONE && dw) {
+    __shared__ double red[STEP_THREADS / 32][2 * DC_MAX_TERMS];
+    for (int k = 0; k < model.n_terms; ++k) {
+      const double a = dc_warp_sum(gw[k]);
+      const double b = dexp ? dc_warp_sum(ge[k]) : 0.0;
+      if (lane == 0) { red[threadIdx.x >> 5][k] = a; red[threadIdx.x >> 5][DC_MAX_TERMS + k] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < model.n_terms) {
+      double a = 0.0, b = 0.0;
+      for (int wv = 0; wv < STEP_THREADS / 32; ++wv) { a += red[wv][threadIdx.x]; b += red[wv][DC_MAX_TERMS + threadIdx.x]; }
+      atomicAdd(dw + threadIdx.x, a);
+      if (dexp) atomicAdd(dexp + threadIdx.x, b);
+    }
+  }
+  // ---- pose gradients: segmented by scan id inside the warp
+  if (dposes) {
+    unsigned int remaining = __ballot_sync(0xffffffffu, live);
+    while (remaining) {
+      const int leader = __ffs(remaining) - 1;
+      const int s = __shfl_sync(0xffffffffu, scan, leader);
+      const bool mine = live && scan == s;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const double v = dc_warp_sum(mine ? gT[k] : 0.0);
+        if (lane == 0) atomicAdd(dposes + 12 * (size_t)s + k, v);
+      }
+      remaining &= ~__ballot_sync(0xffffffffu, mine);
+    }
+  }
+}
+
+extern "C" int dc_step_backward(const void* points, const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta,
+                                int dtype, int64_t n, const int64_t* slice_ptr_t, const int32_t* ell_idx_t,
+                                const double* stash, const double* upstream_pp, const double* poses, int n_scans,
+                                int model_kind, const double* w, const double* exponent, int n_terms, double* dw,
+                                double* dexponent, double* dposes, void* stream) {
+  if (n <= 0) return DC_OK;
+  if (n_terms < 0 || n_terms > DC_MAX_TERMS) return dc_set_error(DC_ERR_ARG, "dc_step_backward: too many polynomial terms");
+  (void)n_scans;
+  dc_model m = {model_kind, n_terms, w, exponent};
+  const int blocks = dc_blocks(((n + 31) / 32) * 32, STEP_THREADS);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DC_F32)
+    step_backward_kernel<float><<<blocks, STEP_THREADS, 0, st>>>((const dc_point*)points, (const float4*)rec_dir, (const float4*)rec_vp,
+                                                                 rec_meta, n, slice_ptr_t, ell_idx_t, (const dc_stash*)stash,
+                                                                 upstream_pp, poses, m, dw, dexponent, dposes);
+  else
+    step_backward_kernel<double><<<blocks, STEP_THREADS, 0, st>>>((const dc_point*)points, (const double4*)rec_dir, (const double4*)rec_vp,
+                                                                  rec_meta, n, slice_ptr_t, ell_idx_t, (const dc_stash*)stash,
+                                                                  upstream_pp, poses, m, dw, dexponent, dposes);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SE(3) pose corrections (eval.py:68-82, transform.py:68-78): one thread per scan.
+// ---------------------------------------------------------------------------------------------
+__global__ void pose_compose_kernel(const double* __restrict__ poses, const double* __restrict__ deltas, int n_scans,
+                                    int n_deltas, double* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_scans) return;
+  double P[16], d[6], T[12];
+  for (int k = 0; k < 16; ++k) P[k] = poses[16 * s + k];
+  const double* dp = deltas + 6 * (n_deltas == 1 ? 0 : s);
+  for (int k = 0; k < 6; ++k) d[k] = dp[k];
+  dc_pose_compose(P, d, T);
+  for (int k = 0; k < 12; ++k) out[12 * s + k] = T[k];
+}
+
+__global__ void pose_compose_bwd_kernel(const double* __restrict__ poses, const double* __restrict__ deltas, int n_scans,
+                                        int n_deltas, const double* __restrict__ dout, double* __restrict__ ddeltas) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_scans) return;
+  double P[16], d[6], g[12], gd[6];
+  for (int k = 0; k < 16; ++k) P[k] = poses[16 * s + k];
+  const double* dp = deltas + 6 * (n_deltas == 1 ? 0 : s);
+  for (int k = 0; k < 6; ++k) d[k] = dp[k];
+  for (int k = 0; k < 12; ++k) g[k] = dout[12 * s + k];
+  dc_pose_compose_bwd(P, d, g, gd);
+  if (n_deltas == 1) {
+    for (int k = 0; k < 6; ++k) atomicAdd(ddeltas + k, gd[k]);
+  } else {
+    for (int k = 0; k < 6; ++k) ddeltas[6 * s + k] = gd[k];
+  }
+}
+
+extern "C" int dc_pose_compose(const double* poses, const double* deltas, int n_scans, int n_deltas, double* out, void* stream) {
+  if (n_scans <= 0) return DC_OK;
+  if (n_deltas != 1 && n_deltas != n_scans) return dc_set_error(DC_ERR_ARG, "dc_pose_compose: n_deltas must be 1 or n_scans");
+  pose_compose_kernel<<<dc_blocks(n_scans, 64), 64, 0, (cudaStream_t)stream>>>(poses, deltas, n_scans, n_deltas, out);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+extern "C" int dc_pose_compose_backward(const double* poses, const double* deltas, int n_scans, int n_deltas,
+                                        const double* dout, double* ddeltas, void* stream) {
+  if (n_scans <= 0) return DC_OK;
+  if (n_deltas != 1 && n_deltas != n_scans) return dc_set_error(DC_ERR_ARG, "dc_pose_compose_backward: n_deltas must be 1 or n_scans");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_deltas == 1) DC_CUDA_CHECK(cudaMemsetAsync(ddeltas, 0, 6 * sizeof(double), st));
+  pose_compose_bwd_kernel<<<dc_blocks(n_scans, 64), 64, 0, st>>>(poses, deltas, n_scans, n_deltas, dout, ddeltas);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}

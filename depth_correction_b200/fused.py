@@ -1,0 +1,174 @@
+"""Fused fixed-graph map-consistency step (kernels 2 and 3) behind torch.autograd.
+
+One `StepState` holds everything that is constant over the optimisation loop of
+scripts/model_poses_learning:119-135 / train.py:225-312 for one global cloud: the cell-sorted
+packed scan records, the neighbourhood graph (and its transpose), and the scratch buffers the
+kernels write (corrected points, backward stash, per-point loss).  `fused_loss` runs
+
+    model(cloud) -> transform(pose) -> concatenate -> update_points/mean/cov/eig -> loss   (forward)
+    d loss / d {w, exponent, poses}                                                        (backward)
+
+as three kernel launches forward+backward-prologue and one backward launch.
+"""
+import torch
+
+from . import _lib as L
+
+__all__ = ['StepState', 'fused_loss', 'model_kind_of']
+
+
+def model_kind_of(model):
+    if model is None:
+        return L.MODEL_NONE
+    name = type(model).__name__
+    if name == 'ScaledPolynomial':
+        return L.MODEL_SCALED_POLYNOMIAL
+    if name == 'Polynomial':
+        return L.MODEL_POLYNOMIAL
+    if name == 'BaseModel':
+        return L.MODEL_NONE
+    raise NotImplementedError('fused step supports Polynomial / ScaledPolynomial models, got %s' % name)
+
+
+class StepState(object):
+    def __init__(self, graph, clouds):
+        """graph: Graph over the initial global cloud; clouds: per-scan local DepthClouds (in scan order)."""
+        smap = graph.map
+        dev = smap.device
+        n = smap.n
+        assert graph.self_query and graph.n_rows == n
+        sizes = [len(c) for c in clouds]
+        assert sum(sizes) == n, 'clouds (%i points) do not match the graph (%i points)' % (sum(sizes), n)
+        self.graph = graph
+        self.n = n
+        self.n_scans = len(clouds)
+        self.device = dev
+        dt = clouds[0].depth.dtype
+        self.dtype = dt
+        self.code = L.dtype_code(dt)
+        st = L.stream()
+        self.rec_dir = torch.empty((n, 4), dtype=dt, device=dev)
+        self.rec_vp = torch.empty((n, 4), dtype=dt, device=dev)
+        self.rec_meta = torch.empty(n, dtype=torch.int32, device=dev)
+        first = 0
+        keep = []
+        for s, c in enumerate(clouds):
+            cnt = len(c)
+            assert c.depth.dtype == dt and c.dirs.is_cuda
+            dirs = c.dirs.detach().reshape(-1, 3).contiguous()
+            vps = c.vps.detach().to(dt).expand(cnt, 3).contiguous()
+            depth = c.depth.detach().reshape(-1).contiguous()
+            inc = None if c.inc_angles is None else c.inc_angles.detach().reshape(-1).to(dt).contiguous()
+            mm = None if c.mask is None else c.mask.detach().to(torch.uint8).contiguous()
+            keep += [dirs, vps, depth, inc, mm]
+            L.call('dc_pack_records', L.ptr(vps), L.ptr(dirs), L.ptr(depth), L.ptr(inc), L.ptr(mm), None, self.code,
+                   first, cnt, s, L.ptr(smap.inv_order), L.ptr(self.rec_dir), L.ptr(self.rec_vp), L.ptr(self.rec_meta), st)
+            first += cnt
+        torch.cuda.current_stream().synchronize()   # `keep` temporaries may be freed after this point
+        self.has_inc = all(c.inc_angles is not None for c in clouds)
+        self.P = torch.empty((n, 4), dtype=torch.float64, device=dev)
+        self.stash = torch.empty((n, 8), dtype=torch.float64, device=dev)
+        self.loss_pp = torch.empty(n, dtype=torch.float64, device=dev)
+        self.n_blocks = ((n + 31) // 32 * 32 + 127) // 128
+        self.partials = torch.zeros(2 * self.n_blocks + 2, dtype=torch.float64, device=dev)
+        self._mask_key = None
+        self.generation = 0
+
+    def set_loss_mask(self, mask):
+        """mask: bool [N] in original (concatenated) order or None (= all points)."""
+        key = None if mask is None else (mask.data_ptr(), mask._version, tuple(mask.shape))
+        if key == self._mask_key:
+            return
+        m8 = None
+        if mask is not None:
+            assert mask.numel() == self.n
+            m8 = mask.detach().to(device=self.device).to(torch.uint8).contiguous()
+        L.call('dc_set_loss_mask', L.ptr(m8), self.n, L.ptr(self.graph.map.order), L.ptr(self.rec_meta), L.stream())
+        self._mask_key = key
+        self._mask_keepalive = m8
+
+
+class _FusedStep(torch.autograd.Function):
+    """Output: raw=False -> tensor [2] = (loss_sum, count); raw=True -> per-point raw loss in sorted space."""
+
+    @staticmethod
+    def forward(ctx, w, exponent, poses, state, model_kind, loss_kind, flags):
+        dev = state.device
+        st = L.stream()
+        S = state.n_scans
+        assert poses.shape[-2:] == (4, 4) and poses.shape[0] == S, 'poses must be [%i,4,4]' % S
+        poses12 = poses.detach()[:, :3, :].to(device=dev, dtype=torch.float64).reshape(S, 12).contiguous()
+        n_terms = 0
+        wv = ev = None
+        if model_kind != L.MODEL_NONE:
+            assert state.has_inc, 'model correction needs per-scan inc_angles (model.py:251)'
+            wv = w.detach().to(device=dev, dtype=torch.float64).reshape(-1).contiguous()
+            ev = exponent.detach().to(device=dev, dtype=torch.float64).reshape(-1).contiguous()
+            n_terms = wv.numel()
+            assert 1 <= n_terms <= L.MAX_TERMS and ev.numel() == n_terms
+        g = state.graph
+        L.call('dc_step_points', L.ptr(state.rec_dir), L.ptr(state.rec_vp), L.ptr(state.rec_meta), state.code, state.n,
+               L.ptr(poses12), S, model_kind, L.ptr(wv), L.ptr(ev), n_terms, L.ptr(state.P), st)
+        raw = bool(flags & L.FLAG_RAW)
+        loss_sum = None if raw else torch.empty(2, dtype=torch.float64, device=dev)
+        L.call('dc_step_forward', L.ptr(state.P), L.ptr(state.rec_meta), state.n, L.ptr(g.slice_ptr), L.ptr(g.ell_idx),
+               loss_kind, flags, L.ptr(state.loss_pp), L.ptr(state.stash), None, L.ptr(loss_sum),
+               L.ptr(state.partials), state.partials.numel() * 8, st)
+        state.generation += 1
+        ctx.state, ctx.generation = state, state.generation
+        ctx.args = (poses12, wv, ev, n_terms, model_kind, raw)
+        ctx.shapes = (w.shape if w is not None else None, exponent.shape if exponent is not None else None,
+                      poses.shape, poses.dtype, poses.device)
+        ctx.exp_grad = exponent is not None and isinstance(exponent, torch.Tensor) and exponent.requires_grad
+        if raw:
+            return state.loss_pp.clone()
+        return loss_sum
+
+    @staticmethod
+    def backward(ctx, *grads):
+        state = ctx.state
+        if state.generation != ctx.generation:
+            raise RuntimeError('fused step: backward() after a newer forward() on the same cloud; '
+                               'the backward stash has been overwritten (call backward before the next forward)')
+        poses12, wv, ev, n_terms, model_kind, raw = ctx.args
+        dev = state.device
+        st = L.stream()
+        S = state.n_scans
+        gt = state.graph.transposed()
+        dw = torch.zeros(max(n_terms, 1), dtype=torch.float64, device=dev)
+        dexp = torch.zeros(max(n_terms, 1), dtype=torch.float64, device=dev) if ctx.exp_grad else None
+        dposes = torch.zeros((S, 12), dtype=torch.float64, device=dev)
+        upstream = None
+        if raw:
+            upstream = grads[0].to(torch.float64).contiguous()
+        L.call('dc_step_backward', L.ptr(state.P), L.ptr(state.rec_dir), L.ptr(state.rec_vp), L.ptr(state.rec_meta),
+               state.code, state.n, L.ptr(gt.slice_ptr), L.ptr(gt.ell_idx), L.ptr(state.stash), L.ptr(upstream),
+               L.ptr(poses12), S, model_kind, L.ptr(wv), L.ptr(ev), n_terms, L.ptr(dw), L.ptr(dexp), L.ptr(dposes), st)
+        scale = None if raw else grads[0][0]
+        w_shape, e_shape, p_shape, p_dtype, p_dev = ctx.shapes
+        gw = ge = None
+        if model_kind != L.MODEL_NONE and ctx.needs_input_grad[0]:
+            gw = (dw[:n_terms] if scale is None else dw[:n_terms] * scale).reshape(w_shape)
+        if dexp is not None and ctx.needs_input_grad[1]:
+            ge = (dexp[:n_terms] if scale is None else dexp[:n_terms] * scale).reshape(e_shape)
+        gp = None
+        if ctx.needs_input_grad[2]:
+            gp = torch.zeros(p_shape, dtype=torch.float64, device=dev)
+            gp[:, :3, :] = (dposes if scale is None else dposes * scale).reshape(S, 3, 4)
+            gp = gp.to(device=p_dev, dtype=p_dtype)
+        return gw, ge, gp, None, None, None, None
+
+
+def fused_loss(state, model, poses, loss_kind, flags, mask=None):
+    """Returns a tensor [2] = (loss_sum, count) (fast path) or the per-point raw loss in ORIGINAL order
+    when `flags & FLAG_RAW` (general path: inlier selection, offsets, custom reductions)."""
+    state.set_loss_mask(mask)
+    kind = model_kind_of(model)
+    w = getattr(model, 'w', None) if kind != L.MODEL_NONE else None
+    e = getattr(model, 'exponent', None) if kind != L.MODEL_NONE else None
+    if isinstance(poses, (list, tuple)):
+        poses = torch.stack(list(poses))
+    out = _FusedStep.apply(w, e, poses, state, kind, loss_kind, flags)
+    if flags & L.FLAG_RAW:
+        return out[state.graph.map.inv_order.long()]
+    return out

@@ -1,0 +1,296 @@
+"""Cell-sorted map and neighbourhood graph (host-side orchestration of kernel 1).
+
+`SortedMap` = the point set sorted by uniform-grid cell (the replacement of the cKDTree index built
+at nearest_neighbors.py:46); `Graph` = a neighbourhood graph in sorted space, sliced-ELL int32
+(see include/dc_b200.h), convertible to/from the reference layout (int64 [N,K], -1 padded,
+nearest_neighbors.py:69-78).  All heavy work is done by libdcb200.so; torch is used for device
+memory and tiny glue (permutation inverse, scalar read-backs at setup time).
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib as L
+
+__all__ = ['SortedMap', 'Graph', 'search']
+
+DENSE_TABLE_MAX_CELLS = 1 << 27
+
+
+def _as_points(x):
+    assert isinstance(x, torch.Tensor)
+    x = x.detach().reshape(-1, x.shape[-1])
+    assert x.shape[-1] == 3, 'the B200 neighbour search is specialised for 3-D points'
+    return x.contiguous()
+
+
+class SortedMap(object):
+    """Points sorted by grid cell: P (fp64 32-byte records), keys, order / inv_order, optional dense cell table."""
+
+    def __init__(self, points, cell, also_cover=None):
+        points = _as_points(points)
+        dev = points.device
+        self.device = dev
+        self.n = points.shape[0]
+        self.dtype = points.dtype
+        code = L.dtype_code(points.dtype)
+        n = self.n
+        st = L.stream()
+
+        bounds = torch.empty(6, dtype=torch.float64, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.call('dc_bounds', L.ptr(points), code, n, L.ptr(bounds), L.ptr(bad), st)
+        b = bounds.cpu()
+        if int(bad.item()) > 0:
+            raise ValueError('points must be finite (cKDTree raises as well)')
+        if also_cover is not None and also_cover.shape[0] > 0:
+            q = _as_points(also_cover)
+            qb = torch.empty(6, dtype=torch.float64, device=dev)
+            L.call('dc_bounds', L.ptr(q), L.dtype_code(q.dtype), q.shape[0], L.ptr(qb), L.ptr(bad), st)
+            qb = qb.cpu()
+            b = torch.cat([torch.minimum(b[:3], qb[:3]), torch.maximum(b[3:], qb[3:])])
+        if n == 0:
+            b = torch.zeros(6, dtype=torch.float64)
+        lo, hi = b[:3].tolist(), b[3:].tolist()
+        self.spec = L.GridSpec()
+        self.cell = float(cell)
+        self.spec.cell = self.cell
+        ext = []
+        for a in range(3):
+            self.spec.origin[a] = lo[a] - 1e-3 * self.cell
+            self.spec.dims[a] = int(math.floor((hi[a] - self.spec.origin[a]) / self.cell)) + 1
+            ext.append(hi[a] - lo[a])
+        # fastest key digit = shortest extent, slowest = longest (slabs along the trajectory stay contiguous)
+        axes = sorted(range(3), key=lambda a: (ext[a], a))
+        for i, a in enumerate(axes):
+            self.spec.axis[i] = a
+        self.axes = axes
+        self.n_cells = int(self.spec.dims[0]) * int(self.spec.dims[1]) * int(self.spec.dims[2])
+        if self.n_cells >= (1 << 62):
+            raise OverflowError('search grid has too many cells; increase the cell size')
+        self.key_bits = max(1, int(self.n_cells - 1).bit_length())
+
+        keys = torch.empty(n, dtype=torch.int64, device=dev)     # uint64 bit patterns (< 2^62)
+        ids = torch.empty(n, dtype=torch.int32, device=dev)
+        self.keys = torch.empty(n, dtype=torch.int64, device=dev)
+        self.order = torch.empty(n, dtype=torch.int32, device=dev)
+        self.P = torch.empty((n, 4), dtype=torch.float64, device=dev)
+        if n > 0:
+            L.call('dc_cell_keys', L.ptr(points), code, n, ctypes.byref(self.spec), L.ptr(keys), L.ptr(ids), st)
+            L.call_with_temp('dc_sort_pairs', dev, L.ptr(keys), L.ptr(self.keys), L.ptr(ids), L.ptr(self.order), n,
+                             self.key_bits, after=(st,))
+            L.call('dc_gather_points', L.ptr(points), code, L.ptr(self.order), n, L.ptr(self.P), st)
+        self.inv_order = torch.empty(n, dtype=torch.int32, device=dev)
+        self.inv_order[self.order.long()] = torch.arange(n, dtype=torch.int32, device=dev)
+        self.cell_start = None
+        if 0 < self.n_cells <= DENSE_TABLE_MAX_CELLS and n > 0:
+            self.cell_start = torch.empty(self.n_cells + 1, dtype=torch.int32, device=dev)
+            L.call('dc_cell_table', L.ptr(self.keys), n, self.n_cells, L.ptr(self.cell_start), st)
+
+    def sort_queries(self, query):
+        """Sort a query set by the same grid -> (Q records, qkeys, q_order)."""
+        query = _as_points(query)
+        nq = query.shape[0]
+        dev = self.device
+        st = L.stream()
+        code = L.dtype_code(query.dtype)
+        keys = torch.empty(nq, dtype=torch.int64, device=dev)
+        ids = torch.empty(nq, dtype=torch.int32, device=dev)
+        qkeys = torch.empty(nq, dtype=torch.int64, device=dev)
+        qorder = torch.empty(nq, dtype=torch.int32, device=dev)
+        Q = torch.empty((nq, 4), dtype=torch.float64, device=dev)
+        if nq > 0:
+            L.call('dc_cell_keys', L.ptr(query), code, nq, ctypes.byref(self.spec), L.ptr(keys), L.ptr(ids), st)
+            L.call_with_temp('dc_sort_pairs', dev, L.ptr(keys), L.ptr(qkeys), L.ptr(ids), L.ptr(qorder), nq,
+                             self.key_bits, after=(st,))
+            L.call('dc_gather_points', L.ptr(query), code, L.ptr(qorder), nq, L.ptr(Q), st)
+        return Q, qkeys, qorder
+
+    def occupancy(self):
+        """Mean number of points per occupied cell."""
+        if self.n == 0:
+            return 0.0
+        n_occ = int((self.keys[1:] != self.keys[:-1]).sum().item()) + 1
+        return self.n / n_occ
+
+
+def _n_slices(n):
+    return (n + L.SLICE - 1) // L.SLICE
+
+
+class Graph(object):
+    """Neighbourhood graph in sorted space (sliced-ELL) over a SortedMap.
+
+    rows = queries (sorted by the map's grid), columns = map points.  `symmetric` graphs (self-query
+    radius graphs) are their own transpose; otherwise `transposed()` builds the reverse lists the
+    backward kernel gathers over.
+    """
+
+    def __init__(self, smap, slice_ptr, ell_idx, n_rows, width, q_order=None, ell_d2=None, mode='radius',
+                 symmetric=False, k=None, r=None):
+        self.map = smap
+        self.slice_ptr = slice_ptr
+        self.ell_idx = ell_idx
+        self.n_rows = n_rows
+        self.width = width            # K of the reference layout (max row length / k)
+        self.q_order = q_order if q_order is not None else smap.order
+        self.self_query = q_order is None
+        self.ell_d2 = ell_d2
+        self.mode = mode
+        self.symmetric = symmetric
+        self.k, self.r = k, r
+        self._transposed = None
+        self._step_cache = {}
+
+    # ---- reference layout views ---------------------------------------------------------------
+    def neighbors(self):
+        """int64 [n_rows, K] in original order, -1 = missing (what nearest_neighbors() returns)."""
+        dev = self.map.device
+        K = self.width
+        out = torch.empty((self.n_rows, K), dtype=torch.int64, device=dev)
+        st = L.stream()
+        if self.n_rows > 0 and K > 0:
+            L.call('dc_ell_to_padded', L.ptr(self.slice_ptr), L.ptr(self.ell_idx), self.n_rows, L.ptr(self.map.order),
+                   L.ptr(self.q_order), K, L.ptr(out), st)
+            if self.mode == 'radius':
+                # query_ball_point on many points returns index-sorted rows
+                L.call_with_temp('dc_sort_rows', dev, L.ptr(out), self.n_rows, K, after=(st,))
+        return out
+
+    def distances(self):
+        """fp64 [n_rows, k] (inf = missing) for kNN graphs, None for radius graphs (nearest_neighbors.py:51)."""
+        if self.ell_d2 is None:
+            return None
+        out = torch.empty((self.n_rows, self.width), dtype=torch.float64, device=self.map.device)
+        if self.n_rows > 0:
+            L.call('dc_ell_to_dist', self.width, L.ptr(self.ell_d2), L.ptr(self.ell_idx), self.n_rows,
+                   L.ptr(self.q_order), L.ptr(out), L.stream())
+        return out
+
+    def degrees(self):
+        """Valid neighbours per row, sorted space, int32."""
+        deg = torch.empty(self.n_rows, dtype=torch.int32, device=self.map.device)
+        if self.n_rows > 0:
+            L.call('dc_graph_degrees', L.ptr(self.slice_ptr), L.ptr(self.ell_idx), self.n_rows, L.ptr(deg), L.stream())
+        return deg
+
+    def valid_counts(self):
+        """Valid neighbours per row in ORIGINAL order (filter_valid_neighbors, filters.py:184-193)."""
+        out = torch.empty(self.n_rows, dtype=torch.int64, device=self.map.device)
+        out[self.q_order.long()] = self.degrees().long()
+        return out
+
+    # ---- transpose ----------------------------------------------------------------------------
+    def transposed(self):
+        if self.symmetric:
+            return self
+        if self._transposed is not None:
+            return self._transposed
+        assert self.self_query, 'transpose is only defined for self-query graphs'
+        dev = self.map.device
+        st = L.stream()
+        n = self.n_rows
+        deg = self.degrees()
+        offs = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        L.call_with_temp('dc_exclusive_sum_i32_i64', dev, L.ptr(deg), L.ptr(offs), n, after=(st,))
+        n_edges = int(offs[-1].item())
+        pairs = torch.empty(max(n_edges, 1), dtype=torch.int64, device=dev)
+        pairs_sorted = torch.empty(max(n_edges, 1), dtype=torch.int64, device=dev)
+        L.call('dc_graph_edges', L.ptr(self.slice_ptr), L.ptr(self.ell_idx), n, L.ptr(offs), L.ptr(pairs), st)
+        bits = 32 + max(1, int(max(n - 1, 1)).bit_length())
+        if n_edges > 0:
+            L.call_with_temp('dc_sort_keys', dev, L.ptr(pairs), L.ptr(pairs_sorted), n_edges, bits, after=(st,))
+        del pairs
+        indeg = torch.empty(n, dtype=torch.int32, device=dev)
+        sw = torch.zeros(_n_slices(n), dtype=torch.int32, device=dev)
+        L.call('dc_transpose_widths', L.ptr(pairs_sorted), n_edges, n, L.ptr(indeg), L.ptr(sw), st)
+        sp = torch.empty(_n_slices(n) + 1, dtype=torch.int64, device=dev)
+        L.call_with_temp('dc_ell_offsets', dev, L.ptr(sw), _n_slices(n), L.ptr(sp), after=(st,))
+        total = int(sp[-1].item())
+        idx_t = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        L.call('dc_transpose_fill', L.ptr(pairs_sorted), n_edges, n, L.ptr(sp), L.ptr(idx_t), st)
+        width = int(indeg.max().item()) if n > 0 else 0
+        self._transposed = Graph(self.map, sp, idx_t, n, width, mode='transposed', symmetric=False)
+        self._transposed._transposed = self
+        return self._transposed
+
+    # ---- import -------------------------------------------------------------------------------
+    @staticmethod
+    def from_padded(smap, neighbors):
+        """Build the sorted-space graph from a reference-layout int64 [N,K] tensor (self-query)."""
+        assert neighbors.dim() == 2 and neighbors.shape[0] == smap.n
+        neighbors = neighbors.contiguous().to(torch.int64)
+        n, K = neighbors.shape
+        dev = smap.device
+        st = L.stream()
+        sw = torch.zeros(_n_slices(n), dtype=torch.int32, device=dev)
+        L.call('dc_padded_to_ell', L.ptr(neighbors), n, K, L.ptr(smap.order), L.ptr(smap.inv_order), L.ptr(sw), None, None, st)
+        sp = torch.empty(_n_slices(n) + 1, dtype=torch.int64, device=dev)
+        L.call_with_temp('dc_ell_offsets', dev, L.ptr(sw), _n_slices(n), L.ptr(sp), after=(st,))
+        total = int(sp[-1].item())
+        idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        L.call('dc_padded_to_ell', L.ptr(neighbors), n, K, L.ptr(smap.order), L.ptr(smap.inv_order), None, L.ptr(sp), L.ptr(idx), st)
+        return Graph(smap, sp, idx, n, K, mode='imported', symmetric=False)
+
+
+def _knn_cell_size(points, k, r):
+    """Cell edge for kNN search: aim at ~k/4 points per occupied cell (surface-like data puts ~9
+    occupied cells in a 3x3x3 block), estimated from one coarse sort."""
+    n = points.shape[0]
+    if r:
+        c0 = float(r)
+    else:
+        ext = (points.max(dim=0).values - points.min(dim=0).values).double()
+        c0 = max(float(ext.max().item()) / 256.0, 1e-9)
+    for _ in range(3):
+        occ = SortedMap(points, c0).occupancy()
+        target = max(k / 4.0, 2.0)
+        if occ <= 2.0 * target:
+            break
+        c0 = c0 * max(math.sqrt(target / occ), 1.0 / 8.0)
+    return c0
+
+
+def search(points, query=None, k=None, r=None, cell=None):
+    """Neighbour search -> Graph.  Modes follow nearest_neighbors.py:47-53:
+    k (and optionally r as a strict upper bound) -> kNN graph; r only -> radius graph (<= r)."""
+    assert k or r
+    points = _as_points(points)
+    n = points.shape[0]
+    dev = points.device
+    self_query = query is None or query is points
+    if cell is None:
+        if k:
+            cell = _knn_cell_size(points, int(k), r) if n > 0 else 1.0
+        else:
+            cell = float(r) * (1.0 + 1e-6)   # a hair above r: one ring of cells is always enough
+    smap = SortedMap(points, cell, also_cover=None if self_query else query)
+    st = L.stream()
+    if self_query:
+        Q, qkeys, qorder, nq = smap.P, smap.keys, None, n
+    else:
+        Q, qkeys, qorder = smap.sort_queries(query)
+        nq = Q.shape[0]
+    ns = _n_slices(nq)
+    spec = ctypes.byref(smap.spec)
+    if k:
+        k = int(k)
+        sp = torch.arange(ns + 1, dtype=torch.int64, device=dev) * (L.SLICE * k)
+        idx = torch.empty(max(ns * L.SLICE * k, 1), dtype=torch.int32, device=dev)
+        d2 = torch.empty(max(ns * L.SLICE * k, 1), dtype=torch.float64, device=dev)
+        L.call('dc_knn', L.ptr(smap.P), L.ptr(smap.keys), n, L.ptr(Q), L.ptr(qkeys), nq, spec, L.ptr(smap.cell_start),
+               k, float(r) if r else 0.0, L.ptr(idx), L.ptr(d2), st)
+        return Graph(smap, sp, idx, nq, k, q_order=qorder, ell_d2=d2, mode='knn', symmetric=False, k=k, r=r)
+    counts = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
+    sw = torch.zeros(max(ns, 1), dtype=torch.int32, device=dev)
+    L.call('dc_radius_count', L.ptr(smap.P), L.ptr(smap.keys), n, L.ptr(Q), L.ptr(qkeys), nq, spec,
+           L.ptr(smap.cell_start), float(r), L.ptr(counts), L.ptr(sw), st)
+    sp = torch.empty(ns + 1, dtype=torch.int64, device=dev)
+    L.call_with_temp('dc_ell_offsets', dev, L.ptr(sw), ns, L.ptr(sp), after=(st,))
+    total = int(sp[-1].item())
+    width = int(counts[:nq].max().item()) if nq > 0 else 0
+    idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    L.call('dc_radius_fill', L.ptr(smap.P), L.ptr(smap.keys), n, L.ptr(Q), L.ptr(qkeys), nq, spec,
+           L.ptr(smap.cell_start), float(r), L.ptr(sp), L.ptr(idx), st)
+    return Graph(smap, sp, idx, nq, width, q_order=qorder, mode='radius', symmetric=self_query, k=None, r=r)

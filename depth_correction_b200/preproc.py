@@ -1,0 +1,291 @@
+"""Pipeline glue of the hot path (preproc.py:25-243 of the reference, ball neighbourhoods only).
+
+`global_cloud` returns a *lazy* GlobalCloud: it remembers the per-scan clouds, the model and the
+poses instead of eagerly running model -> transform -> concatenate (preproc.py:80-119).  When such
+a cloud reaches `min_eigval_loss` / `trace_loss` with a fixed neighbourhood graph attached by
+`compute_neighborhood_features`, the whole chain runs in the fused sm_100a kernels (fused.py);
+any attribute the reference would have computed (vps, dirs, depth, points, mean, cov, eigvals, ...)
+is still available and is materialised on first access through the staged kernels.
+Plane neighbourhoods (RANSAC planes, preproc.py:218-243) are out of scope.
+"""
+import numpy as np
+import torch
+
+from .config import NeighborhoodType
+from .depth_cloud import DepthCloud
+from .filters import filter_depth, filter_eigenvalue_ratios, filter_eigenvalues, filter_valid_neighbors, within_bounds
+from .fused import StepState, model_kind_of
+from .graph import Graph, SortedMap, search
+from .transform import xyz_axis_angle_to_matrix
+
+__all__ = [
+    'compute_neighborhood_features',
+    'establish_neighborhoods',
+    'filtered_cloud',
+    'global_cloud',
+    'global_cloud_mask',
+    'GlobalCloud',
+    'local_feature_cloud',
+    'Neighborhoods',
+    'offset_cloud',
+]
+
+_FEATURE_FIELDS = ('points', 'mean', 'cov', 'eigvals', 'eigvecs', 'normals', 'inc_angles', 'trace')
+_SOURCE_FIELDS = ('vps', 'dirs', 'depth', 'mask')
+
+
+class Neighborhoods(object):
+    """(neighbors, weights) pair as returned by establish_neighborhoods (preproc.py:185), backed by the
+    sorted-space graph.  Unpacks like the reference's tuple; the padded tensors are built on demand."""
+
+    def __init__(self, graph):
+        self.graph = graph
+        self._pair = None
+
+    def _materialize(self):
+        if self._pair is None:
+            nb = self.graph.neighbors()
+            nb._dc_graph = self.graph
+            w = (nb >= 0).float()[..., None]
+            w._dc_is_mask = True
+            self._pair = (nb, w)
+        return self._pair
+
+    def __iter__(self):
+        return iter(self._materialize())
+
+    def __getitem__(self, i):
+        return self._materialize()[i]
+
+    def __len__(self):
+        return 2
+
+
+class GlobalCloud(DepthCloud):
+    """Lazy global cloud = concatenation of model-corrected, pose-transformed scans."""
+
+    def __init__(self, clouds, model, poses):
+        # deliberately no DepthCloud.__init__: source and feature fields appear on first access
+        self._scans = list(clouds)
+        self._model = model
+        self._poses = poses
+        self._graph = None
+        self._neighbors = None
+        self._weights = None
+        self._distances = None
+        self._distances_stale = False
+        self._features_pending = False
+        self._scale = None
+        self.neighbor_points = None
+        self.dir_neighbors = self.dir_neighbor_weights = self.dir_distances = None
+        self.loss = None
+
+    def __getattr__(self, name):
+        # only reached when `name` is not in __dict__
+        if name in _SOURCE_FIELDS:
+            self._materialize_sources()
+            return self.__dict__[name]
+        if name in _FEATURE_FIELDS:
+            if '_scans' not in self.__dict__:
+                raise AttributeError(name)
+            self._materialize_features()
+            return self.__dict__.get(name)
+        raise AttributeError(name)
+
+    def size(self):
+        return sum(len(c) for c in self._scans)
+
+    def device(self):
+        return self._scans[0].depth.device
+
+    def poses_tensor(self):
+        p = self._poses
+        if isinstance(p, (list, tuple)):
+            p = torch.stack(list(p))
+        return p
+
+    def _materialize_sources(self):
+        """Reference semantics, staged: model(cloud).transform(pose), concatenated (preproc.py:108-119)."""
+        poses = self.poses_tensor()
+        parts = []
+        for i, cloud in enumerate(self._scans):
+            if self._model is not None:
+                cloud = self._model(cloud)
+            parts.append(cloud.transform(poses[i]))
+        dc = DepthCloud.concatenate(parts, dependent=True)
+        for f in ('vps', 'dirs', 'depth', 'mask', 'normals'):
+            if f not in self.__dict__:
+                self.__dict__[f] = getattr(dc, f)
+
+    def _materialize_features(self):
+        for f in _FEATURE_FIELDS:
+            self.__dict__.setdefault(f, None)
+        if self._graph is None and self._neighbors is None:
+            self.update_points()
+            return
+        self._features_pending = False
+        DepthCloud.update_all(self, scale=self._scale, keep_neighbors=True)
+
+    def copy(self):
+        dc = GlobalCloud(self._scans, self._model, self._poses)
+        dc.__dict__.update(self.__dict__)
+        return dc
+
+    # ---- fused path ---------------------------------------------------------------------------
+    def fusable(self):
+        if self._graph is None or self._scale is not None or self._kernel_weights() is not None:
+            return False
+        if not self._scans or not self._scans[0].depth.is_cuda:
+            return False
+        if self._graph.map.n != self.size() or not self._graph.self_query:
+            return False
+        try:
+            model_kind_of(self._model)
+        except NotImplementedError:
+            return False
+        # source fields overridden by the caller would not be seen by the packed records
+        return not any(f in self.__dict__ for f in ('vps', 'dirs', 'depth'))
+
+    def step_state(self):
+        key = tuple((id(c), c.depth.data_ptr(), c.dirs.data_ptr(),
+                     None if c.inc_angles is None else c.inc_angles.data_ptr(),
+                     None if c.mask is None else (c.mask.data_ptr(), c.mask._version)) for c in self._scans)
+        cache = self._graph._step_cache
+        if key not in cache:
+            cache.clear()
+            cache[key] = StepState(self._graph, self._scans)
+        return cache[key]
+
+
+def filtered_cloud(cloud, cfg):
+    """Depth filter of preproc.py:25-32.  The voxel-grid filter (`filter_grid`, a Python dict over all
+    points in the reference) belongs to the per-scan preprocessing row of SURVEY.md section 8(f)."""
+    if ((cfg.min_depth is not None and cfg.min_depth > 0.0)
+            or (cfg.max_depth is not None and cfg.max_depth < float('inf'))):
+        cloud = filter_depth(cloud, min=cfg.min_depth, max=cfg.max_depth, log=cfg.log_filters)
+    if getattr(cfg, 'grid_res', 0.0) and cfg.grid_res > 0.0:
+        from .filters_grid import filter_grid
+        cloud = filter_grid(cloud, grid_res=cfg.grid_res, keep='first')
+    return cloud
+
+
+def local_feature_cloud(cloud, cfg):
+    """Per-scan features: neighbours + mean/cov/eig/normals/incidence angles + planarity mask (preproc.py:35-64)."""
+    if isinstance(cloud, np.ndarray):
+        if cloud.dtype.names:
+            cloud = DepthCloud.from_structured_array(cloud, dtype=cfg.numpy_float_type(), device=cfg.device)
+        else:
+            cloud = DepthCloud.from_points(cloud, dtype=cfg.numpy_float_type(), device=cfg.device)
+    assert isinstance(cloud, DepthCloud)
+    if getattr(cfg, 'shadow_angle_bounds', None):
+        raise NotImplementedError('shadow-point filter: SURVEY.md section 8(f) row 1 (not built yet)')
+    cloud.update_all(k=cfg.nn_k, r=cfg.nn_r)
+    if cfg.eigenvalue_bounds:
+        if cloud.mask is None:
+            cloud.mask = torch.ones((len(cloud),), dtype=torch.bool, device=cloud.device())
+        cloud.mask = cloud.mask & filter_eigenvalues(cloud, cfg.eigenvalue_bounds, only_mask=True, log=cfg.log_filters)
+    if cfg.eigenvalue_ratio_bounds:
+        if cloud.mask is None:
+            cloud.mask = torch.ones((len(cloud),), dtype=torch.bool, device=cloud.device())
+        cloud.mask = cloud.mask & filter_eigenvalue_ratios(cloud, cfg.eigenvalue_ratio_bounds, only_mask=True,
+                                                           log=cfg.log_filters)
+    return cloud
+
+
+def offset_cloud(clouds, model):
+    corrected = [model(c) if model is not None else c for c in clouds]
+    return DepthCloud.concatenate(corrected, fields=DepthCloud.source_fields + ['eigvals'])
+
+
+def global_cloud(clouds=None, model=None, poses=None, pose_corrections=None, dataset=None):
+    """Global cloud with corrected depth (preproc.py:80-119) -- lazy, see GlobalCloud."""
+    if dataset is not None:
+        assert clouds is None
+        assert poses is None
+        clouds, poses = zip(*dataset)
+        clouds = [DepthCloud.from_structured_array(c, dtype=np.float32, device='cuda') for c in clouds]
+        poses = torch.as_tensor(np.array(poses), device='cuda')
+    assert clouds is not None
+    assert poses is not None
+    if pose_corrections is not None:
+        if isinstance(poses, (list, tuple)):
+            poses = torch.stack(list(poses))
+        if pose_corrections.shape[-1] == 6:
+            pose_corrections = xyz_axis_angle_to_matrix(pose_corrections)
+        poses = poses @ pose_corrections
+    return GlobalCloud(clouds, model, poses)
+
+
+def global_cloud_mask(cloud, mask, cfg):
+    """Mask of points used by the loss (preproc.py:122-164)."""
+    if mask is None:
+        mask = torch.ones((len(cloud),), dtype=torch.bool, device=cloud.device())
+    if cfg.min_valid_neighbors:
+        mask = mask & filter_valid_neighbors(cloud, min=cfg.min_valid_neighbors, only_mask=True, log=cfg.log_filters)
+    if cfg.eigenvalue_bounds:
+        mask = mask & filter_eigenvalues(cloud, bounds=cfg.eigenvalue_bounds, only_mask=True, log=cfg.log_filters)
+    if cfg.eigenvalue_ratio_bounds:
+        mask = mask & filter_eigenvalue_ratios(cloud, bounds=cfg.eigenvalue_ratio_bounds, only_mask=True, log=cfg.log_filters)
+    if cfg.dir_dispersion_bounds:
+        mask = mask & within_bounds(cloud.dir_dispersion(), bounds=cfg.dir_dispersion_bounds)
+    if cfg.vp_dispersion_bounds:
+        mask = mask & within_bounds(cloud.vp_dispersion(), bounds=cfg.vp_dispersion_bounds)
+    if cfg.vp_dispersion_to_depth2_bounds:
+        mask = mask & within_bounds(cloud.vp_dispersion_to_depth2(), bounds=cfg.vp_dispersion_to_depth2_bounds)
+    return mask
+
+
+def establish_neighborhoods(dataset=None, clouds=None, poses=None, cloud=None, cfg=None):
+    """Neighbourhood graph of the initial global cloud (preproc.py:168-191): kernel 1 on the GPU.
+    Returns a Neighborhoods pair (unpacks to (neighbors int64 [N,K], weights float32 [N,K,1]))."""
+    if cloud is None:
+        cloud = global_cloud(clouds=clouds, poses=poses, dataset=dataset)
+    assert cloud is not None
+    if cfg.nn_type != NeighborhoodType.ball:
+        raise NotImplementedError('plane neighbourhoods (RANSAC) are out of scope of the B200 hot path')
+    pts = cloud.to_points().detach()
+    graph = search(pts, None, k=cfg.nn_k, r=cfg.nn_r)
+    return Neighborhoods(graph)
+
+
+def compute_neighborhood_features(dataset=None, clouds=None, poses=None, model=None, pose_corrections=None, cloud=None,
+                                  neighborhoods=None, cfg=None):
+    """Attach a fixed graph to the (lazy) global cloud (preproc.py:195-217, ball branch).
+
+    The reference runs update_all(keep_neighbors=True) here; we defer it: the losses run the fused
+    kernels, and reading any feature attribute computes them through the staged kernels."""
+    if cfg.nn_type != NeighborhoodType.ball:
+        raise NotImplementedError('plane neighbourhoods (RANSAC) are out of scope of the B200 hot path')
+    if neighborhoods is None:
+        neighborhoods = establish_neighborhoods(dataset=dataset, cloud=cloud, cfg=cfg)
+    if cloud is None:
+        cloud = global_cloud(clouds=clouds, model=model, poses=poses, pose_corrections=pose_corrections, dataset=dataset)
+    assert neighborhoods is not None
+    if isinstance(neighborhoods, Neighborhoods):
+        graph = neighborhoods.graph
+        weights = None
+    else:
+        nb, weights = neighborhoods
+        graph = getattr(nb, '_dc_graph', None)
+        if graph is None:
+            # a graph from elsewhere (e.g. the reference's cKDTree): import it once and remember it on the tensor
+            ref_pts = cloud.to_points().detach()
+            cell = getattr(cfg, 'nn_r', None) or 0.5
+            graph = Graph.from_padded(SortedMap(ref_pts, cell), nb.to(ref_pts.device))
+            nb._dc_graph = graph
+        if weights is not None and getattr(weights, '_dc_is_mask', False):
+            weights = None
+    if isinstance(cloud, GlobalCloud):
+        for f in _FEATURE_FIELDS:
+            cloud.__dict__.pop(f, None)
+        cloud._graph = graph
+        cloud._neighbors = None
+        cloud._weights = weights
+        cloud._scale = cfg.nn_scale
+        cloud._features_pending = True
+        return cloud
+    cloud._graph = graph
+    cloud._neighbors = None
+    cloud._weights = weights
+    cloud.update_all(scale=cfg.nn_scale, keep_neighbors=True)
+    return cloud

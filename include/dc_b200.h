@@ -1,0 +1,207 @@
+/* depth_correction_b200 -- C ABI of the B200 (sm_100a) map-consistency hot path.
+ *
+ * The reference (ctu-vras/depth_correction) is pure Python with no FFI layer; its boundary for this
+ * path is the Python API.  Each entry point below names the reference
+ * call (file:line under /root/reference/src/depth_correction/) whose native work it replaces.
+ * The Python mirror in depth_correction_b200/ binds these symbols with ctypes;
+ * there are no torch types in any signature.
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory unless the name ends in _host; buffers are caller-allocated
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it unless noted
+ *   - return value: 0 = ok, otherwise a DC_ERR_* code; dc_last_error() gives a message (thread-local)
+ *   - functions with (temp, temp_bytes): call with temp == NULL to get the size in *temp_bytes
+ *   - dtype: DC_F32 / DC_F64 storage of caller tensors; all arithmetic is fp64
+ *   - "sorted space": positions after sorting the map by grid cell; `order[s]` = original row of
+ *     sorted position s.  Graphs are sliced-ELL in sorted space: rows are grouped in slices of 32,
+ *     slice t holds width_t = (slice_ptr[t+1]-slice_ptr[t])/32 columns, entry (row, c) lives at
+ *     ell_idx[slice_ptr[row/32] + c*32 + row%32], -1 = no neighbour.
+ */
+#ifndef DC_B200_H
+#define DC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DC_OK 0
+#define DC_ERR_CUDA 1
+#define DC_ERR_ARG 2
+#define DC_ERR_OVERFLOW 3
+
+#define DC_F32 0
+#define DC_F64 1
+
+/* model kinds (model.py:149-286) */
+#define DC_MODEL_NONE 0
+#define DC_MODEL_POLYNOMIAL 1        /* d' = d - sum_k w_k g^e_k            (model.py:194-205) */
+#define DC_MODEL_SCALED_POLYNOMIAL 2 /* d' = d (1 - sum_k w_k g^e_k)        (model.py:250-261) */
+#define DC_MAX_TERMS 8
+
+/* loss kinds (loss.py:216-370) and flags */
+#define DC_LOSS_MIN_EIGVAL 0
+#define DC_LOSS_TRACE 1
+#define DC_FLAG_NORMALIZATION 1 /* lambda0 / clamp(sum lambda, 1e-6)   (loss.py:253-254) */
+#define DC_FLAG_SQRT 2          /* sqrt after relu                     (loss.py:286-287) */
+#define DC_FLAG_RAW 4           /* per-point value before relu/sqrt (general path: inliers, offsets) */
+
+/* per-point flag bits in the packed scan records */
+#define DC_PT_MODEL_MASK 1u /* depth is corrected by the model (DepthCloud.mask of the scan, model.py:254-260) */
+#define DC_PT_LOSS_MASK 2u  /* point contributes a loss term (mask argument of the losses, loss.py:245-248) */
+
+typedef struct dc_grid_spec {
+  double origin[3]; /* min corner, xyz */
+  double cell;      /* cell edge length */
+  int32_t dims[3];  /* cells along x, y, z */
+  int32_t axis[3];  /* axis[0] = fastest varying axis of the cell key ... axis[2] = slowest */
+} dc_grid_spec;
+
+const char* dc_last_error(void);
+int dc_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel 1: neighbour search.  Replaces nearest_neighbors() = scipy cKDTree build + query /
+ * query_ball_point on the host (nearest_neighbors.py:22-80), called from
+ * DepthCloud.update_neighbors (depth_cloud.py:210-215).
+ * ------------------------------------------------------------------------------------------- */
+
+/* min/max over rows of pts[n,3]: out6 = {minx,miny,minz,maxx,maxy,maxz}; bad_count = #non-finite rows */
+int dc_bounds(const void* pts, int dtype, int64_t n, double* out6, int32_t* bad_count, void* stream);
+
+/* cell key of every row (linear index with spec->axis ordering) and ids = 0..n-1 */
+int dc_cell_keys(const void* pts, int dtype, int64_t n, const dc_grid_spec* spec_host, uint64_t* keys, int32_t* ids,
+                 void* stream);
+
+/* stable radix sort of (key, id) pairs on key bits [0, end_bit) */
+int dc_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const int32_t* ids_in, int32_t* ids_out, int64_t n,
+                  int end_bit, void* temp, size_t* temp_bytes, void* stream);
+
+/* sorted[s] = {double(pts[order[s]]), tag = order[s]}   (32-byte records) */
+int dc_gather_points(const void* pts, int dtype, const int32_t* order, int64_t n, void* sorted_points, void* stream);
+
+/* dense table cell_start[c] = first sorted position with key >= c, c in [0, n_cells] (optional accelerator) */
+int dc_cell_table(const uint64_t* keys_sorted, int64_t n, int64_t n_cells, int32_t* cell_start, void* stream);
+
+/* radius mode, pass 1: counts[q] = #{p : |p - q|^2 <= r^2} (fp64, same summation order as cKDTree),
+ * slice_width[t] = max count in slice t.  Queries must be sorted by the same grid (self query: Q == P). */
+int dc_radius_count(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
+                    const dc_grid_spec* spec_host, const int32_t* cell_start, double r, int32_t* counts,
+                    int32_t* slice_width, void* stream);
+
+/* slice_ptr[t] = 32 * exclusive_sum(slice_width)[t], t in [0, n_slices]  (int64) */
+int dc_ell_offsets(const int32_t* slice_width, int64_t n_slices, int64_t* slice_ptr, void* temp, size_t* temp_bytes,
+                   void* stream);
+
+/* radius mode, pass 2: fill ell_idx (sorted-space indices, ascending; -1 padding) */
+int dc_radius_fill(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
+                   const dc_grid_spec* spec_host, const int32_t* cell_start, double r, const int64_t* slice_ptr,
+                   int32_t* ell_idx, void* stream);
+
+/* kNN (r <= 0) or kNN within r (strict <, like cKDTree's distance_upper_bound): fixed-width ELL
+ * (slice_ptr[t] = 32*k*t), entries ordered by (d^2, original index); ell_d2 optional. */
+int dc_knn(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
+           const dc_grid_spec* spec_host, const int32_t* cell_start, int k, double r, int32_t* ell_idx, double* ell_d2,
+           void* stream);
+
+/* export to the reference layout: out[order_q[row], c] = order_p[ell(row, c)] (int64, -1 padding), K columns */
+int dc_ell_to_padded(const int64_t* slice_ptr, const int32_t* ell_idx, int64_t nq,
+                     const int32_t* order_p, const int32_t* order_q, int K, int64_t* out, void* stream);
+/* distances: out[order_q[row], c] = sqrt(d2) (fp64; +inf where missing) */
+int dc_ell_to_dist(int k, const double* ell_d2, const int32_t* ell_idx, int64_t nq, const int32_t* order_q, double* out,
+                   void* stream);
+/* ascending sort of every row of an [n,K] int64 matrix with -1 kept last (radius mode row order) */
+int dc_sort_rows(int64_t* rows, int64_t n, int K, void* temp, size_t* temp_bytes, void* stream);
+
+/* import a reference-layout graph (neighbors int64 [n,K], -1 = missing, original order) into sorted space.
+ * pass 1 (ell_idx == NULL): slice_width; pass 2: fill.  inv_order[orig] = sorted position. */
+int dc_padded_to_ell(const int64_t* neighbors, int64_t n, int K, const int32_t* order, const int32_t* inv_order,
+                     int32_t* slice_width, const int64_t* slice_ptr, int32_t* ell_idx, void* stream);
+
+/* transposed graph (who lists me as a neighbour), needed by the backward pass for asymmetric (kNN) graphs:
+ * step 1 writes one (dst<<32 | src) pair per valid edge and the total; the caller sorts the pairs with
+ * dc_sort_keys; step 2 computes in-degrees and slice widths; step 3 fills the transposed ELL. */
+int dc_graph_edges(const int64_t* slice_ptr, const int32_t* ell_idx, int64_t n_rows,
+                   const int64_t* edge_offset, uint64_t* pairs, void* stream);
+int dc_graph_degrees(const int64_t* slice_ptr, const int32_t* ell_idx, int64_t n_rows,
+                     int32_t* out_degree, void* stream);
+int dc_sort_keys(const uint64_t* keys_in, uint64_t* keys_out, int64_t n, int end_bit, void* temp, size_t* temp_bytes,
+                 void* stream);
+int dc_exclusive_sum_i32_i64(const int32_t* in, int64_t* out, int64_t n, void* temp, size_t* temp_bytes, void* stream);
+int dc_transpose_widths(const uint64_t* pairs_sorted, int64_t n_edges, int64_t n_cols, int32_t* in_degree,
+                        int32_t* slice_width, void* stream);
+int dc_transpose_fill(const uint64_t* pairs_sorted, int64_t n_edges, int64_t n_cols, const int64_t* slice_ptr_t,
+                      int32_t* ell_idx_t, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernels 2/3: fused fixed-graph step.  Replaces, per training iteration,
+ *   model(cloud) + cloud.transform(pose) + DepthCloud.concatenate      (preproc.py:80-119)
+ *   update_points / update_mean / update_cov / update_eig              (depth_cloud.py:122-128,291-399)
+ *   min_eigval_loss / trace_loss + reduce                              (loss.py:125-150,216-370)
+ *   loss.backward() down to model.w, model.exponent and the poses     (train.py:306-312)
+ * Scan records are packed once, in sorted space:
+ *   rec_dir[s]  = {dir.x, dir.y, dir.z, depth}      (float4 / double4)
+ *   rec_vp[s]   = {vp.x, vp.y, vp.z, inc_angle}     (float4 / double4)
+ *   rec_meta[s] = scan_id << 2 | DC_PT_* flags      (uint32)
+ * poses: fp64 [S,12] row-major 3x4 (already corrected, see dc_pose_compose).
+ * ------------------------------------------------------------------------------------------- */
+
+/* pack rows of one scan into sorted space: row i of the scan is global row `first + i` */
+int dc_pack_records(const void* vps, const void* dirs, const void* depth, const void* inc_angles,
+                    const uint8_t* model_mask, const uint8_t* loss_mask, int dtype, int64_t first, int64_t count,
+                    int scan_id, const int32_t* inv_order, void* rec_dir, void* rec_vp, uint32_t* rec_meta,
+                    void* stream);
+/* overwrite the DC_PT_LOSS_MASK bit from a global-order mask (NULL = all true) */
+int dc_set_loss_mask(const uint8_t* loss_mask, int64_t n, const int32_t* order, uint32_t* rec_meta, void* stream);
+
+/* pass A: corrected world points, 32-byte fp64 records in sorted space */
+int dc_step_points(const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta, int dtype, int64_t n,
+                   const double* poses, int n_scans, int model_kind, const double* w, const double* exponent, int n_terms,
+                   void* points_out, void* stream);
+
+/* pass B: neighbourhood mean / covariance / eigen / loss.
+ * outputs (any may be NULL): loss_pp[n] per-point loss (0 where DC_PT_LOSS_MASK is clear, unless RAW),
+ * stash[n,8] = {mean xyz, v0 xyz, alpha, beta} for the backward pass, eigvals[n,3], partial sums ->
+ * loss_sum[0] = sum of per-point losses over the loss mask, loss_sum[1] = number of masked points.
+ * partials: scratch of 2*grid doubles + one uint32 counter (zeroed by the caller once). */
+int dc_step_forward(const void* points, const uint32_t* rec_meta, int64_t n, const int64_t* slice_ptr,
+                    const int32_t* ell_idx, int loss_kind, int flags, double* loss_pp, double* stash, double* eigvals,
+                    double* loss_sum, void* partials, size_t partials_bytes, void* stream);
+
+/* pass C: g_j = sum_{i : j in N(i)} A_i (p_j - m_i) over the TRANSPOSED graph, chained to
+ * dw[n_terms], dexponent[n_terms] (NULL to skip) and dposes[S,12]; outputs are ACCUMULATED (caller zeroes).
+ * upstream_pp: optional per-point upstream gradient in sorted space (NULL = 1 for every row). */
+int dc_step_backward(const void* points, const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta, int dtype,
+                     int64_t n, const int64_t* slice_ptr_t, const int32_t* ell_idx_t,
+                     const double* stash, const double* upstream_pp, const double* poses, int n_scans, int model_kind,
+                     const double* w, const double* exponent, int n_terms, double* dw, double* dexponent,
+                     double* dposes, void* stream);
+
+/* SE(3) correction T_s = P_s * Delta(delta_s): create_corrected_poses (eval.py:68-82) +
+ * xyz_axis_angle_to_matrix (transform.py:68-78).  poses fp64 [S,16]; deltas fp64 [n_deltas,6] with
+ * n_deltas == S or 1 (shared, PoseCorrection.common / .sequence); out fp64 [S,12]. */
+int dc_pose_compose(const double* poses, const double* deltas, int n_scans, int n_deltas, double* out, void* stream);
+int dc_pose_compose_backward(const double* poses, const double* deltas, int n_scans, int n_deltas, const double* dout,
+                             double* ddeltas, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Unfused feature kernels on caller-ordered tensors, behind DepthCloud.update_mean / update_cov /
+ * update_eig / update_normals / update_incidence_angles (depth_cloud.py:291-424) and their autograd.
+ * neighbors int64 [n,K] (-1 = missing), weights float32 [n,K] or NULL (= valid mask).
+ * ------------------------------------------------------------------------------------------- */
+int dc_features(const void* points, int dtype, int64_t n, const int64_t* neighbors, const float* weights, int K,
+                void* mean, void* cov, void* stream);
+int dc_features_backward(const void* points, int dtype, int64_t n, const int64_t* neighbors, const float* weights, int K,
+                         const void* gmean, const void* gcov, void* gpoints, void* stream);
+int dc_eigh3(const void* cov, int dtype, int64_t n, void* eigvals, void* eigvecs, void* stream);
+int dc_eigh3_backward(const void* eigvals, const void* eigvecs, int dtype, int64_t n, const void* geigvals,
+                      const void* geigvecs, void* gcov, void* stream);
+/* normals = -sign(dirs . v0) v0, inc = arccos(|dirs . n|) or arccos(-dirs . n)  (depth_cloud.py:401-424) */
+int dc_normals_angles(const void* dirs, const void* eigvecs, int dtype, int64_t n, int use_normal_sign, void* normals,
+                      void* inc_angles, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DC_B200_H */

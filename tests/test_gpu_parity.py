@@ -1,0 +1,382 @@
+"""GPU parity tests: the sm_100a path (through the C-ABI library) against
+  (a) golden vectors produced by the unmodified reference (tests/golden, float64 clouds), and
+  (b) the CPU oracle on the same float32 values (the storage type of the bench path).
+Tolerance (north_star): neighbour indices bit-exact; loss / eigenvalues / gradients <= 1e-5 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import RTOL, STEP_TAGS, rel_err, rel_err_norm, same_neighbor_sets, step_inputs, well_separated
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dc():
+    import depth_correction_b200 as dc
+    return dc
+
+
+@pytest.fixture(scope='module')
+def dev():
+    return torch.device('cuda:0')
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel 1: neighbour search
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+@pytest.mark.parametrize('key,kw', [('radius_r0.4', dict(r=0.4)), ('radius_r0.15', dict(r=0.15)), ('knn8', dict(k=8)),
+                                    ('knn16_r0.3', dict(k=16, r=0.3)), ('knn32_r0.1', dict(k=32, r=0.1))])
+def test_nn_bit_exact_vs_reference(dc, dev, golden, key, kw, dtype):
+    g = golden('nn')
+    p = torch.as_tensor(g['points'], device=dev).to(dtype)      # float32 values, exact in both dtypes
+    dist, idx = dc.nearest_neighbors(p, p, **kw)
+    assert idx.dtype == torch.int64 and idx.is_cuda
+    assert np.array_equal(idx.cpu().numpy(), g[key]), key
+    if key + '_dist' in g.files:
+        assert dist.dtype == torch.float64
+        assert np.array_equal(dist.cpu().numpy(), g[key + '_dist'])     # sqrt of the same fp64 d2: bit-exact
+    else:
+        assert dist is None
+
+
+def test_nn_cross_query(dc, dev, golden):
+    g = golden('nn')
+    p = torch.as_tensor(g['points'], device=dev)
+    q = torch.as_tensor(g['query'], device=dev)
+    dist, idx = dc.nearest_neighbors(p, q, k=4)
+    assert np.array_equal(idx.cpu().numpy(), g['cross_knn4'])
+    assert np.array_equal(dist.cpu().numpy(), g['cross_knn4_dist'])
+
+
+def test_nn_boundary_and_ties(dc, dev, golden):
+    """d == r is inside a ball and outside a kNN upper bound; exact ties are compared as sets
+    (cKDTree returns them in tree-traversal order, we use (d2, index) order)."""
+    g = golden('nn')
+    lat = torch.as_tensor(g['lattice'], device=dev)
+    _, idx = dc.nearest_neighbors(lat, lat, r=0.5)
+    assert np.array_equal(idx.cpu().numpy(), g['lattice_radius_r0.5'])
+    dist, idx = dc.nearest_neighbors(lat, lat, k=3, r=0.5)
+    assert same_neighbor_sets(idx.cpu().numpy()[:, :2], g['lattice_knn3_r0.5'][:, :2])
+    assert np.array_equal(dist.cpu().numpy(), g['lattice_knn3_r0.5_dist'])
+    assert idx[0].tolist() == [0, 6, -1]
+
+
+def test_nn_edge_cases(dc, dev):
+    one = torch.zeros((1, 3), device=dev)
+    d, i = dc.nearest_neighbors(one, one, r=1.0)
+    assert i.tolist() == [[0]] and d is None
+    d, i = dc.nearest_neighbors(one, one, k=3)
+    assert i.tolist() == [[0, -1, -1]] and d[0, 0].item() == 0.0 and torch.isinf(d[0, 1:]).all()
+    # 33 points: a full slice plus a ragged tail; duplicates of one location
+    p = torch.zeros((33, 3), device=dev)
+    p[:, 0] = torch.arange(33, device=dev) // 3
+    _, i = dc.nearest_neighbors(p, p, r=0.5)
+    assert i.shape == (33, 3) and (i >= 0).all()
+    assert i[4].tolist() == [3, 4, 5]
+    with pytest.raises(AssertionError):
+        dc.nearest_neighbors(p, p)
+
+
+def test_nn_large_random_vs_ckdtree(dc, dev):
+    """Full-size style check against the oracle (cKDTree) on 200k clustered points."""
+    from oracle import oracle
+    rng = np.random.default_rng(7)
+    c = rng.uniform(-20, 20, (400, 3))
+    pts = (c[rng.integers(0, 400, 200000)] + rng.normal(0, 0.3, (200000, 3))).astype(np.float32)
+    p = torch.as_tensor(pts, device=dev)
+    p64 = torch.as_tensor(pts.astype(np.float64))
+    for kw in (dict(r=0.12), dict(k=16, r=0.25), dict(k=8)):
+        dist, idx = dc.nearest_neighbors(p, p, **kw)
+        d_ref, i_ref = oracle.nearest_neighbors(p64, k=kw.get('k'), r=kw.get('r'))
+        assert torch.equal(idx.cpu(), i_ref), kw
+        if d_ref is not None:
+            assert torch.equal(dist.cpu(), d_ref)
+
+
+def test_graph_roundtrip_and_transpose(dc, dev, golden):
+    from depth_correction_b200.graph import Graph, SortedMap, search
+    g = golden('nn')
+    p = torch.as_tensor(g['points'], device=dev)
+    nb = torch.as_tensor(g['knn16_r0.3'], device=dev)
+    gr = Graph.from_padded(SortedMap(p, 0.3), nb)
+    back = gr.neighbors()
+    assert torch.equal(back, nb)            # valid entries keep their order, padding stays last
+    t = gr.transposed().neighbors().cpu().numpy()
+    ref = [[] for _ in range(len(nb))]
+    for i, row in enumerate(g['knn16_r0.3']):
+        for j in row:
+            if j >= 0:
+                ref[j].append(i)
+    for j in range(len(nb)):
+        assert sorted(x for x in t[j] if x >= 0) == ref[j]
+    sym = search(p, None, r=0.15)
+    assert sym.symmetric and sym.transposed() is sym
+    assert torch.equal(sym.valid_counts().cpu(), torch.as_tensor((g['radius_r0.15'] >= 0).sum(1)))
+
+
+# ------------------------------------------------------------------------------------------------
+# staged DepthCloud API (unfused kernels) against the reference's update_all
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('tag,kw', [('r', dict(r=0.4)), ('kr', dict(k=12, r=0.5))])
+def test_update_all_vs_reference(dc, dev, golden, tag, kw):
+    g = golden('features_' + tag)
+    cloud = dc.DepthCloud.from_points(torch.as_tensor(g['points'].astype(np.float64), device=dev))
+    cloud.update_all(**kw)
+    assert np.array_equal(cloud.neighbors.cpu().numpy(), g['neighbors'])
+    assert str(cloud.weights.dtype) == str(g['weights_dtype']) and list(cloud.weights.shape) == list(g['weights_shape'])
+    if 'distances' in g.files:
+        assert np.array_equal(cloud.distances.cpu().numpy(), g['distances'])
+    scale = np.abs(g['eigvals']).max()
+    assert np.max(np.abs(cloud.mean.cpu().numpy() - g['mean'])) < 1e-12
+    assert np.max(np.abs(cloud.cov.cpu().numpy() - g['cov'])) < 1e-13
+    assert rel_err(cloud.eigvals.cpu().numpy(), g['eigvals'], floor=1e-12 * scale) < 1e-7
+    ok = well_separated(g['eigvals'])
+    V = cloud.eigvecs.cpu().numpy()
+    dots = np.abs(np.einsum('nij,nij->nj', V, g['eigvecs']))
+    assert np.all(np.abs(dots[ok] - 1) < 1e-7)
+    # every decomposition must reconstruct its matrix, also in degenerate rows
+    C = cloud.cov.cpu().numpy()
+    rec = np.einsum('nij,nj,nkj->nik', V, cloud.eigvals.cpu().numpy(), V)
+    assert np.max(np.abs(rec - C)) < 1e-12
+    assert np.max(np.abs(cloud.normals.cpu().numpy()[ok] - g['normals'][ok])) < 1e-7
+    assert np.max(np.abs(cloud.inc_angles.cpu().numpy()[ok] - g['inc_angles'][ok])) < 1e-6
+    ratio = dc.filter_eigenvalue_ratios(cloud, [[0, 1, 0, 0.25], [1, 2, 0.25, 1.0]], only_mask=True).cpu().numpy()
+    assert (ratio != g['mask_ratio']).mean() < 1e-3      # knife-edge rows may flip at 1e-16
+    assert np.array_equal(dc.filter_valid_neighbors(cloud, min=5, only_mask=True).cpu().numpy(), g['mask_valid'])
+    assert np.max(np.abs(cloud.vp_dispersion().cpu().numpy() - g['vp_dispersion'])) < 1e-12
+    assert np.max(np.abs(cloud.dir_dispersion().cpu().numpy() - g['dir_dispersion'])) < 1e-12
+
+
+def test_staged_autograd_matches_torch(dc, dev):
+    """update_cov / update_eig backward kernels vs torch autograd of the same formulas."""
+    from oracle import oracle
+    rng = np.random.default_rng(3)
+    pts = torch.as_tensor(rng.normal(0, 1, (300, 3)) * [1.0, 0.6, 0.05], device=dev, requires_grad=True)
+    _, nb = oracle.nearest_neighbors(pts.detach().cpu(), k=9)
+    nb[::7, -2:] = -1
+    cloud = dc.DepthCloud.from_points(pts.detach())
+    cloud.points = pts
+    cloud.neighbors = nb.to(dev)
+    cloud.update_mean()
+    cloud.update_cov()
+    cloud.update_eig()
+    coef = torch.as_tensor(rng.normal(0, 1, (300, 3)), device=dev)
+    (cloud.eigvals * coef).sum().backward()
+    g_ours = pts.grad.clone()
+    p2 = pts.detach().cpu().clone().requires_grad_(True)
+    f = oracle.neighborhood_features(p2, nb, eigvecs=False)
+    (f['eigvals'] * coef.cpu()).sum().backward()
+    assert rel_err_norm(g_ours.cpu().numpy(), p2.grad.numpy()) < 1e-9
+    # mean + cov + eigenvector adjoint
+    pts.grad = None
+    cloud.update_mean()
+    cloud.update_cov()
+    cloud.update_eig()
+    (cloud.mean.sum() + (cloud.cov ** 2).sum() + (cloud.eigvecs[:, :, 0] ** 2 * coef).sum()).backward()
+    p3 = pts.detach().cpu().clone().requires_grad_(True)
+    f = oracle.neighborhood_features(p3, nb)
+    (f['mean'].sum() + (f['cov'] ** 2).sum() + (f['eigvecs'][:, :, 0] ** 2 * coef.cpu()).sum()).backward()
+    assert rel_err_norm(pts.grad.cpu().numpy(), p3.grad.numpy()) < 1e-7
+
+
+def test_eigh3_degenerate(dc, dev):
+    from depth_correction_b200 import ops
+    mats = torch.zeros((6, 3, 3), dtype=torch.float64, device=dev)
+    mats[1] = torch.eye(3, device=dev) * 2.5                                  # triple
+    mats[2] = torch.diag(torch.tensor([1.0, 1.0, 3.0], device=dev))           # double low
+    mats[3] = torch.diag(torch.tensor([3.0, 1e-30, 3.0], device=dev))         # double high
+    v = torch.tensor([1.0, 2.0, -1.0], dtype=torch.float64, device=dev)
+    mats[4] = torch.outer(v, v)                                               # rank one
+    mats[5] = torch.tensor([[4e-5, 1e-5, 0], [1e-5, 3e-2, 2e-3], [0, 2e-3, 5e-2]], device=dev)
+    lam, V = ops.eigh3(mats)
+    assert torch.isfinite(lam).all() and torch.isfinite(V).all()
+    ref = torch.linalg.eigvalsh(mats.cpu())
+    assert (lam.cpu() - ref).abs().max() < 1e-13 * 6
+    rec = torch.einsum('nij,nj,nkj->nik', V, lam, V)
+    assert (rec - mats).abs().max() < 1e-12
+    eye = torch.einsum('nij,nik->njk', V, V)
+    assert (eye - torch.eye(3, device=dev)).abs().max() < 1e-12
+    bad = torch.full((1, 3, 3), float('nan'), dtype=torch.float64, device=dev)
+    lam, V = ops.eigh3(bad)
+    assert torch.isnan(lam).all()
+
+
+def test_pose_compose_kernel(dc, dev, golden):
+    from depth_correction_b200 import ops
+    from oracle import oracle
+    g = golden('misc')
+    d = torch.as_tensor(g['xyz_axis_angle'], device=dev)
+    S = d.shape[0]
+    eye = torch.eye(4, dtype=torch.float64, device=dev).expand(S, 4, 4).contiguous()
+    assert (ops.pose_compose(eye, d).cpu().numpy() - g['matrices']).__abs__().max() < 1e-15
+    rng = np.random.default_rng(2)
+    P = oracle.xyz_axis_angle_to_matrix(torch.as_tensor(rng.normal(0, 1, (S, 6))))
+    G = torch.as_tensor(rng.normal(0, 1, (S, 4, 4)))
+    for deltas in (torch.as_tensor(g['xyz_axis_angle']), torch.zeros((S, 6), dtype=torch.float64),
+                   torch.as_tensor(g['xyz_axis_angle'][:1])):
+        d_ref = deltas.clone().requires_grad_(True)
+        (oracle.create_corrected_poses(P, d_ref) * G).sum().backward()
+        d_gpu = deltas.clone().to(dev).requires_grad_(True)
+        out = ops.pose_compose(P.to(dev), d_gpu)
+        (out * G.to(dev)).sum().backward()
+        assert (out.detach().cpu() - oracle.create_corrected_poses(P, deltas)).abs().max() < 1e-14
+        assert rel_err_norm(d_gpu.grad.cpu().numpy(), d_ref.grad.numpy()) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+# kernels 2 + 3: the fused training step against the reference's goldens (float64 clouds)
+# ------------------------------------------------------------------------------------------------
+def _build_step(dc, dev, g, dtype, own_search):
+    inp = step_inputs(g)
+    S = len(inp['scans'])
+    clouds = []
+    for sc in inp['scans']:
+        if dtype == torch.float64:
+            c = dc.DepthCloud.from_points(torch.as_tensor(sc['points32'].astype(np.float64), device=dev))
+        else:
+            c = dc.DepthCloud.from_points(torch.as_tensor(sc['points32'], device=dev))
+        c.inc_angles = sc['inc_angles'].to(dev).to(dtype)
+        c.mask = sc['mask'].to(dev)
+        clouds.append(c)
+    k, r = int(g['nn_k']), float(g['nn_r'])
+    cfg = dc.Config(nn_k=k, nn_r=r or None, pose_correction=str(g['pose_correction']))
+    poses = inp['poses'].to(dev)
+    if own_search:
+        ns = dc.establish_neighborhoods(clouds=clouds, poses=poses, cfg=cfg)
+    else:
+        nb = inp['neighbors'].to(dev)
+        ns = (nb, (nb >= 0).float()[..., None])
+        ns[1]._dc_is_mask = True
+    Model = dc.ScaledPolynomial if inp['scaled'] else dc.Polynomial
+    model = Model(w=inp['w'].flatten().tolist(), exponent=inp['exponent'].flatten().tolist(), device=dev)
+    deltas = None
+    if inp['pose_deltas'] is not None:
+        deltas = inp['pose_deltas'].to(dev).requires_grad_(True)
+        poses_c = torch.stack(dc.create_corrected_poses(poses, deltas, cfg))
+    else:
+        poses_c = poses.clone().requires_grad_(True)
+    if deltas is not None:
+        poses_c.retain_grad()
+    cloud = dc.global_cloud(clouds=clouds, model=model, poses=poses_c)
+    feats = dc.compute_neighborhood_features(cloud=cloud, model=None, neighborhoods=ns, cfg=cfg)
+    return inp, clouds, ns, model, deltas, poses_c, feats
+
+
+def _run_loss(dc, inp, feats, dev, **extra):
+    mask = None if inp['loss_mask'] is None else inp['loss_mask'].to(dev)
+    kw = dict(sqrt=inp['sqrt'], reduction=dc.Reduction(inp['reduction']), **extra)
+    if inp['loss'] == 'min_eigval_loss':
+        return dc.min_eigval_loss(feats, mask=mask, normalization=inp['normalization'], **kw)
+    return dc.trace_loss(feats, mask=mask, **kw)
+
+
+@pytest.mark.parametrize('own_search', [True, False])
+@pytest.mark.parametrize('tag', STEP_TAGS)
+def test_fused_step_vs_reference_golden(dc, dev, golden, tag, own_search):
+    g = golden('step_' + tag)
+    inp, clouds, ns, model, deltas, poses_c, feats = _build_step(dc, dev, g, torch.float64, own_search)
+    if own_search:
+        nb = ns[0].cpu().numpy()
+        assert nb.shape == g['neighbors'].shape and np.array_equal(nb, g['neighbors'])
+    assert feats.fusable()
+    loss, loss_cloud = _run_loss(dc, inp, feats, dev)
+    loss.backward()
+    assert rel_err(loss.item(), g['loss']) < 1e-9
+    assert rel_err_norm(loss_cloud.loss.cpu().numpy(), g['per_point']) < 1e-9
+    assert rel_err_norm(model.w.grad.cpu().numpy(), g['w_grad']) < 1e-8
+    assert rel_err_norm(poses_c.grad.cpu().numpy(), g['poses_grad']) < 1e-8
+    if deltas is not None:
+        assert rel_err_norm(deltas.grad.cpu().numpy(), g['pose_deltas_grad']) < 1e-8
+    # lazily materialised features of the same cloud agree with the reference's update_all
+    scale = np.abs(g['eigvals']).max()
+    assert rel_err(feats.eigvals.detach().cpu().numpy(), g['eigvals'], floor=1e-10 * scale) < 1e-6
+    assert np.max(np.abs(feats.points.detach().cpu().numpy() - g['points'])) < 1e-12
+    assert np.max(np.abs(feats.cov.detach().cpu().numpy() - g['cov'])) < 1e-13
+
+
+@pytest.mark.parametrize('tag', STEP_TAGS)
+def test_fused_step_float32_storage_vs_oracle(dc, dev, golden, tag):
+    """The bench configuration: float32 records; the oracle consumes the same float32 values in fp64."""
+    from oracle import oracle
+    g = golden('step_' + tag)
+    inp, clouds, ns, model, deltas, poses_c, feats = _build_step(dc, dev, g, torch.float32, True)
+    scans = [{'vps': c.vps.double().cpu().expand(len(c), 3), 'dirs': c.dirs.double().cpu(), 'depth': c.depth.double().cpu(),
+              'inc_angles': c.inc_angles.double().cpu(), 'mask': c.mask.cpu()} for c in clouds]
+    pts0, _ = oracle.global_points(scans, inp['poses'])
+    _, nb_ref = oracle.nearest_neighbors(pts0, k=int(g['nn_k']) or None, r=float(g['nn_r']) or None)
+    assert torch.equal(ns[0].cpu(), nb_ref)
+    ref = oracle.map_consistency_step(scans, inp['poses'], nb_ref, inp['w'], inp['exponent'], pose_deltas=inp['pose_deltas'],
+                                      loss_mask=inp['loss_mask'], loss=inp['loss'], scaled=inp['scaled'],
+                                      normalization=inp['normalization'], sqrt=inp['sqrt'], reduction=inp['reduction'])
+    loss, loss_cloud = _run_loss(dc, inp, feats, dev)
+    loss.backward()
+    assert rel_err(loss.item(), ref['loss'].item()) < RTOL
+    assert rel_err_norm(loss_cloud.loss.cpu().numpy(), ref['per_point'].numpy()) < RTOL
+    assert rel_err_norm(model.w.grad.cpu().numpy(), ref['w_grad'].numpy()) < RTOL
+    assert rel_err_norm(poses_c.grad.cpu().numpy(), ref['poses_grad'].numpy()) < RTOL
+    if deltas is not None:
+        assert rel_err_norm(deltas.grad.cpu().numpy(), ref['pose_deltas_grad'].numpy()) < RTOL
+
+
+def test_general_path_inliers_and_none_reduction(dc, dev, golden):
+    """inlier_ratio / reduction none go through the per-point kernel output and per-point upstream gradient."""
+    from oracle import oracle
+    g = golden('step_scaled_mineig_norm_r')
+    inp, clouds, ns, model, deltas, poses_c, feats = _build_step(dc, dev, g, torch.float64, False)
+    mask = inp['loss_mask'].to(dev)
+    loss, lc = dc.min_eigval_loss(feats, mask=mask, normalization=True, inlier_ratio=0.8)
+    loss.backward()
+    for sc in inp['scans']:
+        sc.pop('points32')
+    w = inp['w'].clone().requires_grad_(True)
+    d = inp['pose_deltas'].clone().requires_grad_(True)
+    pts, _ = oracle.global_points(inp['scans'], oracle.create_corrected_poses(inp['poses'], d), w, inp['exponent'], True)
+    f = oracle.neighborhood_features(pts, inp['neighbors'], eigvecs=False)
+    ref, _ = oracle.min_eigval_loss(f['eigvals'], inp['loss_mask'], normalization=True, inlier_ratio=0.8)
+    ref.backward()
+    assert rel_err(loss.item(), ref.item()) < 1e-9
+    assert rel_err_norm(model.w.grad.cpu().numpy(), w.grad.numpy()) < 1e-8
+    assert rel_err_norm(deltas.grad.cpu().numpy(), d.grad.numpy()) < 1e-8
+    model.w.grad = None
+    feats2 = dc.compute_neighborhood_features(cloud=dc.global_cloud(clouds=clouds, model=model, poses=poses_c.detach()),
+                                              neighborhoods=ns, cfg=dc.Config(nn_r=0.4))
+    pp, _ = dc.min_eigval_loss(feats2, mask=mask, normalization=True, reduction=dc.Reduction.NONE)
+    assert pp.shape == (int(mask.sum()),)
+    assert rel_err_norm(pp.detach().cpu().numpy(), g['per_point']) < 1e-9
+
+
+def test_batch_of_clouds_and_invariances(dc, dev, golden):
+    g = golden('step_scaled_mineig_norm_r')
+    inp, clouds, ns, model, deltas, poses_c, feats = _build_step(dc, dev, g, torch.float64, False)
+    mask = inp['loss_mask'].to(dev)
+    single, _ = dc.min_eigval_loss(feats, mask=mask, normalization=True)
+    feats_b = dc.compute_neighborhood_features(cloud=dc.global_cloud(clouds=clouds, model=model, poses=poses_c.detach()),
+                                               neighborhoods=ns, cfg=dc.Config(nn_r=0.4))
+    both, lcs = dc.min_eigval_loss([feats, feats_b], mask=[mask, mask], normalization=True)
+    assert len(lcs) == 2 and abs(both.item() - single.item()) < 1e-15
+    # rigid motion of the whole map leaves eigenvalue losses unchanged (graph is fixed)
+    from oracle import oracle
+    M = oracle.xyz_axis_angle_to_matrix(torch.tensor([[3.0, -2.0, 1.0, 0.3, -0.5, 0.2]], dtype=torch.float64))[0].to(dev)
+    moved = dc.compute_neighborhood_features(cloud=dc.global_cloud(clouds=clouds, model=model, poses=M @ poses_c.detach()),
+                                             neighborhoods=ns, cfg=dc.Config(nn_r=0.4))
+    l2, _ = dc.min_eigval_loss(moved, mask=mask, normalization=True)
+    assert abs(l2.item() - single.item()) < 1e-11 * abs(single.item()) + 1e-15
+    # mask all false -> mean over nothing is NaN like torch's mean of an empty tensor
+    none, _ = dc.min_eigval_loss(moved, mask=torch.zeros_like(mask), normalization=True)
+    assert torch.isnan(none)
+
+
+def test_local_feature_cloud_vs_reference(dc, dev, golden):
+    g = golden('step_scaled_mineig_norm_r')
+    cfg = dc.Config(nn_k=0, nn_r=0.4)
+    for i in range(int(g['n_scans'])):
+        c = dc.DepthCloud.from_points(torch.as_tensor(g['scan%d_points' % i].astype(np.float64), device=dev))
+        c = dc.local_feature_cloud(c, cfg)
+        flips = (c.mask.cpu().numpy() != g['scan%d_mask' % i]).mean()
+        assert flips < 2e-3
+        inc = c.inc_angles.cpu().numpy()
+        ok = g['scan%d_mask' % i] & c.mask.cpu().numpy()
+        assert np.max(np.abs(inc[ok] - g['scan%d_inc_angles' % i][ok])) < 1e-6
