@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the map-consistency hot path (BASELINE.json metric: points/s for
+neighbors + cov + eig map-consistency loss fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scans S]
+
+One "step" = one neighbour search over the global cloud (kNN k=32 within r=0.4 m, incl. the transposed
+graph the backward needs and the packing of the scan records) + one fused forward + backward of
+min_eigval_loss(normalization=True) through ScaledPolynomial(w=[0,0], exponent=[2,4]) and per-scan SE(3)
+pose corrections, on a synthetic corridor of full-resolution OS0-128 scans (BASELINE.json configs[1]).
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the byte accounting.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from depth_correction_b200.synthetic import make_sequence   # noqa: E402  (numpy only)
+
+NN_K, NN_R = 32, 0.4
+METRIC = 'points/s (neighbour search + fused map-consistency loss fwd+bwd)'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--scans', type=int, default=64, help='scans per GPU (weak scaling)')
+    ap.add_argument('--pattern', default='os0-128')
+    ap.add_argument('--cpu-scans', type=int, default=6, help='scans in the bounded CPU-baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile', action='store_true', help='small fixed workload for ncu (no baseline, no e2e)')
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        rows = [r for r in self.rows if len(r) == 6 and r[0].isdigit()]
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in rows)]
+        return {'sm_mhz': float(np.median([int(r[0]) for r in rows])), 'sm_max_mhz': float(rows[0][1]), 'reasons': reasons}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def host_scans(n_scans, pattern, first_scan=0):
+    scans, _, poses = make_sequence('corridor', n_scans=n_scans, pattern=pattern, seed=0, first_scan=first_scan)
+    return [s['points'] for s in scans], poses
+
+
+def local_features(dc, pts_dev, cfg):
+    """Per-scan constants of the optimisation: incidence angles and planarity mask (preproc.py:35-64)."""
+    clouds = []
+    for p in pts_dev:
+        c = dc.local_feature_cloud(dc.DepthCloud.from_points(p), cfg)
+        # keep only what the loop reads; drop the per-scan graph and feature tensors
+        clouds.append(dc.DepthCloud(vps=c.vps, dirs=c.dirs, depth=c.depth, inc_angles=c.inc_angles, mask=c.mask))
+    return clouds
+
+
+def one_step(dc, clouds, poses, deltas, model, cfg, ns=None, timers=None):
+    """search (unless a graph is given) + fused forward + backward; returns (loss, ns)."""
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    e0, e1, e2 = ev(), ev(), ev()
+    e0.record()
+    if ns is None:
+        ns = dc.establish_neighborhoods(clouds=clouds, poses=poses, cfg=cfg)
+        cloud = dc.global_cloud(clouds=clouds, model=model, poses=poses)
+        feats = dc.compute_neighborhood_features(cloud=cloud, neighborhoods=ns, cfg=cfg)
+        feats.step_state()                       # pack the scan records in sorted order
+        ns.graph.transposed()                    # reverse lists for the gather-form backward
+    e1.record()
+    model.zero_grad(set_to_none=True)
+    deltas.grad = None
+    poses_c = torch.stack(dc.create_corrected_poses(poses, deltas, cfg))
+    cloud = dc.global_cloud(clouds=clouds, model=model, poses=poses_c)
+    feats = dc.compute_neighborhood_features(cloud=cloud, neighborhoods=ns, cfg=cfg)
+    loss, _ = dc.min_eigval_loss(feats, normalization=True)
+    loss.backward()
+    e2.record()
+    if timers is not None:
+        timers.append((e0, e1, e2))
+    return loss, ns
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import depth_correction_b200 as dc
+    from depth_correction_b200 import _lib as L
+
+    n_scans = 4 if args.profile else args.scans
+    pts_host, poses_np = host_scans(n_scans, args.pattern, first_scan=rank * n_scans)
+    cfg = dc.Config(nn_k=NN_K, nn_r=NN_R, pose_correction=dc.PoseCorrection.pose)
+    pts_pinned = [torch.from_numpy(p).pin_memory() for p in pts_host]
+    pts_dev = [p.to(dev, non_blocking=True) for p in pts_pinned]
+    clouds = local_features(dc, pts_dev, cfg)
+    n_local = sum(len(c) for c in clouds)
+    poses = torch.as_tensor(poses_np, device=dev)
+    deltas = torch.zeros((n_scans, 6), dtype=torch.float64, device=dev, requires_grad=True)
+    model = dc.ScaledPolynomial(w=[0.0, 0.0], exponent=[2, 4], device=dev)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def allreduce_step(loss):
+        # weak scaling over independent corridor segments: each rank owns the loss terms of its own
+        # scans; the per-iteration exchange is the small gradient / loss-partial vector (multi-GPU)
+        if world > 1:
+            buf = torch.cat([loss.detach().reshape(1) * n_local, torch.tensor([float(n_local)], device=dev, dtype=torch.float64),
+                             model.w.grad.reshape(-1) * n_local])
+            dist.all_reduce(buf)
+            return buf[0] / buf[1]
+        return loss.detach()
+
+    # warm-up (also builds nothing persistent: every step searches again)
+    for _ in range(max(args.warmup, 3 if not args.profile else 1)):
+        loss, ns = one_step(dc, clouds, poses, deltas, model, cfg)
+        allreduce_step(loss)
+    sync()
+    if args.profile:
+        print(json.dumps({'profile_run': True, 'n_points': n_local, 'loss': loss.item()}))
+        return
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    timers = []
+    launches0 = L.launch_count
+    L.profile = {}
+    sync()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        loss, ns = one_step(dc, clouds, poses, deltas, model, cfg, timers=timers)
+        gl = allreduce_step(loss)
+    t1.record()
+    sync()
+    kernel_ms = L.collect_profile()
+    L.profile = None
+    launches = L.launch_count - launches0
+    clocks = sampler.summary()
+    total_ms = t0.elapsed_time(t1)
+    search_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in timers]))
+    step_ms = float(np.mean([b.elapsed_time(c) for _, b, c in timers]))
+    if world > 1:
+        t = torch.tensor([total_ms, search_ms, step_ms, float(n_local)], device=dev, dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_ms, search_ms, step_ms = tmax[0].item(), tmax[1].item(), tmax[2].item()
+        n_total = int(t[3].item())
+    else:
+        n_total = n_local
+    ms_per_step = total_ms / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the public API from pinned HOST buffers (H2D + D2H inside the timed region)
+    inc_host = [c.inc_angles.cpu().pin_memory() for c in clouds]
+    mask_host = [c.mask.cpu().pin_memory() for c in clouds]
+    poses_host = torch.as_tensor(poses_np).pin_memory()
+    h2d = sum(p.numel() * 4 for p in pts_pinned) + sum(x.numel() * 4 for x in inc_host) + sum(x.numel() for x in mask_host) \
+        + poses_host.numel() * 8
+
+    def e2e_step():
+        cl = []
+        for p, a, m in zip(pts_pinned, inc_host, mask_host):
+            c = dc.DepthCloud.from_points(p.to(dev, non_blocking=True))
+            c.inc_angles = a.to(dev, non_blocking=True)
+            c.mask = m.to(dev, non_blocking=True)
+            cl.append(c)
+        ps = poses_host.to(dev, non_blocking=True)
+        loss, _ = one_step(dc, cl, ps, deltas, model, cfg)
+        out = torch.cat([loss.detach().reshape(1), model.w.grad.reshape(-1), deltas.grad.reshape(-1)]).cpu()
+        return out
+
+    e2e_step()
+    sync()
+    n_e2e = max(2, min(args.steps, 3))
+    w0 = time.perf_counter()
+    for _ in range(n_e2e):
+        out = e2e_step()
+    sync()
+    e2e_s = (time.perf_counter() - w0) / n_e2e
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    d2h = out.numel() * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event durations of the timed region)
+    g = ns.graph
+    gt = g.transposed()
+    idx_fwd = g.ell_idx.numel() * 4
+    idx_bwd = gt.ell_idx.numel() * 4
+    alg = {   # algorithmic bytes per launch: every array once per pass, gathers assumed L2-served
+        'dc_step_points': n_local * (36 + 32),
+        'dc_step_forward': idx_fwd + n_local * (32 + 4 + 8 + 64),
+        'dc_step_backward': idx_bwd + n_local * (32 + 36),
+    }
+    peak, peak_src = peaks()
+    kern = {k: v for k, v in kernel_ms.items() if k in alg}
+    top = max(kern, key=lambda k: kern[k]['ms_total']) if kern else None
+    roofline = None
+    if top:
+        avg_ms = kern[top]['ms_total'] / kern[top]['calls']
+        ach = alg[top] / (avg_ms * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': top, 'achieved': round(ach, 1), 'peak': peak, 'unit': 'GB/s',
+                    'frac': round(ach / peak, 4), 'traffic': None, 'peak_source': peak_src,
+                    'avg_kernel_ms': round(avg_ms, 4), 'algorithmic_bytes': alg[top],
+                    'step_kernels_ms': {k: round(v['ms_total'] / v['calls'], 4) for k, v in kern.items()},
+                    'step_fraction_of_roofline': round(sum(alg.values()) / (step_ms * 1e-3) / 1e9 / peak, 4)}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64 arithmetic on f32 records', 'data': 'synthetic',
+        'config': {'workload': 'corridor, %d full-res %s scans per GPU, kNN k=%d within r=%.1f m, ScaledPolynomial[2,4] + '
+                               'min_eigval_loss(normalization) + per-scan SE(3) corrections' % (n_scans, args.pattern, NN_K, NN_R),
+                   'n_points': n_total, 'n_points_per_gpu': n_local, 'k': NN_K, 'r': NN_R,
+                   'l2_policy': 'inputs larger than L2 (point + index + stash arrays %.0f MB)' %
+                                ((n_local * (32 + 64 + 36) + idx_fwd + idx_bwd) / 1e6),
+                   'parallelism': 'spatial slabs of the corridor, one per GPU; all-reduce of loss/gradient partials'},
+        'search_ms': search_ms, 'fixed_graph_step_ms': step_ms,
+        'search_points_per_s': n_total / (search_ms * 1e-3), 'fixed_graph_step_points_per_s': n_total / (step_ms * 1e-3),
+        'loss': float(gl.item()),
+        'clocks': clocks, 'gpu_launches': launches,
+        'e2e': {'value': n_total / e2e_s, 'unit': 'points/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': e2e_s * 1e3},
+        'roofline': roofline,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line['cpu_baseline'] = cpu_baseline(args.cpu_scans, args.pattern, steps=1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's CPU path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step(scans, poses, k, r):
+    from oracle import oracle
+    t0 = time.perf_counter()
+    pts, _ = oracle.global_points(scans, poses)
+    _, nb = oracle.nearest_neighbors(pts, k=k, r=r)
+    t1 = time.perf_counter()
+    S = len(scans)
+    out = oracle.map_consistency_step(scans, poses, nb, torch.zeros((1, 2), dtype=torch.float64),
+                                      torch.tensor([[2.0, 4.0]], dtype=torch.float64),
+                                      pose_deltas=torch.zeros((S, 6), dtype=torch.float64),
+                                      loss='min_eigval_loss', normalization=True)
+    t2 = time.perf_counter()
+    return len(pts), t1 - t0, t2 - t1, float(out['loss'])
+
+
+def cpu_workload(n_scans, pattern):
+    """Bounded sample of the same workload for the CPU path (float32 values up-cast to float64)."""
+    from oracle import oracle
+    pts_host, poses_np = host_scans(n_scans, pattern)
+    scans = []
+    for p in pts_host:
+        p64 = torch.as_tensor(p.astype(np.float64))
+        vps, dirs, depth = oracle.from_points(p64)
+        # local features are setup, not part of the timed step: planar corridor -> analytic-free cheap stand-in
+        _, nb = oracle.nearest_neighbors(p64, k=NN_K, r=NN_R)
+        f = oracle.neighborhood_features(p64, nb, dirs=dirs)
+        mask = oracle.eigenvalue_masks(f['eigvals'], (), [[0, 1, 0, 0.25], [1, 2, 0.25, 1.0]])
+        scans.append({'vps': vps, 'dirs': dirs, 'depth': depth, 'inc_angles': f['inc_angles'], 'mask': mask})
+    return scans, torch.as_tensor(poses_np)
+
+
+def cpu_baseline(n_scans, pattern, steps=1):
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    scans, poses = cpu_workload(n_scans, pattern)
+    best = None
+    for _ in range(steps):
+        n, ts, tf, loss = cpu_step(scans, poses, NN_K, NN_R)
+        if best is None or ts + tf < best[1] + best[2]:
+            best = (n, ts, tf, loss)
+    n, ts, tf, loss = best
+    return {'value': n / (ts + tf), 'unit': 'points/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d of the same OS0-128 corridor scans (%d points), cKDTree search %.2f s + torch fp64 step fwd+bwd %.2f s'
+                      % (n_scans, n, ts, tf),
+            'search_s': ts, 'fixed_graph_step_s': tf, 'loss': loss}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle port: scipy cKDTree + torch fp64 autograd,
+    all host threads) on a bounded sample of the same workload.  Rank 0 only."""
+    if int(os.environ.get('RANK', 0)) != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    scans, poses = cpu_workload(args.cpu_scans, args.pattern)
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(scans, poses, NN_K, NN_R)
+    times = []
+    for _ in range(args.steps):
+        n, ts, tf, loss = cpu_step(scans, poses, NN_K, NN_R)
+        times.append((ts, tf))
+    ts = float(np.mean([t[0] for t in times]))
+    tf = float(np.mean([t[1] for t in times]))
+    value = n / (ts + tf)
+    sample = '%d of the same OS0-128 corridor scans (%d points) per step' % (args.cpu_scans, n)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': (ts + tf) * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'corridor, full-res %s scans, kNN k=%d within r=%.1f m, ScaledPolynomial[2,4] + '
+                               'min_eigval_loss(normalization) + per-scan SE(3) corrections; bounded CPU sample: %s'
+                               % (args.pattern, NN_K, NN_R, sample), 'n_points': n, 'k': NN_K, 'r': NN_R},
+        'search_ms': ts * 1e3, 'fixed_graph_step_ms': tf * 1e3, 'loss': loss,
+        'cpu_baseline': {'value': value, 'unit': 'points/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -114,12 +114,31 @@ def dtype_code(dt):
     raise TypeError('depth_correction_b200 supports float32 / float64 clouds, got %s' % dt)
 
 
+# optional per-entry-point CUDA-event timing (bench.py): set `profile = {}` to enable, None to disable
+profile = None
+
+
 def call(name, *args):
     global launch_count
+    if profile is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(_lib, name)(*args)
     if rc != 0:
         raise DcError('%s failed (code %d): %s' % (name, rc, _lib.dc_last_error().decode()))
     launch_count += 1
+    if profile is not None:
+        e1.record()
+        profile.setdefault(name, []).append((e0, e1))
+
+
+def collect_profile():
+    """{entry point: {'calls': n, 'ms_total': t}} from the recorded events (call after a synchronize)."""
+    out = {}
+    for name, evs in (profile or {}).items():
+        out[name] = {'calls': len(evs), 'ms_total': float(sum(a.elapsed_time(b) for a, b in evs))}
+    return out
 
 
 def call_with_temp(name, device, *args_before_temp, after=()):

@@ -166,7 +166,10 @@ __global__ void eigh3_bwd_kernel(const T* __restrict__ eigvals, const T* __restr
       for (int b = 0; b < 3; ++b) X[3 * a + b] = V[a] * GV[b] + V[3 + a] * GV[3 + b] + V[6 + a] * GV[6 + b];   // V^T gV
     for (int a = 0; a < 3; ++a)
       for (int b = 0; b < 3; ++b)
-        if (a != b) M[3 * a + b] = 0.5 * (X[3 * a + b] - X[3 * b + a]) / (L[b] - L[a]);
+        if (a != b) {
+          const double num = 0.5 * (X[3 * a + b] - X[3 * b + a]);
+          M[3 * a + b] = num != 0.0 ? num / (L[b] - L[a]) : 0.0;   // no 0/0 for repeated eigenvalues without eigenvector gradient
+        }
   }
   if (gl) for (int a = 0; a < 3; ++a) M[4 * a] = (double)gl[3 * i + a];
   // gA = V M V^T

@@ -66,7 +66,56 @@ DC_HD double dc_sym3_rayleigh(const dc_sym3& m, const double v[3]) {
   return v[0] * ax + v[1] * ay + v[2] * az;
 }
 
-// lam[3] ascending.  If want_vecs: V[3*j + i] = component i of eigenvector j (unit, right-handed).
+// Orthonormal pair (u, v) spanning the plane orthogonal to the unit vector w, with u x v = w.
+DC_HD void dc_complement(const double w[3], double u[3], double v[3]) {
+  if (fabs(w[0]) > fabs(w[1])) {
+    const double inv = 1.0 / sqrt(w[0] * w[0] + w[2] * w[2]);
+    u[0] = -w[2] * inv; u[1] = 0.0; u[2] = w[0] * inv;
+  } else {
+    const double inv = 1.0 / sqrt(w[1] * w[1] + w[2] * w[2]);
+    u[0] = 0.0; u[1] = w[2] * inv; u[2] = -w[1] * inv;
+  }
+  dc_cross(w, u, v);
+}
+
+DC_HD void dc_sym3_apply(const dc_sym3& m, const double x[3], double y[3]) {
+  y[0] = m.xx * x[0] + m.xy * x[1] + m.xz * x[2];
+  y[1] = m.xy * x[0] + m.yy * x[1] + m.yz * x[2];
+  y[2] = m.xz * x[0] + m.yz * x[1] + m.zz * x[2];
+}
+
+// The two remaining eigenpairs of m in the plane orthogonal to the unit eigenvector w: the 2x2
+// problem [[u'mu, u'mv], [u'mv, v'mv]] is solved in closed form, which stays accurate when the two
+// eigenvalues are close to each other or tiny compared to the one already found.
+// Outputs: lo <= hi and the unit eigenvector of lo (elo); the eigenvector of hi is w x elo / elo x w.
+DC_HD void dc_sym3_deflate(const dc_sym3& m, const double w[3], double& lo, double& hi, double elo[3]) {
+  double u[3], v[3], mu[3], mv[3];
+  dc_complement(w, u, v);
+  dc_sym3_apply(m, u, mu);
+  dc_sym3_apply(m, v, mv);
+  const double a = dc_dot3(u, mu), b = dc_dot3(u, mv), c = dc_dot3(v, mv);
+  const double hd = 0.5 * (a - c), mid = 0.5 * (a + c);
+  const double rad = sqrt(hd * hd + b * b);
+  lo = mid - rad;
+  hi = mid + rad;
+  // eigenvector of lo in (u, v) coordinates: (b, lo - a) or (lo - c, b), whichever is longer
+  double x0 = b, y0 = lo - a, x1 = lo - c, y1 = b;
+  if (x1 * x1 + y1 * y1 > x0 * x0 + y0 * y0) { x0 = x1; y0 = y1; }
+  const double n2 = x0 * x0 + y0 * y0;
+  if (n2 > 0.0) {
+    const double inv = 1.0 / sqrt(n2);
+    x0 *= inv; y0 *= inv;
+  } else {
+    x0 = 1.0; y0 = 0.0;   // a == c, b == 0: every direction of the plane is an eigenvector
+  }
+  elo[0] = x0 * u[0] + y0 * v[0]; elo[1] = x0 * u[1] + y0 * v[1]; elo[2] = x0 * u[2] + y0 * v[2];
+}
+
+// lam[3] ascending.  want_vecs: 0 = eigenvalues only, 1 = V[0..2] = eigenvector of lam[0],
+// 3 = V[3*j + i] = component i of eigenvector j (orthonormal, right-handed).
+// Closed form in three steps: trigonometric root for the best separated eigenvalue (largest if
+// det(B) >= 0, else smallest), its eigenvector from cross products + Rayleigh quotient, then the
+// deflated 2x2 problem for the other pair.  Eigenvalue errors are O(eps * |A|) like LAPACK's.
 // Returns false when the input is not finite (outputs are NaN, like LAPACK would propagate).
 DC_HD bool dc_sym3_eig(const dc_sym3& a, double lam[3], double* V, int want_vecs) {
   double s = fabs(a.xx);
@@ -75,65 +124,54 @@ DC_HD bool dc_sym3_eig(const dc_sym3& a, double lam[3], double* V, int want_vecs
   if (!(s < INFINITY)) {   // inf or NaN
     const double nan = NAN;
     lam[0] = lam[1] = lam[2] = nan;
-    if (want_vecs) for (int i = 0; i < 3 * want_vecs; ++i) V[i] = nan;
+    for (int i = 0; i < 3 * want_vecs; ++i) V[i] = nan;
     return false;
   }
-  if (s == 0.0) {
-    lam[0] = lam[1] = lam[2] = 0.0;
-    if (want_vecs >= 1) { V[0] = 1; V[1] = 0; V[2] = 0; }
-    if (want_vecs >= 3) { V[3] = 0; V[4] = 1; V[5] = 0; V[6] = 0; V[7] = 0; V[8] = 1; }
-    return true;
-  }
-  const double inv = 1.0 / s;
-  dc_sym3 m = {a.xx * inv, a.xy * inv, a.xz * inv, a.yy * inv, a.yz * inv, a.zz * inv};
+  const double inv = s > 0.0 ? 1.0 / s : 0.0;
+  const dc_sym3 m = {a.xx * inv, a.xy * inv, a.xz * inv, a.yy * inv, a.yz * inv, a.zz * inv};
   const double q = (m.xx + m.yy + m.zz) * (1.0 / 3.0);
   const double bxx = m.xx - q, byy = m.yy - q, bzz = m.zz - q;
   const double p1 = m.xy * m.xy + m.xz * m.xz + m.yz * m.yz;
   const double p2 = bxx * bxx + byy * byy + bzz * bzz + 2.0 * p1;
-  double l0, l1, l2;
-  if (p2 <= 0.0) {
-    l0 = l1 = l2 = q;
-  } else {
-    const double p = sqrt(p2 * (1.0 / 6.0));
-    const double ip = 1.0 / p;
-    const double cxx = bxx * ip, cyy = byy * ip, czz = bzz * ip, cxy = m.xy * ip, cxz = m.xz * ip, cyz = m.yz * ip;
-    const double det = cxx * (cyy * czz - cyz * cyz) - cxy * (cxy * czz - cyz * cxz) + cxz * (cxy * cyz - cyy * cxz);
-    double r = 0.5 * det;
-    r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
-    const double phi = acos(r) * (1.0 / 3.0);
-    l2 = q + 2.0 * p * cos(phi);
-    l0 = q + 2.0 * p * cos(phi + 2.0943951023931954923);   // + 2 pi / 3
-    l1 = 3.0 * q - l0 - l2;
+  if (p2 <= 0.0) {         // multiple of the identity (including the zero matrix)
+    lam[0] = lam[1] = lam[2] = q * s;
+    if (want_vecs >= 1) { V[0] = 1; V[1] = 0; V[2] = 0; }
+    if (want_vecs >= 3) { V[3] = 0; V[4] = 1; V[5] = 0; V[6] = 0; V[7] = 0; V[8] = 1; }
+    return true;
   }
-  if (want_vecs) {
-    double v0[3], v2[3];
-    dc_sym3_eigvec(m, l0, v0);
-    // Rayleigh quotient: second-order accurate in the eigenvector error, bounded by the gap
-    l0 = dc_sym3_rayleigh(m, v0);
-    V[0] = v0[0]; V[1] = v0[1]; V[2] = v0[2];
+  const double p = sqrt(p2 * (1.0 / 6.0));
+  const double ip = 1.0 / p;
+  const double cxx = bxx * ip, cyy = byy * ip, czz = bzz * ip, cxy = m.xy * ip, cxz = m.xz * ip, cyz = m.yz * ip;
+  const double det = cxx * (cyy * czz - cyz * cyz) - cxy * (cxy * czz - cyz * cxz) + cxz * (cxy * cyz - cyy * cxz);
+  double r = 0.5 * det;
+  r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+  const double phi = acos(r) * (1.0 / 3.0);
+  double l0, l1, l2, w[3], e[3];
+  if (r >= 0.0) {
+    // the largest eigenvalue is the isolated one (linear / generic neighbourhoods)
+    l2 = q + 2.0 * p * cos(phi);
+    dc_sym3_eigvec(m, l2, w);
+    l2 = dc_sym3_rayleigh(m, w);
+    dc_sym3_deflate(m, w, l0, l1, e);
+    if (want_vecs >= 1) { V[0] = e[0]; V[1] = e[1]; V[2] = e[2]; }
     if (want_vecs >= 3) {
-      dc_sym3_eigvec(m, l2, v2);
-      // re-orthogonalise v2 against v0 (they are orthogonal up to rounding unless degenerate)
-      const double d = dc_dot3(v2, v0);
-      double w[3] = {v2[0] - d * v0[0], v2[1] - d * v0[1], v2[2] - d * v0[2]};
-      double n = dc_dot3(w, w);
-      if (n < 1e-20) {   // v2 ~ parallel to v0 (fully degenerate): any unit vector orthogonal to v0
-        const double ax = fabs(v0[0]), ay = fabs(v0[1]), az = fabs(v0[2]);
-        double e[3] = {0.0, 0.0, 0.0};
-        if (ax <= ay && ax <= az) e[0] = 1.0; else if (ay <= az) e[1] = 1.0; else e[2] = 1.0;
-        dc_cross(v0, e, w);
-        n = dc_dot3(w, w);
-      }
-      const double in = 1.0 / sqrt(n);
-      v2[0] = w[0] * in; v2[1] = w[1] * in; v2[2] = w[2] * in;
-      l2 = dc_sym3_rayleigh(m, v2);
       double v1[3];
-      dc_cross(v2, v0, v1);
-      l1 = 3.0 * q - l0 - l2;
+      dc_cross(w, e, v1);
       V[3] = v1[0]; V[4] = v1[1]; V[5] = v1[2];
+      V[6] = w[0]; V[7] = w[1]; V[8] = w[2];
+    }
+  } else {
+    // the smallest eigenvalue is the isolated one (planar neighbourhoods, the common case)
+    l0 = q + 2.0 * p * cos(phi + 2.0943951023931954923);   // + 2 pi / 3
+    dc_sym3_eigvec(m, l0, w);
+    l0 = dc_sym3_rayleigh(m, w);
+    if (want_vecs >= 1) { V[0] = w[0]; V[1] = w[1]; V[2] = w[2]; }
+    dc_sym3_deflate(m, w, l1, l2, e);
+    if (want_vecs >= 3) {
+      double v2[3];
+      dc_cross(w, e, v2);
+      V[3] = e[0]; V[4] = e[1]; V[5] = e[2];
       V[6] = v2[0]; V[7] = v2[1]; V[8] = v2[2];
-    } else {
-      l1 = 3.0 * q - l0 - l2;
     }
   }
   lam[0] = l0 * s; lam[1] = l1 * s; lam[2] = l2 * s;

@@ -218,6 +218,9 @@ step_forward_kernel(const dc_point* __restrict__ P, const uint32_t* __restrict__
     } else {
       double lam[3];
       dc_sym3_eig(C, lam, v0, 1);
+      // rank-deficient neighbourhoods (<= 3 points, exact planes): lambda0 is rounding noise of either sign;
+      // treat it as zero so that sqrt'(noise) ~ 1e9 cannot leak noise into the gradients
+      if (fabs(lam[0]) <= 1e-14 * fabs(lam[2])) lam[0] = 0.0;
       if (eigvals) { eigvals[3 * row] = lam[0]; eigvals[3 * row + 1] = lam[1]; eigvals[3 * row + 2] = lam[2]; }
       if (flags & DC_FLAG_NORMALIZATION) {             // loss.py:253-254
         const double tc = fmax(tr, 1e-6);

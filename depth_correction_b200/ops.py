@@ -19,6 +19,7 @@ def _check(points, neighbors):
 class _MeanCov(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points, neighbors, weights, want_mean, want_cov):
+        ctx.set_materialize_grads(False)
         _check(points, neighbors)
         pts = points.detach().contiguous()
         nb = neighbors.contiguous()
@@ -58,6 +59,7 @@ def neighborhood_mean_cov(points, neighbors, weights=None, mean=True, cov=True):
 class _Eigh3(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cov):
+        ctx.set_materialize_grads(False)
         assert cov.is_cuda and cov.shape[-2:] == (3, 3)
         c = cov.detach().contiguous()
         n = c.shape[0]

