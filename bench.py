@@ -282,6 +282,7 @@ def run_ours(args):
         'e2e': {'value': n_total / e2e_s, 'unit': 'points/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_s * 1e3},
         'roofline': roofline,
+        'entry_points_ms_per_step': {k: round(v['ms_total'] / args.steps, 4) for k, v in sorted(kernel_ms.items())},
     }
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_baseline(args.cpu_scans, args.pattern, steps=1)

@@ -323,16 +323,32 @@ __device__ __forceinline__ double dc_warp_sum(double v) {
   return v;
 }
 
+// Persistent kernel: every warp walks slices (32 rows) with a grid stride.  Per-scan pose gradients are
+// accumulated in shared memory (acc[n_scans][12], shared-memory atomics spread over scan ids) and flushed
+// to global memory once per block; model gradients stay in registers until the end of the loop.
+// acc_scans == 0 selects the fallback for very many scans: warp-segmented reduction + global atomics.
+#define BWD_THREADS 256
+
 template <typename T>
-__global__ void __launch_bounds__(STEP_THREADS)
+__global__ void __launch_bounds__(BWD_THREADS)
 step_backward_kernel(const dc_point* __restrict__ P, const typename vec4_of<T>::type* __restrict__ rec_dir,
                      const typename vec4_of<T>::type* __restrict__ rec_vp, const uint32_t* __restrict__ rec_meta, int64_t n,
                      const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ ell_idx,
                      const dc_stash* __restrict__ stash, const double* __restrict__ upstream,
                      const double* __restrict__ poses, dc_model model, double* __restrict__ dw,
-                     double* __restrict__ dexp, double* __restrict__ dposes) {
-  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+                     double* __restrict__ dexp, double* __restrict__ dposes, int acc_scans) {
+  extern __shared__ double acc[];
   const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < acc_scans * 12; i += BWD_THREADS) acc[i] = 0.0;
+  __syncthreads();
+  double gw_sum[DC_MAX_TERMS], ge_sum[DC_MAX_TERMS];
+#pragma unroll
+  for (int k = 0; k < DC_MAX_TERMS; ++k) { gw_sum[k] = 0.0; ge_sum[k] = 0.0; }
+  const int64_t n_slices = (n + DC_SLICE - 1) / DC_SLICE;
+  const int64_t warp0 = (blockIdx.x * (int64_t)BWD_THREADS + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * BWD_THREADS) >> 5;
+  for (int64_t slice = warp0; slice < n_slices; slice += n_warps) {
+  const int64_t row = slice * DC_SLICE + lane;
   const bool live = row < n;
   double gx = 0, gy = 0, gz = 0;
   dc_point pj;
@@ -399,24 +415,16 @@ step_backward_kernel(const dc_point* __restrict__ P, const typename vec4_of<T>::
     gT[4] = gy * x; gT[5] = gy * y; gT[6] = gy * z; gT[7] = gy;
     gT[8] = gz * x; gT[9] = gz * y; gT[10] = gz * z; gT[11] = gz;
   }
-  // ---- model gradients: warp shuffle -> shared -> one atomic per block and term
-  if (model.kind != DC_MODEL_NONE && dw) {
-    __shared__ double red[STEP_THREADS / 32][2 * DC_MAX_TERMS];
-    for (int k = 0; k < model.n_terms; ++k) {
-      const double a = dc_warp_sum(gw[k]);
-      const double b = dexp ? dc_warp_sum(ge[k]) : 0.0;
-      if (lane == 0) { red[threadIdx.x >> 5][k] = a; red[threadIdx.x >> 5][DC_MAX_TERMS + k] = b; }
+#pragma unroll
+  for (int k = 0; k < DC_MAX_TERMS; ++k) { gw_sum[k] += gw[k]; ge_sum[k] += ge[k]; }
+  // ---- pose gradients
+  if (dposes && acc_scans > 0) {
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) atomicAdd(acc + 12 * scan + k, gT[k]);
     }
-    __syncthreads();
-    if (threadIdx.x < model.n_terms) {
-      double a = 0.0, b = 0.0;
-      for (int wv = 0; wv < STEP_THREADS / 32; ++wv) { a += red[wv][threadIdx.x]; b += red[wv][DC_MAX_TERMS + threadIdx.x]; }
-      atomicAdd(dw + threadIdx.x, a);
-      if (dexp) atomicAdd(dexp + threadIdx.x, b);
-    }
-  }
-  // ---- pose gradients: segmented by scan id inside the warp
-  if (dposes) {
+  } else if (dposes) {
+    // fallback: segmented by scan id inside the warp, one global atomic per scan and entry
     unsigned int remaining = __ballot_sync(0xffffffffu, live);
     while (remaining) {
       const int leader = __ffs(remaining) - 1;
@@ -430,6 +438,30 @@ step_backward_kernel(const dc_point* __restrict__ P, const typename vec4_of<T>::
       remaining &= ~__ballot_sync(0xffffffffu, mine);
     }
   }
+  }   // slice loop
+  // ---- model gradients: registers -> warp shuffle -> shared -> one atomic per block and term
+  if (model.kind != DC_MODEL_NONE && dw) {
+    __shared__ double red[BWD_THREADS / 32][2 * DC_MAX_TERMS];
+    for (int k = 0; k < model.n_terms; ++k) {
+      const double a = dc_warp_sum(gw_sum[k]);
+      const double b = dexp ? dc_warp_sum(ge_sum[k]) : 0.0;
+      if (lane == 0) { red[threadIdx.x >> 5][k] = a; red[threadIdx.x >> 5][DC_MAX_TERMS + k] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < model.n_terms) {
+      double a = 0.0, b = 0.0;
+      for (int wv = 0; wv < BWD_THREADS / 32; ++wv) { a += red[wv][threadIdx.x]; b += red[wv][DC_MAX_TERMS + threadIdx.x]; }
+      atomicAdd(dw + threadIdx.x, a);
+      if (dexp) atomicAdd(dexp + threadIdx.x, b);
+    }
+  }
+  if (dposes && acc_scans > 0) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < acc_scans * 12; i += BWD_THREADS) {
+      const double v = acc[i];
+      if (v != 0.0) atomicAdd(dposes + i, v);
+    }
+  }
 }
 
 extern "C" int dc_step_backward(const void* points, const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta,
@@ -439,18 +471,40 @@ extern "C" int dc_step_backward(const void* points, const void* rec_dir, const v
                                 double* dexponent, double* dposes, void* stream) {
   if (n <= 0) return DC_OK;
   if (n_terms < 0 || n_terms > DC_MAX_TERMS) return dc_set_error(DC_ERR_ARG, "dc_step_backward: too many polynomial terms");
-  (void)n_scans;
   dc_model m = {model_kind, n_terms, w, exponent};
-  const int blocks = dc_blocks(((n + 31) / 32) * 32, STEP_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == DC_F32)
-    step_backward_kernel<float><<<blocks, STEP_THREADS, 0, st>>>((const dc_point*)points, (const float4*)rec_dir, (const float4*)rec_vp,
-                                                                 rec_meta, n, slice_ptr_t, ell_idx_t, (const dc_stash*)stash,
-                                                                 upstream_pp, poses, m, dw, dexponent, dposes);
-  else
-    step_backward_kernel<double><<<blocks, STEP_THREADS, 0, st>>>((const dc_point*)points, (const double4*)rec_dir, (const double4*)rec_vp,
-                                                                  rec_meta, n, slice_ptr_t, ell_idx_t, (const dc_stash*)stash,
-                                                                  upstream_pp, poses, m, dw, dexponent, dposes);
+  // persistent grid: a multiple of the SM count (148 on B200), resident blocks limited by the pose accumulators
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    DC_CUDA_CHECK(cudaGetDevice(&dev));
+    DC_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  size_t smem = (size_t)n_scans * 12 * sizeof(double);
+  int acc_scans = n_scans;
+  if (!dposes || smem > 200 * 1024) { smem = 0; acc_scans = 0; }
+  int per_sm = 4;
+  if (smem > 0) {
+    const int fit = (int)((220 * 1024) / (smem + 1024));
+    per_sm = fit < 1 ? 1 : (fit > 4 ? 4 : fit);
+  }
+  const int64_t n_slices = (n + DC_SLICE - 1) / DC_SLICE;
+  int64_t blocks = (int64_t)sm_count * per_sm;
+  const int64_t need = (n_slices + BWD_THREADS / 32 - 1) / (BWD_THREADS / 32);
+  if (blocks > need) blocks = need;
+  if (dtype == DC_F32) {
+    if (smem > 48 * 1024)
+      DC_CUDA_CHECK(cudaFuncSetAttribute(step_backward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    step_backward_kernel<float><<<(int)blocks, BWD_THREADS, smem, st>>>((const dc_point*)points, (const float4*)rec_dir, (const float4*)rec_vp,
+                                                                        rec_meta, n, slice_ptr_t, ell_idx_t, (const dc_stash*)stash,
+                                                                        upstream_pp, poses, m, dw, dexponent, dposes, acc_scans);
+  } else {
+    if (smem > 48 * 1024)
+      DC_CUDA_CHECK(cudaFuncSetAttribute(step_backward_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    step_backward_kernel<double><<<(int)blocks, BWD_THREADS, smem, st>>>((const dc_point*)points, (const double4*)rec_dir, (const double4*)rec_vp,
+                                                                         rec_meta, n, slice_ptr_t, ell_idx_t, (const dc_stash*)stash,
+                                                                         upstream_pp, poses, m, dw, dexponent, dposes, acc_scans);
+  }
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

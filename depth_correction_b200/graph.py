@@ -28,7 +28,64 @@ def _as_points(x):
 class SortedMap(object):
     """Points sorted by grid cell: P (fp64 32-byte records), keys, order / inv_order, optional dense cell table."""
 
-    def __init__(self, points, cell, also_cover=None):
+    @staticmethod
+    def bounds_of(points, also_cover=None):
+        """(lo[3], hi[3]) of the finite point set (one reduction kernel + one small read-back)."""
+        dev = points.device
+        st = L.stream()
+        out = torch.empty((2, 6), dtype=torch.float64, device=dev)
+        bad = torch.zeros(2, dtype=torch.int32, device=dev)
+        L.call('dc_bounds', L.ptr(points), L.dtype_code(points.dtype), points.shape[0], L.ptr(out[0]), L.ptr(bad[0:1]), st)
+        have_q = also_cover is not None and also_cover.shape[0] > 0
+        if have_q:
+            q = _as_points(also_cover)
+            L.call('dc_bounds', L.ptr(q), L.dtype_code(q.dtype), q.shape[0], L.ptr(out[1]), L.ptr(bad[1:2]), st)
+        b = out.cpu()
+        if int(bad.cpu()[0]) > 0:
+            raise ValueError('points must be finite (cKDTree raises as well)')
+        lo, hi = b[0, :3], b[0, 3:]
+        if have_q:
+            lo, hi = torch.minimum(lo, b[1, :3]), torch.maximum(hi, b[1, 3:])
+        if points.shape[0] == 0:
+            lo, hi = torch.zeros(3, dtype=torch.float64), torch.zeros(3, dtype=torch.float64)
+        return lo.tolist(), hi.tolist()
+
+    @staticmethod
+    def make_spec(lo, hi, cell):
+        spec = L.GridSpec()
+        spec.cell = float(cell)
+        ext = []
+        for a in range(3):
+            spec.origin[a] = lo[a] - 1e-3 * cell
+            spec.dims[a] = int(math.floor((hi[a] - spec.origin[a]) / cell)) + 1
+            ext.append(hi[a] - lo[a])
+        # fastest key digit = shortest extent, slowest = longest (slabs along the trajectory stay contiguous)
+        axes = sorted(range(3), key=lambda a: (ext[a], a))
+        for i, a in enumerate(axes):
+            spec.axis[i] = a
+        n_cells = int(spec.dims[0]) * int(spec.dims[1]) * int(spec.dims[2])
+        if n_cells >= (1 << 62):
+            raise OverflowError('search grid has too many cells; increase the cell size')
+        return spec, axes, n_cells
+
+    @staticmethod
+    def occupancy_of(points, lo, hi, cell):
+        """Mean number of points per occupied cell for a candidate cell size (keys + key-only sort)."""
+        n = points.shape[0]
+        if n == 0:
+            return 0.0
+        spec, _, n_cells = SortedMap.make_spec(lo, hi, cell)
+        dev = points.device
+        st = L.stream()
+        keys = torch.empty(n, dtype=torch.int64, device=dev)
+        ids = torch.empty(n, dtype=torch.int32, device=dev)
+        skeys = torch.empty(n, dtype=torch.int64, device=dev)
+        L.call('dc_cell_keys', L.ptr(points), L.dtype_code(points.dtype), n, ctypes.byref(spec), L.ptr(keys), L.ptr(ids), st)
+        L.call_with_temp('dc_sort_keys', dev, L.ptr(keys), L.ptr(skeys), n, max(1, int(n_cells - 1).bit_length()), after=(st,))
+        n_occ = int((skeys[1:] != skeys[:-1]).sum().item()) + 1
+        return n / n_occ
+
+    def __init__(self, points, cell, also_cover=None, bounds=None):
         points = _as_points(points)
         dev = points.device
         self.device = dev
@@ -37,38 +94,9 @@ class SortedMap(object):
         code = L.dtype_code(points.dtype)
         n = self.n
         st = L.stream()
-
-        bounds = torch.empty(6, dtype=torch.float64, device=dev)
-        bad = torch.zeros(1, dtype=torch.int32, device=dev)
-        L.call('dc_bounds', L.ptr(points), code, n, L.ptr(bounds), L.ptr(bad), st)
-        b = bounds.cpu()
-        if int(bad.item()) > 0:
-            raise ValueError('points must be finite (cKDTree raises as well)')
-        if also_cover is not None and also_cover.shape[0] > 0:
-            q = _as_points(also_cover)
-            qb = torch.empty(6, dtype=torch.float64, device=dev)
-            L.call('dc_bounds', L.ptr(q), L.dtype_code(q.dtype), q.shape[0], L.ptr(qb), L.ptr(bad), st)
-            qb = qb.cpu()
-            b = torch.cat([torch.minimum(b[:3], qb[:3]), torch.maximum(b[3:], qb[3:])])
-        if n == 0:
-            b = torch.zeros(6, dtype=torch.float64)
-        lo, hi = b[:3].tolist(), b[3:].tolist()
-        self.spec = L.GridSpec()
+        lo, hi = bounds if bounds is not None else SortedMap.bounds_of(points, also_cover)
         self.cell = float(cell)
-        self.spec.cell = self.cell
-        ext = []
-        for a in range(3):
-            self.spec.origin[a] = lo[a] - 1e-3 * self.cell
-            self.spec.dims[a] = int(math.floor((hi[a] - self.spec.origin[a]) / self.cell)) + 1
-            ext.append(hi[a] - lo[a])
-        # fastest key digit = shortest extent, slowest = longest (slabs along the trajectory stay contiguous)
-        axes = sorted(range(3), key=lambda a: (ext[a], a))
-        for i, a in enumerate(axes):
-            self.spec.axis[i] = a
-        self.axes = axes
-        self.n_cells = int(self.spec.dims[0]) * int(self.spec.dims[1]) * int(self.spec.dims[2])
-        if self.n_cells >= (1 << 62):
-            raise OverflowError('search grid has too many cells; increase the cell size')
+        self.spec, self.axes, self.n_cells = SortedMap.make_spec(lo, hi, self.cell)
         self.key_bits = max(1, int(self.n_cells - 1).bit_length())
 
         keys = torch.empty(n, dtype=torch.int64, device=dev)     # uint64 bit patterns (< 2^62)
@@ -234,18 +262,17 @@ class Graph(object):
         return Graph(smap, sp, idx, n, K, mode='imported', symmetric=False)
 
 
-def _knn_cell_size(points, k, r):
+def _knn_cell_size(points, k, r, bounds):
     """Cell edge for kNN search: aim at ~k/4 points per occupied cell (surface-like data puts ~9
     occupied cells in a 3x3x3 block), estimated from one coarse sort."""
-    n = points.shape[0]
+    lo, hi = bounds
     if r:
         c0 = float(r)
     else:
-        ext = (points.max(dim=0).values - points.min(dim=0).values).double()
-        c0 = max(float(ext.max().item()) / 256.0, 1e-9)
+        c0 = max(max(h - l for l, h in zip(lo, hi)) / 256.0, 1e-9)
+    target = max(k / 4.0, 2.0)
     for _ in range(3):
-        occ = SortedMap(points, c0).occupancy()
-        target = max(k / 4.0, 2.0)
+        occ = SortedMap.occupancy_of(points, lo, hi, c0)
         if occ <= 2.0 * target:
             break
         c0 = c0 * max(math.sqrt(target / occ), 1.0 / 8.0)
@@ -260,12 +287,13 @@ def search(points, query=None, k=None, r=None, cell=None):
     n = points.shape[0]
     dev = points.device
     self_query = query is None or query is points
+    bounds = SortedMap.bounds_of(points, None if self_query else query)
     if cell is None:
         if k:
-            cell = _knn_cell_size(points, int(k), r) if n > 0 else 1.0
+            cell = _knn_cell_size(points, int(k), r, bounds) if n > 0 else 1.0
         else:
             cell = float(r) * (1.0 + 1e-6)   # a hair above r: one ring of cells is always enough
-    smap = SortedMap(points, cell, also_cover=None if self_query else query)
+    smap = SortedMap(points, cell, bounds=bounds)
     st = L.stream()
     if self_query:
         Q, qkeys, qorder, nq = smap.P, smap.keys, None, n
