@@ -62,6 +62,30 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop_flag = index, [], False
 
     def run(self):
+        # NVML in-process (the same counters nvidia-smi prints); spawning nvidia-smi every 100 ms
+        # perturbs the timed region by tens of milliseconds per step
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            if vis:
+                h = pynvml.nvmlDeviceGetHandleByIndex(int(vis.split(',')[self.index]))
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = [(pynvml.nvmlClocksThrottleReasonHwSlowdown, 2), (pynvml.nvmlClocksThrottleReasonHwThermalSlowdown, 3),
+                    (pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, 4), (pynvml.nvmlClocksThrottleReasonSwPowerCap, 5)]
+            while not self.stop_flag:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                row = [str(sm), str(mx), 'Not Active', 'Not Active', 'Not Active', 'Not Active']
+                for bit, col in bits:
+                    if reasons & bit:
+                        row[col] = 'Active'
+                self.rows.append(row)
+                time.sleep(0.02)
+            return
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
@@ -69,7 +93,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([x.strip() for x in out.strip().split(',')])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.5)
 
     def summary(self):
         self.stop_flag = True

@@ -56,13 +56,14 @@ SIGNATURES = {
     'dc_ell_offsets': [_P, _L, _P, _P, _SZP, _P],
     'dc_radius_fill': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _D, _P, _P, _P],
     'dc_knn': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _I, _D, _P, _P, _P],
+    'dc_knn_sort_rows': [_I, _P, _P, _L, _P],
     'dc_ell_to_padded': [_P, _P, _L, _P, _P, _I, _P, _P],
     'dc_ell_to_dist': [_I, _P, _P, _L, _P, _P, _P],
     'dc_sort_rows': [_P, _L, _I, _P, _SZP, _P],
     'dc_padded_to_ell': [_P, _L, _I, _P, _P, _P, _P, _P, _P],
     'dc_graph_edges': [_P, _P, _L, _P, _P, _P],
     'dc_graph_degrees': [_P, _P, _L, _P, _P],
-    'dc_sort_keys': [_P, _P, _L, _I, _P, _SZP, _P],
+    'dc_sort_keys': [_P, _P, _L, _I, _I, _P, _SZP, _P],
     'dc_exclusive_sum_i32_i64': [_P, _P, _L, _P, _SZP, _P],
     'dc_transpose_widths': [_P, _L, _L, _P, _P, _P],
     'dc_transpose_fill': [_P, _L, _L, _P, _P, _P],

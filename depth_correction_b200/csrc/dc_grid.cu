@@ -151,11 +151,13 @@ extern "C" int dc_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const 
   return DC_OK;
 }
 
-extern "C" int dc_sort_keys(const uint64_t* keys_in, uint64_t* keys_out, int64_t n, int end_bit, void* temp,
-                            size_t* temp_bytes, void* stream) {
-  if (end_bit < 1) end_bit = 1;
+extern "C" int dc_sort_keys(const uint64_t* keys_in, uint64_t* keys_out, int64_t n, int begin_bit, int end_bit,
+                            void* temp, size_t* temp_bytes, void* stream) {
+  if (begin_bit < 0) begin_bit = 0;
   if (end_bit > 64) end_bit = 64;
-  DC_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(temp, *temp_bytes, keys_in, keys_out, n, 0, end_bit, (cudaStream_t)stream));
+  if (end_bit <= begin_bit) end_bit = begin_bit + 1;
+  DC_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(temp, *temp_bytes, keys_in, keys_out, n, begin_bit, end_bit,
+                                               (cudaStream_t)stream));
   return DC_OK;
 }
 

@@ -1,0 +1,276 @@
+// Kernel 1, kNN / kNN-within-r mode: k-nearest SELECTION on the cell-sorted map.
+// Replaces cKDTree.query(k, distance_upper_bound=r) (nearest_neighbors.py:48-49).
+//
+// One thread per query (queries are cell-sorted, so the lanes of a warp read the same candidate rows and
+// the 32-byte candidate records are served by L1).  No per-thread candidate list is kept: the k nearest
+// are found by a two-level histogram select over the squared distances, with the counters in shared
+// memory (32 bins x 128 threads, private columns, no atomics):
+//   1. grow the block of (2 rho + 1)^3 cells until at least k candidates lie inside the radius rho * cell
+//      that the block is guaranteed to cover (or the r bound / the whole grid is reached), histogramming
+//      d2 in 32 linear bins on the way (d2 of points on a surface is uniformly distributed);
+//   2. re-histogram the bin that contains the k-th distance into 32 sub-bins (1024 effective bins);
+//   3. emit every candidate below the boundary sub-bin, and the t smallest of the boundary sub-bin
+//      (almost always 1-2 points) through an 8-entry register list ordered by (d2, sorted index).
+// Each pass recomputes d2 with the identical non-fused instruction sequence, so the classification of a
+// candidate is the same in every pass and the selection is exact.  Rows are emitted UNSORTED (the step
+// kernels only need the set); dc_knn_sort_rows orders them by distance when the reference layout
+// (distance-sorted rows, nearest_neighbors.py:48) is exported.
+#include "dc_common.cuh"
+#include "dc_grid.cuh"
+
+#define KNN_THREADS 128
+#define KNN_BINS 64
+
+__device__ __forceinline__ bool knn_less(double a, int ja, double b, int jb) { return a < b || (a == b && ja < jb); }
+
+template <typename F>
+__device__ __forceinline__ void knn_scan(const dc_grid& g, const uint64_t* __restrict__ pkeys, int64_t n,
+                                         const int32_t* __restrict__ cell_start, const dc_point* __restrict__ P,
+                                         const dc_point& pq, int c0, int c1, int c2, int rho, F&& f) {
+  for (int e2 = -rho; e2 <= rho; ++e2) {
+    for (int e1 = -rho; e1 <= rho; ++e1) {
+      int lo, hi;
+      dc_row_range(g, pkeys, n, cell_start, c0 - rho, c0 + rho, c1 + e1, c2 + e2, lo, hi);
+      for (int j = lo; j < hi; ++j) {
+        const dc_point pj = dc_ld_point(P + j);
+        f(j, dc_dist2(pj, pq));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_select_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
+                  const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
+                  const int32_t* __restrict__ cell_start, int k, double r2cap, int max_ring,
+                  int32_t* __restrict__ ell_idx, double* __restrict__ ell_d2) {
+  __shared__ unsigned short hist[KNN_BINS][KNN_THREADS];
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int32_t* out_j = ell_idx + (q >> 5) * (int64_t)k * DC_SLICE + lane;
+  double* out_d = ell_d2 ? ell_d2 + (q >> 5) * (int64_t)k * DC_SLICE + lane : nullptr;
+  int cnt = 0;
+  if (q < nq) {
+    unsigned short* h = &hist[0][threadIdx.x];
+    const dc_point pq = dc_ld_point(Q + q);
+    int c0, c1, c2;
+    dc_key_coords(g, qkeys[q], c0, c1, c2);
+    const double slack_cell = g.cell * (1.0 - 1e-9);
+    auto emit = [&](int j, double d2) {
+      out_j[(int64_t)cnt * DC_SLICE] = j;
+      if (out_d) out_d[(int64_t)cnt * DC_SLICE] = d2;
+      ++cnt;
+    };
+    // ---- 1. ring growth + level-1 histogram
+    int rho = 1;
+    double bound2, scale1;
+    unsigned int n_in;
+    for (;;) {
+      if (rho > max_ring) rho = max_ring;
+      const bool last = rho >= max_ring;
+      const double reach = rho * slack_cell;
+      bound2 = last ? r2cap : fmin(reach * reach, r2cap);
+      scale1 = (double)KNN_BINS / bound2;
+#pragma unroll
+      for (int b = 0; b < KNN_BINS; ++b) h[b * KNN_THREADS] = (unsigned short)0;
+      n_in = 0u;
+      knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
+        if (d2 < bound2) {
+          int b = __double2int_rz(d2 * scale1);
+          b = b > KNN_BINS - 1 ? KNN_BINS - 1 : b;
+          { const unsigned short v = h[b * KNN_THREADS]; h[b * KNN_THREADS] = v == 65535 ? v : (unsigned short)(v + 1); }
+          ++n_in;
+        }
+      });
+      if (n_in >= (unsigned int)k || last) break;
+      rho = rho < 4 ? rho + 1 : rho * 2;
+    }
+    if (n_in <= (unsigned int)k) {
+      // everything inside the bound is a neighbour (fewer than k exist within r / in the map)
+      knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
+        if (d2 < bound2) emit(j, d2);
+      });
+    } else {
+      // ---- level 1: bin of the k-th distance
+      unsigned int c_lo = 0u, cnt1 = 0u;
+      int b1 = 0;
+      for (; b1 < KNN_BINS; ++b1) {
+        cnt1 = h[b1 * KNN_THREADS];
+        if (c_lo + cnt1 >= (unsigned int)k) break;
+        c_lo += cnt1;
+      }
+      int b2 = KNN_BINS;          // boundary sub-bin; KNN_BINS = "no second level: bin b1 is the boundary set"
+      unsigned int cnt2 = cnt1;
+      const bool lvl2 = cnt1 > 8u && c_lo + cnt1 > (unsigned int)k;
+      if (lvl2) {
+        // ---- 2. level-2 histogram inside bin b1
+#pragma unroll
+        for (int b = 0; b < KNN_BINS; ++b) h[b * KNN_THREADS] = (unsigned short)0;
+        knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
+          if (d2 < bound2) {
+            const double s = d2 * scale1;
+            int b = __double2int_rz(s);
+            b = b > KNN_BINS - 1 ? KNN_BINS - 1 : b;
+            if (b == b1) {
+              int bb = __double2int_rz((s - (double)b1) * (double)KNN_BINS);
+              bb = bb < 0 ? 0 : (bb > KNN_BINS - 1 ? KNN_BINS - 1 : bb);
+              { const unsigned short v = h[bb * KNN_THREADS]; h[bb * KNN_THREADS] = v == 65535 ? v : (unsigned short)(v + 1); }
+            }
+          }
+        });
+        for (b2 = 0; b2 < KNN_BINS; ++b2) {
+          cnt2 = h[b2 * KNN_THREADS];
+          if (c_lo + cnt2 >= (unsigned int)k) break;
+          c_lo += cnt2;
+        }
+      }
+      // ---- 3. emit: everything below the boundary (sub-)bin, and the t smallest of the boundary sub-bin
+      const unsigned int t = (unsigned int)k - c_lo;     // how many of the cnt2 boundary candidates are neighbours
+      const bool take_all = (t == cnt2);
+      const bool use_list = !take_all && cnt2 <= 8u;
+      double bd[8];
+      int bj[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { bd[i] = INFINITY; bj[i] = 0x7fffffff; }
+      knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
+        if (d2 < bound2) {
+          const double s = d2 * scale1;
+          int b = __double2int_rz(s);
+          b = b > KNN_BINS - 1 ? KNN_BINS - 1 : b;
+          if (b < b1) {
+            emit(j, d2);
+          } else if (b == b1) {
+            bool boundary = true;
+            if (lvl2) {
+              int bb = __double2int_rz((s - (double)b1) * (double)KNN_BINS);
+              bb = bb < 0 ? 0 : (bb > KNN_BINS - 1 ? KNN_BINS - 1 : bb);
+              if (bb < b2) emit(j, d2);
+              boundary = (bb == b2);
+            }
+            if (boundary) {
+              if (take_all) {
+                emit(j, d2);
+              } else if (use_list) {
+#pragma unroll
+                for (int i = 7; i >= 0; --i) {
+                  const bool lt_prev = (i > 0) ? knn_less(d2, j, bd[i > 0 ? i - 1 : 0], bj[i > 0 ? i - 1 : 0]) : false;
+                  if (lt_prev) { bd[i] = bd[i > 0 ? i - 1 : 0]; bj[i] = bj[i > 0 ? i - 1 : 0]; }
+                  else if (knn_less(d2, j, bd[i], bj[i])) { bd[i] = d2; bj[i] = j; }
+                }
+              }
+            }
+          }
+        }
+      });
+      if (!take_all) {
+        if (use_list) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if ((unsigned int)i < t) emit(bj[i], bd[i]);
+        } else {
+          // more than 8 candidates share the boundary sub-bin (exact ties / duplicates): repeated minimum
+          // selection in (d2, index) order -- O(t * candidates), rare
+          double last_d = -1.0;
+          int last_j = -1;
+          for (unsigned int s_ = 0; s_ < t; ++s_) {
+            double best_d = INFINITY;
+            int best_j = 0x7fffffff;
+            knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
+              if (d2 < bound2) {
+                const double s = d2 * scale1;
+                int b = __double2int_rz(s);
+                b = b > KNN_BINS - 1 ? KNN_BINS - 1 : b;
+                if (b == b1) {
+                  int bb = b2;
+                  if (lvl2) {
+                    bb = __double2int_rz((s - (double)b1) * (double)KNN_BINS);
+                    bb = bb < 0 ? 0 : (bb > KNN_BINS - 1 ? KNN_BINS - 1 : bb);
+                  }
+                  if (bb == b2 && knn_less(last_d, last_j, d2, j) && knn_less(d2, j, best_d, best_j)) {
+                    best_d = d2;
+                    best_j = j;
+                  }
+                }
+              }
+            });
+            emit(best_j, best_d);
+            last_d = best_d;
+            last_j = best_j;
+          }
+        }
+      }
+    }
+  }
+  if (nq > 0 && (q >> 5) <= ((nq - 1) >> 5)) {
+    for (int c = cnt; c < k; ++c) {
+      out_j[(int64_t)c * DC_SLICE] = -1;
+      if (out_d) out_d[(int64_t)c * DC_SLICE] = INFINITY;
+    }
+  }
+}
+
+extern "C" int dc_knn(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
+                      const dc_grid_spec* spec, const int32_t* cell_start, int k, double r, int32_t* ell_idx,
+                      double* ell_d2, void* stream) {
+  if (nq <= 0) return DC_OK;
+  if (k < 1) return dc_set_error(DC_ERR_ARG, "dc_knn: k must be positive");
+  dc_grid g;
+  int rc = dc_make_grid(spec, &g);
+  if (rc) return rc;
+  int max_ring = g.d[0] > g.d[1] ? g.d[0] : g.d[1];
+  max_ring = max_ring > g.d[2] ? max_ring : g.d[2];
+  // finite cap on every squared distance inside (or clamped into) the grid box, used when there is no r
+  const double ex = g.d[0] * g.cell, ey = g.d[1] * g.cell, ez = g.d[2] * g.cell;
+  double r2cap = 16.0 * (ex * ex + ey * ey + ez * ez) + 1.0;
+  if (r > 0.0) {
+    r2cap = r * r;      // cKDTree: d2 < distance_upper_bound ** 2, strict
+    const int rr = (int)ceil(r / g.cell);
+    if (rr < max_ring) max_ring = rr;
+  }
+  if (max_ring < 1) max_ring = 1;
+  const int blocks = dc_blocks(((nq + 31) / 32) * 32, KNN_THREADS);
+  knn_select_kernel<<<blocks, KNN_THREADS, 0, (cudaStream_t)stream>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq,
+                                                                      g, cell_start, k, r2cap, max_ring, ell_idx, ell_d2);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Order every row by (d2, index): the reference returns distance-sorted rows.  Export path only.
+// ---------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void knn_sort_rows_kernel(int k, int32_t* __restrict__ ell_idx, double* __restrict__ ell_d2, int64_t nq) {
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int lane = (int)(q & 31);
+  int32_t* pj = ell_idx + (q >> 5) * (int64_t)k * DC_SLICE + lane;
+  double* pd = ell_d2 + (q >> 5) * (int64_t)k * DC_SLICE + lane;
+  double d[KMAX];
+  int j[KMAX];
+  int m = 0;
+  for (int c = 0; c < k; ++c) {
+    const int jj = pj[(int64_t)c * DC_SLICE];
+    if (jj < 0) continue;
+    const double dd = pd[(int64_t)c * DC_SLICE];
+    int pos = m++;
+    while (pos > 0 && knn_less(dd, jj, d[pos - 1], j[pos - 1])) { d[pos] = d[pos - 1]; j[pos] = j[pos - 1]; --pos; }
+    d[pos] = dd;
+    j[pos] = jj;
+  }
+  for (int c = 0; c < k; ++c) {
+    pj[(int64_t)c * DC_SLICE] = c < m ? j[c] : -1;
+    pd[(int64_t)c * DC_SLICE] = c < m ? d[c] : INFINITY;
+  }
+}
+
+extern "C" int dc_knn_sort_rows(int k, int32_t* ell_idx, double* ell_d2, int64_t nq, void* stream) {
+  if (nq <= 0) return DC_OK;
+  if (k < 1 || k > 1024) return dc_set_error(DC_ERR_ARG, "dc_knn_sort_rows: k must be in [1, 1024]");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = dc_blocks(nq, 128);
+  if (k <= 32) knn_sort_rows_kernel<32><<<blocks, 128, 0, st>>>(k, ell_idx, ell_d2, nq);
+  else if (k <= 128) knn_sort_rows_kernel<128><<<blocks, 128, 0, st>>>(k, ell_idx, ell_d2, nq);
+  else knn_sort_rows_kernel<1024><<<blocks, 128, 0, st>>>(k, ell_idx, ell_d2, nq);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}

@@ -103,121 +103,7 @@ extern "C" int dc_radius_fill(const void* P, const uint64_t* pkeys, int64_t n, c
 // The k best (d2, original index) pairs live in a per-thread sorted list in local memory
 // (L1-resident); candidates that lose against the current k-th are rejected with one compare.
 // ---------------------------------------------------------------------------------------------
-template <int KMAX>
-struct TopK {
-  double d[KMAX];
-  int j[KMAX];       // sorted-space index
-  int cnt;
-};
-
-template <int KMAX>
-__device__ __forceinline__ void topk_insert(TopK<KMAX>& t, int k, double d2, int j, long long tag,
-                                            const dc_point* __restrict__ P) {
-  if (t.cnt == k) {
-    const double dw = t.d[k - 1];
-    if (d2 > dw) return;
-    if (d2 == dw && tag > P[t.j[k - 1]].tag) return;
-  }
-  int pos = (t.cnt < k) ? t.cnt++ : k - 1;
-  while (pos > 0) {
-    const double dp = t.d[pos - 1];
-    if (dp < d2) break;
-    if (dp == d2 && P[t.j[pos - 1]].tag < tag) break;
-    t.d[pos] = dp;
-    t.j[pos] = t.j[pos - 1];
-    --pos;
-  }
-  t.d[pos] = d2;
-  t.j[pos] = j;
-}
-
-template <int KMAX>
-__global__ void __launch_bounds__(NN_THREADS)
-knn_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
-           const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
-           const int32_t* __restrict__ cell_start, int k, double r2, int max_ring, int32_t* __restrict__ ell_idx,
-           double* __restrict__ ell_d2) {
-  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const int64_t base = (q >> 5) * (int64_t)k * DC_SLICE;
-  if (q >= nq) {
-    if (nq > 0 && (q >> 5) <= ((nq - 1) >> 5))
-      for (int c = 0; c < k; ++c) {
-        ell_idx[base + (int64_t)c * DC_SLICE + lane] = -1;
-        if (ell_d2) ell_d2[base + (int64_t)c * DC_SLICE + lane] = INFINITY;
-      }
-    return;
-  }
-  TopK<KMAX> t;
-  t.cnt = 0;
-  const dc_point pq = dc_ld_point(Q + q);
-  int c0, c1, c2;
-  dc_key_coords(g, qkeys[q], c0, c1, c2);
-  // a query outside the grid box is clamped into a border cell; its distance to the box adds to the bound
-  const double slack_cell = g.cell * (1.0 - 1e-9);
-  for (int rho = 0; rho <= max_ring; ++rho) {
-    for (int e2 = -rho; e2 <= rho; ++e2) {
-      for (int e1 = -rho; e1 <= rho; ++e1) {
-        const bool full_row = (e2 == -rho || e2 == rho || e1 == -rho || e1 == rho);
-        const int nseg = full_row ? 1 : 2;   // interior rows only contribute their two end cells
-        for (int sgm = 0; sgm < nseg; ++sgm) {
-          int a, b;
-          if (full_row) { a = c0 - rho; b = c0 + rho; }
-          else if (sgm == 0) { a = b = c0 - rho; }
-          else { a = b = c0 + rho; }
-          int lo, hi;
-          dc_row_range(g, pkeys, n, cell_start, a, b, c1 + e1, c2 + e2, lo, hi);
-          for (int j = lo; j < hi; ++j) {
-            const dc_point pj = dc_ld_point(P + j);
-            const double d2 = dc_dist2(pj, pq);
-            if (d2 < r2) topk_insert<KMAX>(t, k, d2, j, pj.tag, P);
-          }
-        }
-      }
-    }
-    if (t.cnt == k) {
-      const double reach = rho * slack_cell;
-      if (t.d[k - 1] < reach * reach) break;
-    }
-  }
-  for (int c = 0; c < k; ++c) {
-    const bool ok = c < t.cnt;
-    ell_idx[base + (int64_t)c * DC_SLICE + lane] = ok ? t.j[c] : -1;
-    if (ell_d2) ell_d2[base + (int64_t)c * DC_SLICE + lane] = ok ? t.d[c] : INFINITY;
-  }
-}
-
-extern "C" int dc_knn(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
-                      const dc_grid_spec* spec, const int32_t* cell_start, int k, double r, int32_t* ell_idx,
-                      double* ell_d2, void* stream) {
-  if (nq <= 0) return DC_OK;
-  if (k < 1 || k > 256) return dc_set_error(DC_ERR_ARG, "dc_knn: k must be in [1, 256]");
-  dc_grid g;
-  int rc = dc_make_grid(spec, &g);
-  if (rc) return rc;
-  int max_ring = g.d[0] > g.d[1] ? g.d[0] : g.d[1];
-  max_ring = max_ring > g.d[2] ? max_ring : g.d[2];
-  double r2 = INFINITY;
-  if (r > 0.0) {
-    r2 = r * r;
-    const int rr = (int)ceil(r / g.cell);
-    if (rr < max_ring) max_ring = rr;
-  }
-  const int blocks = dc_blocks(((nq + 31) / 32) * 32, NN_THREADS);
-  cudaStream_t st = (cudaStream_t)stream;
-#define DC_KNN_CASE(KM)                                                                                          \
-  knn_kernel<KM><<<blocks, NN_THREADS, 0, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq, g, \
-                                                 cell_start, k, r2, max_ring, ell_idx, ell_d2)
-  if (k <= 8) DC_KNN_CASE(8);
-  else if (k <= 16) DC_KNN_CASE(16);
-  else if (k <= 32) DC_KNN_CASE(32);
-  else if (k <= 64) DC_KNN_CASE(64);
-  else if (k <= 128) DC_KNN_CASE(128);
-  else DC_KNN_CASE(256);
-#undef DC_KNN_CASE
-  DC_LAUNCH_CHECK();
-  return DC_OK;
-}
+// (implemented in dc_knn.cu)
 
 // ---------------------------------------------------------------------------------------------
 // Export / import between sliced-ELL (sorted space, int32) and the reference layout
@@ -363,10 +249,21 @@ extern "C" int dc_graph_degrees(const int64_t* slice_ptr, const int32_t* ell_idx
 __global__ void graph_edges_kernel(const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ ell_idx,
                                    int64_t n_rows, const int64_t* __restrict__ edge_offset, uint64_t* __restrict__ pairs) {
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (row >= n_rows) return;
+  if ((row >> 5) > ((n_rows - 1) >> 5)) return;
   const int lane = (int)(row & 31);
   const int64_t base = slice_ptr[row >> 5];
   const int width = (int)((slice_ptr[(row >> 5) + 1] - base) >> 5);
+  if (!edge_offset) {
+    // slot mode: one pair per ELL slot (coalesced, no prefix sum); padding gets dst = n_rows, which sorts last
+    const uint64_t pad = ((uint64_t)(uint32_t)n_rows << 32) | 0xffffffffull;
+    for (int c = 0; c < width; ++c) {
+      const int64_t e = base + (int64_t)c * DC_SLICE + lane;
+      const int j = row < n_rows ? ell_idx[e] : -1;
+      pairs[e] = j >= 0 ? (((uint64_t)(uint32_t)j << 32) | (uint64_t)(uint32_t)row) : pad;
+    }
+    return;
+  }
+  if (row >= n_rows) return;
   int64_t e = edge_offset[row];
   for (int c = 0; c < width; ++c) {
     const int j = ell_idx[base + (int64_t)c * DC_SLICE + lane];
@@ -377,7 +274,8 @@ __global__ void graph_edges_kernel(const int64_t* __restrict__ slice_ptr, const 
 extern "C" int dc_graph_edges(const int64_t* slice_ptr, const int32_t* ell_idx, int64_t n_rows,
                               const int64_t* edge_offset, uint64_t* pairs, void* stream) {
   if (n_rows <= 0) return DC_OK;
-  graph_edges_kernel<<<dc_blocks(n_rows, 128), 128, 0, (cudaStream_t)stream>>>(slice_ptr, ell_idx, n_rows, edge_offset, pairs);
+  const int blocks = dc_blocks(((n_rows + 31) / 32) * 32, 128);
+  graph_edges_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(slice_ptr, ell_idx, n_rows, edge_offset, pairs);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

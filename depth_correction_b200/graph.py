@@ -81,7 +81,7 @@ class SortedMap(object):
         ids = torch.empty(n, dtype=torch.int32, device=dev)
         skeys = torch.empty(n, dtype=torch.int64, device=dev)
         L.call('dc_cell_keys', L.ptr(points), L.dtype_code(points.dtype), n, ctypes.byref(spec), L.ptr(keys), L.ptr(ids), st)
-        L.call_with_temp('dc_sort_keys', dev, L.ptr(keys), L.ptr(skeys), n, max(1, int(n_cells - 1).bit_length()), after=(st,))
+        L.call_with_temp('dc_sort_keys', dev, L.ptr(keys), L.ptr(skeys), n, 0, max(1, int(n_cells - 1).bit_length()), after=(st,))
         n_occ = int((skeys[1:] != skeys[:-1]).sum().item()) + 1
         return n / n_occ
 
@@ -161,7 +161,8 @@ class Graph(object):
         self.slice_ptr = slice_ptr
         self.ell_idx = ell_idx
         self.n_rows = n_rows
-        self.width = width            # K of the reference layout (max row length / k)
+        self._width = width           # K of the reference layout (max row length / k); None = computed on demand
+        self._in_degree = None
         self.q_order = q_order if q_order is not None else smap.order
         self.self_query = q_order is None
         self.ell_d2 = ell_d2
@@ -169,11 +170,26 @@ class Graph(object):
         self.symmetric = symmetric
         self.k, self.r = k, r
         self._transposed = None
+        self._rows_sorted = False
         self._step_cache = {}
 
+    @property
+    def width(self):
+        if self._width is None:
+            deg = self._in_degree if self._in_degree is not None else self.degrees()
+            self._width = int(deg.max().item()) if self.n_rows > 0 else 0
+        return self._width
+
     # ---- reference layout views ---------------------------------------------------------------
+    def _sort_knn_rows(self):
+        """kNN rows come out of the selection kernel unordered; the reference layout is distance-sorted."""
+        if self.mode == 'knn' and not self._rows_sorted and self.n_rows > 0:
+            L.call('dc_knn_sort_rows', self.width, L.ptr(self.ell_idx), L.ptr(self.ell_d2), self.n_rows, L.stream())
+        self._rows_sorted = True
+
     def neighbors(self):
         """int64 [n_rows, K] in original order, -1 = missing (what nearest_neighbors() returns)."""
+        self._sort_knn_rows()
         dev = self.map.device
         K = self.width
         out = torch.empty((self.n_rows, K), dtype=torch.int64, device=dev)
@@ -190,6 +206,7 @@ class Graph(object):
         """fp64 [n_rows, k] (inf = missing) for kNN graphs, None for radius graphs (nearest_neighbors.py:51)."""
         if self.ell_d2 is None:
             return None
+        self._sort_knn_rows()
         out = torch.empty((self.n_rows, self.width), dtype=torch.float64, device=self.map.device)
         if self.n_rows > 0:
             L.call('dc_ell_to_dist', self.width, L.ptr(self.ell_d2), L.ptr(self.ell_idx), self.n_rows,
@@ -219,27 +236,25 @@ class Graph(object):
         dev = self.map.device
         st = L.stream()
         n = self.n_rows
-        deg = self.degrees()
-        offs = torch.empty(n + 1, dtype=torch.int64, device=dev)
-        L.call_with_temp('dc_exclusive_sum_i32_i64', dev, L.ptr(deg), L.ptr(offs), n, after=(st,))
-        n_edges = int(offs[-1].item())
-        pairs = torch.empty(max(n_edges, 1), dtype=torch.int64, device=dev)
-        pairs_sorted = torch.empty(max(n_edges, 1), dtype=torch.int64, device=dev)
-        L.call('dc_graph_edges', L.ptr(self.slice_ptr), L.ptr(self.ell_idx), n, L.ptr(offs), L.ptr(pairs), st)
-        bits = 32 + max(1, int(max(n - 1, 1)).bit_length())
-        if n_edges > 0:
-            L.call_with_temp('dc_sort_keys', dev, L.ptr(pairs), L.ptr(pairs_sorted), n_edges, bits, after=(st,))
+        # one (dst << 32 | src) pair per ELL slot (padding: dst = n, sorts last); the radix sort is stable, so
+        # sorting the dst bits alone gives every transposed row in a deterministic order, in 3-4 passes
+        m = self.ell_idx.numel()
+        pairs = torch.empty(m, dtype=torch.int64, device=dev)
+        pairs_sorted = torch.empty(m, dtype=torch.int64, device=dev)
+        L.call('dc_graph_edges', L.ptr(self.slice_ptr), L.ptr(self.ell_idx), n, None, L.ptr(pairs), st)
+        bits = 32 + max(1, int(n).bit_length())
+        L.call_with_temp('dc_sort_keys', dev, L.ptr(pairs), L.ptr(pairs_sorted), m, 32, bits, after=(st,))
         del pairs
         indeg = torch.empty(n, dtype=torch.int32, device=dev)
         sw = torch.zeros(_n_slices(n), dtype=torch.int32, device=dev)
-        L.call('dc_transpose_widths', L.ptr(pairs_sorted), n_edges, n, L.ptr(indeg), L.ptr(sw), st)
+        L.call('dc_transpose_widths', L.ptr(pairs_sorted), m, n, L.ptr(indeg), L.ptr(sw), st)
         sp = torch.empty(_n_slices(n) + 1, dtype=torch.int64, device=dev)
         L.call_with_temp('dc_ell_offsets', dev, L.ptr(sw), _n_slices(n), L.ptr(sp), after=(st,))
-        total = int(sp[-1].item())
+        total = int(sp[-1].item())           # the one host read-back of the transpose
         idx_t = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-        L.call('dc_transpose_fill', L.ptr(pairs_sorted), n_edges, n, L.ptr(sp), L.ptr(idx_t), st)
-        width = int(indeg.max().item()) if n > 0 else 0
-        self._transposed = Graph(self.map, sp, idx_t, n, width, mode='transposed', symmetric=False)
+        L.call('dc_transpose_fill', L.ptr(pairs_sorted), m, n, L.ptr(sp), L.ptr(idx_t), st)
+        self._transposed = Graph(self.map, sp, idx_t, n, None, mode='transposed', symmetric=False)
+        self._transposed._in_degree = indeg
         self._transposed._transposed = self
         return self._transposed
 
@@ -270,12 +285,17 @@ def _knn_cell_size(points, k, r, bounds):
         c0 = float(r)
     else:
         c0 = max(max(h - l for l, h in zip(lo, hi)) / 256.0, 1e-9)
-    target = max(k / 4.0, 2.0)
-    for _ in range(3):
+    # a disc of radius c on a surface with `occ` points per c^2 holds pi * occ points: occ ~ 0.45 k makes the
+    # first ring of cells (guaranteed reach c) contain the k nearest for a typical query
+    target = max(0.45 * k, 2.0)
+    for _ in range(4):
         occ = SortedMap.occupancy_of(points, lo, hi, c0)
-        if occ <= 2.0 * target:
+        if 0.75 * target <= occ <= 1.6 * target:
             break
-        c0 = c0 * max(math.sqrt(target / occ), 1.0 / 8.0)
+        c0 = c0 * min(max(math.sqrt(target / occ), 1.0 / 8.0), 8.0)
+        if r and c0 > r:
+            c0 = float(r)
+            break
     return c0
 
 
@@ -317,8 +337,9 @@ def search(points, query=None, k=None, r=None, cell=None):
     sp = torch.empty(ns + 1, dtype=torch.int64, device=dev)
     L.call_with_temp('dc_ell_offsets', dev, L.ptr(sw), ns, L.ptr(sp), after=(st,))
     total = int(sp[-1].item())
-    width = int(counts[:nq].max().item()) if nq > 0 else 0
     idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
     L.call('dc_radius_fill', L.ptr(smap.P), L.ptr(smap.keys), n, L.ptr(Q), L.ptr(qkeys), nq, spec,
            L.ptr(smap.cell_start), float(r), L.ptr(sp), L.ptr(idx), st)
-    return Graph(smap, sp, idx, nq, width, q_order=qorder, mode='radius', symmetric=self_query, k=None, r=r)
+    g = Graph(smap, sp, idx, nq, None, q_order=qorder, mode='radius', symmetric=self_query, k=None, r=r)
+    g._in_degree = counts[:nq]       # row lengths; the padded width K = max is only needed for export
+    return g

@@ -100,10 +100,15 @@ int dc_radius_fill(const void* P, const uint64_t* pkeys, int64_t n, const void* 
                    int32_t* ell_idx, void* stream);
 
 /* kNN (r <= 0) or kNN within r (strict <, like cKDTree's distance_upper_bound): fixed-width ELL
- * (slice_ptr[t] = 32*k*t), entries ordered by (d^2, original index); ell_d2 optional. */
+ * (slice_ptr[t] = 32*k*t) holding the k nearest of every query in NO particular order (the step kernels
+ * only need the set); ell_d2 (optional) receives the squared distances.  Exact ties at the k-th distance
+ * are broken by the smaller sorted-space index. */
 int dc_knn(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
            const dc_grid_spec* spec_host, const int32_t* cell_start, int k, double r, int32_t* ell_idx, double* ell_d2,
            void* stream);
+/* order every kNN row by (d^2, index) in place: cKDTree.query returns distance-sorted rows
+ * (nearest_neighbors.py:48); needed only when the reference layout is exported */
+int dc_knn_sort_rows(int k, int32_t* ell_idx, double* ell_d2, int64_t nq, void* stream);
 
 /* export to the reference layout: out[order_q[row], c] = order_p[ell(row, c)] (int64, -1 padding), K columns */
 int dc_ell_to_padded(const int64_t* slice_ptr, const int32_t* ell_idx, int64_t nq,
@@ -126,8 +131,10 @@ int dc_graph_edges(const int64_t* slice_ptr, const int32_t* ell_idx, int64_t n_r
                    const int64_t* edge_offset, uint64_t* pairs, void* stream);
 int dc_graph_degrees(const int64_t* slice_ptr, const int32_t* ell_idx, int64_t n_rows,
                      int32_t* out_degree, void* stream);
-int dc_sort_keys(const uint64_t* keys_in, uint64_t* keys_out, int64_t n, int end_bit, void* temp, size_t* temp_bytes,
-                 void* stream);
+/* stable radix sort on key bits [begin_bit, end_bit): edge pairs arrive ordered by src, so sorting the
+ * dst bits alone (begin_bit = 32) yields (dst, src) order in 3-4 passes */
+int dc_sort_keys(const uint64_t* keys_in, uint64_t* keys_out, int64_t n, int begin_bit, int end_bit, void* temp,
+                 size_t* temp_bytes, void* stream);
 int dc_exclusive_sum_i32_i64(const int32_t* in, int64_t* out, int64_t n, void* temp, size_t* temp_bytes, void* stream);
 int dc_transpose_widths(const uint64_t* pairs_sorted, int64_t n_edges, int64_t n_cols, int32_t* in_degree,
                         int32_t* slice_width, void* stream);
