@@ -31,7 +31,18 @@ __device__ __forceinline__ void knn_scan(const dc_grid& g, const uint64_t* __res
     for (int e1 = -rho; e1 <= rho; ++e1) {
       int lo, hi;
       dc_row_range(g, pkeys, n, cell_start, c0 - rho, c0 + rho, c1 + e1, c2 + e2, lo, hi);
-      for (int j = lo; j < hi; ++j) {
+      // four independent candidate loads in flight per thread (the loop is latency bound otherwise)
+      int j = lo;
+      for (; j + 4 <= hi; j += 4) {
+        const dc_point p0 = dc_ld_point(P + j), p1 = dc_ld_point(P + j + 1);
+        const dc_point p2 = dc_ld_point(P + j + 2), p3 = dc_ld_point(P + j + 3);
+        const double d0 = dc_dist2(p0, pq), d1 = dc_dist2(p1, pq), d2 = dc_dist2(p2, pq), d3 = dc_dist2(p3, pq);
+        f(j, d0);
+        f(j + 1, d1);
+        f(j + 2, d2);
+        f(j + 3, d3);
+      }
+      for (; j < hi; ++j) {
         const dc_point pj = dc_ld_point(P + j);
         f(j, dc_dist2(pj, pq));
       }

@@ -290,7 +290,7 @@ def _knn_cell_size(points, k, r, bounds):
     target = max(0.45 * k, 2.0)
     for _ in range(4):
         occ = SortedMap.occupancy_of(points, lo, hi, c0)
-        if 0.75 * target <= occ <= 1.6 * target:
+        if 0.8 * target <= occ <= 1.25 * target:
             break
         c0 = c0 * min(max(math.sqrt(target / occ), 1.0 / 8.0), 8.0)
         if r and c0 > r:
