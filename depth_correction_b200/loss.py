@@ -127,6 +127,16 @@ def _fused_reduced(loss_fun, cloud, mask, kw):
     return out, _LazyLossCloud(cloud, state, mask)
 
 
+def fused_sum_count(cloud, mask=None, loss='min_eigval_loss', sqrt=False, normalization=False):
+    """Tensor [2] = (sum of per-point losses over `mask`, number of masked points) from the fused kernels, with
+    autograd history.  Building block of multi-GPU reductions (parallel.reduce_step): the mean over all ranks
+    is sum-of-sums / sum-of-counts."""
+    assert _is_fusable(cloud), 'fused_sum_count needs a lazy global cloud with a fixed graph on the GPU'
+    loss_fun = trace_loss if loss in ('trace_loss', trace_loss) else min_eigval_loss
+    out, _ = _fused_reduced(loss_fun, cloud, mask, dict(sqrt=sqrt, normalization=normalization))
+    return out
+
+
 def _finish(cloud, loss, mask, offset, sqrt, reduction, inlier_max_loss, inlier_ratio, inlier_loss_mult,
             only_finite, skip_nans):
     """Element-wise tail shared by both losses (loss.py:256-293 / 332-369)."""

@@ -55,6 +55,19 @@ def _yaw_pose(x, y, z, yaw):
     return T
 
 
+def scan_pose(scene, sid, step=1.0):
+    """Ground-truth sensor-to-world pose of scan `sid` (a function of the scan id only, so that every rank of
+    a multi-GPU run can rebuild the poses of all scans without generating their points)."""
+    sensor_z = 1.0 if scene != 'street' else 1.73
+    yaw = 0.05 * np.sin(0.7 * sid)
+    y0 = 0.2 * np.sin(0.3 * sid) if scene != 'street' else 1.5 * np.sin(0.02 * sid)
+    return _yaw_pose(step * sid, y0, sensor_z, yaw)
+
+
+def make_poses(scene, n_scans, step=1.0, first_scan=0):
+    return np.stack([scan_pose(scene, first_scan + k, step) for k in range(n_scans)])
+
+
 def voxel_keep_first(points, grid_res):
     """Keep the first point of every occupied voxel (generator-side density control; plays the
     role of the reference's filter_grid, filters.py:24-82, but deterministic)."""
@@ -80,14 +93,11 @@ def make_sequence(scene='corridor', n_scans=10, pattern='os0-128', seed=0, step=
     """
     el0, az0 = beam_pattern(pattern, rings, azimuths)
     planes = scene_planes(scene)
-    sensor_z = 1.0 if scene != 'street' else 1.73
     scans, poses_gt, poses_init = [], [], []
     for k in range(n_scans):
         sid = first_scan + k
         rng = np.random.default_rng([seed, sid])
-        yaw = 0.05 * np.sin(0.7 * sid)
-        y0 = 0.2 * np.sin(0.3 * sid) if scene != 'street' else 1.5 * np.sin(0.02 * sid)
-        T = _yaw_pose(step * sid, y0, sensor_z, yaw)
+        T = scan_pose(scene, sid, step)
         el = el0 + angle_jitter * rng.standard_normal(el0.shape)
         az = az0 + angle_jitter * rng.standard_normal(az0.shape)
         d_local = np.stack([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)], axis=1)
