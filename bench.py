@@ -214,19 +214,29 @@ def run_ours(args):
         return
 
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not os.environ.get('DC_BENCH_NO_SAMPLER'):
+        sampler.start()
     timers = []
     launches0 = L.launch_count
-    L.profile = {}
+    L.profile = None if os.environ.get('DC_BENCH_NO_PROFILE') else {}
     sync()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
+    prof = None
+    if os.environ.get('DC_BENCH_CPROFILE'):
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     t0.record()
     for _ in range(args.steps):
         loss, ns = one_step(dc, clouds, poses, deltas, model, cfg, timers=timers, local=local)
         gl = loss.detach()
     t1.record()
     sync()
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats('tottime').print_stats(14)
     kernel_ms = L.collect_profile()
     L.profile = None
     launches = L.launch_count - launches0

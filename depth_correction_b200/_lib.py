@@ -57,6 +57,7 @@ SIGNATURES = {
     'dc_radius_fill': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _D, _P, _P, _P],
     'dc_knn': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _I, _D, _P, _P, _P],
     'dc_knn_sort_rows': [_I, _P, _P, _L, _P],
+    'dc_knn_distances': [_P, _P, _I, _P, _L, _P, _P],
     'dc_ell_to_padded': [_P, _P, _L, _P, _P, _I, _P, _P],
     'dc_ell_to_dist': [_I, _P, _P, _L, _P, _P, _P],
     'dc_sort_rows': [_P, _L, _I, _P, _SZP, _P],
@@ -79,6 +80,7 @@ SIGNATURES = {
     'dc_eigh3': [_P, _I, _L, _P, _P, _P],
     'dc_eigh3_backward': [_P, _P, _I, _L, _P, _P, _P, _P],
     'dc_normals_angles': [_P, _P, _I, _L, _I, _P, _P, _P],
+    'dc_world_points': [_P, _P, _P, _I, _L, _P, _P, _P],
 }
 
 for _name, _args in SIGNATURES.items():
@@ -142,6 +144,29 @@ def collect_profile():
     return out
 
 
+# Reusable scratch buffers, one per (tag, device), grown to the largest request.  Reuse is stream-ordered
+# (everything runs on the current stream), so a scratch buffer may be handed out again as soon as the
+# kernels that used it have been enqueued.  Keeps multi-GB temporaries (radix-sort double buffers, edge
+# pairs) out of the caching allocator's split/merge churn when the search is repeated.
+_workspace = {}
+
+
+def scratch(tag, numel, dtype, device):
+    nbytes = int(numel) * torch.empty((), dtype=dtype).element_size()
+    key = (tag, str(device))
+    buf = _workspace.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _workspace.pop(key, None)
+        buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _workspace[key] = buf
+    return buf[:nbytes].view(dtype)
+
+
+def release_workspace():
+    _workspace.clear()
+
+
 def call_with_temp(name, device, *args_before_temp, after=()):
     """Two-phase (temp, temp_bytes) protocol: size query with temp == NULL, then the real call."""
     nbytes = ctypes.c_size_t(0)
@@ -149,7 +174,7 @@ def call_with_temp(name, device, *args_before_temp, after=()):
     rc = getattr(_lib, name)(*args_before_temp, None, ctypes.byref(nbytes), *after)
     if rc != 0:
         raise DcError('%s (size query) failed (code %d): %s' % (name, rc, _lib.dc_last_error().decode()))
-    temp = torch.empty(max(int(nbytes.value), 1), dtype=torch.uint8, device=device)
+    temp = scratch('temp:' + name, max(int(nbytes.value), 1), torch.uint8, device)
     nbytes = ctypes.c_size_t(temp.numel())
     call(name, *args_before_temp, ptr(temp), ctypes.byref(nbytes), *after)
     return temp

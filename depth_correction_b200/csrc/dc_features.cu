@@ -226,3 +226,33 @@ extern "C" int dc_normals_angles(const void* dirs, const void* eigvecs, int dtyp
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Points of one scan in the map frame, p = R (vp + depth * dir) + t, evaluated in fp64 from the stored
+// records: cloud.transform(pose).to_points() of preproc.py:108-119 / depth_cloud.py:122-152 for the initial
+// (uncorrected) global cloud that the neighbour search runs on.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void world_points_kernel(const T* __restrict__ vps, const T* __restrict__ dirs, const T* __restrict__ depth,
+                                    int64_t n, const double* __restrict__ pose, double* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double d = (double)depth[i];
+  double x = d * (double)dirs[3 * i], y = d * (double)dirs[3 * i + 1], z = d * (double)dirs[3 * i + 2];
+  if (vps) { x += (double)vps[3 * i]; y += (double)vps[3 * i + 1]; z += (double)vps[3 * i + 2]; }
+  out[3 * i] = pose[0] * x + pose[1] * y + pose[2] * z + pose[3];
+  out[3 * i + 1] = pose[4] * x + pose[5] * y + pose[6] * z + pose[7];
+  out[3 * i + 2] = pose[8] * x + pose[9] * y + pose[10] * z + pose[11];
+}
+
+extern "C" int dc_world_points(const void* vps, const void* dirs, const void* depth, int dtype, int64_t n,
+                               const double* pose, double* out, void* stream) {
+  if (n <= 0) return DC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DC_F32)
+    world_points_kernel<float><<<dc_blocks(n, 256), 256, 0, st>>>((const float*)vps, (const float*)dirs, (const float*)depth, n, pose, out);
+  else
+    world_points_kernel<double><<<dc_blocks(n, 256), 256, 0, st>>>((const double*)vps, (const double*)dirs, (const double*)depth, n, pose, out);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}

@@ -285,3 +285,32 @@ extern "C" int dc_knn_sort_rows(int k, int32_t* ell_idx, double* ell_d2, int64_t
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
+
+// Squared distances of a kNN graph, recomputed from the records with the same instruction sequence the
+// selection used (bit-identical values).  The hot search does not store them (8 bytes per edge would be the
+// largest write of the whole search); they are only needed to export distance-sorted rows and `distances`.
+__global__ void knn_distances_kernel(const dc_point* __restrict__ P, const dc_point* __restrict__ Q, int k,
+                                     const int32_t* __restrict__ ell_idx, int64_t nq, double* __restrict__ ell_d2) {
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ((q >> 5) > ((nq - 1) >> 5)) return;
+  const int lane = (int)(q & 31);
+  const int64_t base = (q >> 5) * (int64_t)k * DC_SLICE + lane;
+  if (q >= nq) {
+    for (int c = 0; c < k; ++c) ell_d2[base + (int64_t)c * DC_SLICE] = INFINITY;
+    return;
+  }
+  const dc_point pq = dc_ld_point(Q + q);
+  for (int c = 0; c < k; ++c) {
+    const int j = ell_idx[base + (int64_t)c * DC_SLICE];
+    ell_d2[base + (int64_t)c * DC_SLICE] = j >= 0 ? dc_dist2(dc_ld_point(P + j), pq) : INFINITY;
+  }
+}
+
+extern "C" int dc_knn_distances(const void* P, const void* Q, int k, const int32_t* ell_idx, int64_t nq, double* ell_d2,
+                                void* stream) {
+  if (nq <= 0) return DC_OK;
+  const int blocks = dc_blocks(((nq + 31) / 32) * 32, 128);
+  knn_distances_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>((const dc_point*)P, (const dc_point*)Q, k, ell_idx, nq, ell_d2);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}

@@ -114,7 +114,7 @@ class DepthCloud(object):
             x = self.get_points()
             self._distances = torch.linalg.norm(x.unsqueeze(dim=1) - x[self.neighbors], dim=-1)
             self._distances_stale = False
-        elif self._distances is None and self._graph is not None and self._graph.ell_d2 is not None:
+        elif self._distances is None and self._graph is not None and self._graph.mode == 'knn':
             self._distances = self._graph.distances()
         return self._distances
 

@@ -10,6 +10,8 @@ kernels write (corrected points, backward stash, per-point loss).  `fused_loss` 
 
 as three kernel launches forward+backward-prologue and one backward launch.
 """
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -39,7 +41,9 @@ class StepState(object):
         assert graph.self_query and graph.n_rows == n
         sizes = [len(c) for c in clouds]
         assert sum(sizes) == n, 'clouds (%i points) do not match the graph (%i points)' % (sum(sizes), n)
-        self.graph = graph
+        # the graph owns this state (graph._step_cache); a weak reference back avoids a reference cycle, so that
+        # dropping the graph frees its device memory immediately instead of at the next cyclic GC
+        self._graph_ref = weakref.ref(graph)
         self.n = n
         self.n_scans = len(clouds)
         self.device = dev
@@ -73,6 +77,12 @@ class StepState(object):
         self.partials = torch.zeros(2 * self.n_blocks + 2, dtype=torch.float64, device=dev)
         self._mask_key = None
         self.generation = 0
+
+    @property
+    def graph(self):
+        g = self._graph_ref()
+        assert g is not None, 'the neighbourhood graph of this step state has been released'
+        return g
 
     def set_loss_mask(self, mask):
         """mask: bool [N] in original (concatenated) order or None (= all points)."""
@@ -116,6 +126,7 @@ class _FusedStep(torch.autograd.Function):
                L.ptr(state.partials), state.partials.numel() * 8, st)
         state.generation += 1
         ctx.state, ctx.generation = state, state.generation
+        ctx.graph = g                 # keeps the graph (and with it the state's buffers) alive until backward
         ctx.args = (poses12, wv, ev, n_terms, model_kind, raw)
         ctx.shapes = (w.shape if w is not None else None, exponent.shape if exponent is not None else None,
                       poses.shape, poses.dtype, poses.device)
@@ -134,7 +145,7 @@ class _FusedStep(torch.autograd.Function):
         dev = state.device
         st = L.stream()
         S = state.n_scans
-        gt = state.graph.transposed()
+        gt = ctx.graph.transposed()
         dw = torch.zeros(max(n_terms, 1), dtype=torch.float64, device=dev)
         dexp = torch.zeros(max(n_terms, 1), dtype=torch.float64, device=dev) if ctx.exp_grad else None
         dposes = torch.zeros((S, 12), dtype=torch.float64, device=dev)

@@ -77,9 +77,9 @@ class SortedMap(object):
         spec, _, n_cells = SortedMap.make_spec(lo, hi, cell)
         dev = points.device
         st = L.stream()
-        keys = torch.empty(n, dtype=torch.int64, device=dev)
-        ids = torch.empty(n, dtype=torch.int32, device=dev)
-        skeys = torch.empty(n, dtype=torch.int64, device=dev)
+        keys = L.scratch('keys', n, torch.int64, dev)
+        ids = L.scratch('ids', n, torch.int32, dev)
+        skeys = L.scratch('skeys', n, torch.int64, dev)
         L.call('dc_cell_keys', L.ptr(points), L.dtype_code(points.dtype), n, ctypes.byref(spec), L.ptr(keys), L.ptr(ids), st)
         L.call_with_temp('dc_sort_keys', dev, L.ptr(keys), L.ptr(skeys), n, 0, max(1, int(n_cells - 1).bit_length()), after=(st,))
         n_occ = int((skeys[1:] != skeys[:-1]).sum().item()) + 1
@@ -99,8 +99,8 @@ class SortedMap(object):
         self.spec, self.axes, self.n_cells = SortedMap.make_spec(lo, hi, self.cell)
         self.key_bits = max(1, int(self.n_cells - 1).bit_length())
 
-        keys = torch.empty(n, dtype=torch.int64, device=dev)     # uint64 bit patterns (< 2^62)
-        ids = torch.empty(n, dtype=torch.int32, device=dev)
+        keys = L.scratch('keys', n, torch.int64, dev)     # uint64 bit patterns (< 2^62)
+        ids = L.scratch('ids', n, torch.int32, dev)
         self.keys = torch.empty(n, dtype=torch.int64, device=dev)
         self.order = torch.empty(n, dtype=torch.int32, device=dev)
         self.P = torch.empty((n, 4), dtype=torch.float64, device=dev)
@@ -163,6 +163,7 @@ class Graph(object):
         self.n_rows = n_rows
         self._width = width           # K of the reference layout (max row length / k); None = computed on demand
         self._in_degree = None
+        self._Q = None                # sorted query records of a cross query (self query: the map's own records)
         self.q_order = q_order if q_order is not None else smap.order
         self.self_query = q_order is None
         self.ell_d2 = ell_d2
@@ -184,6 +185,12 @@ class Graph(object):
     def _sort_knn_rows(self):
         """kNN rows come out of the selection kernel unordered; the reference layout is distance-sorted."""
         if self.mode == 'knn' and not self._rows_sorted and self.n_rows > 0:
+            if self.ell_d2 is None:
+                # the search does not store distances; recompute them (bit-identical) for the export
+                self.ell_d2 = torch.empty(self.ell_idx.numel(), dtype=torch.float64, device=self.map.device)
+                Q = self.map.P if self._Q is None else self._Q
+                L.call('dc_knn_distances', L.ptr(self.map.P), L.ptr(Q), self.width, L.ptr(self.ell_idx), self.n_rows,
+                       L.ptr(self.ell_d2), L.stream())
             L.call('dc_knn_sort_rows', self.width, L.ptr(self.ell_idx), L.ptr(self.ell_d2), self.n_rows, L.stream())
         self._rows_sorted = True
 
@@ -204,7 +211,7 @@ class Graph(object):
 
     def distances(self):
         """fp64 [n_rows, k] (inf = missing) for kNN graphs, None for radius graphs (nearest_neighbors.py:51)."""
-        if self.ell_d2 is None:
+        if self.mode != 'knn':
             return None
         self._sort_knn_rows()
         out = torch.empty((self.n_rows, self.width), dtype=torch.float64, device=self.map.device)
@@ -239,12 +246,11 @@ class Graph(object):
         # one (dst << 32 | src) pair per ELL slot (padding: dst = n, sorts last); the radix sort is stable, so
         # sorting the dst bits alone gives every transposed row in a deterministic order, in 3-4 passes
         m = self.ell_idx.numel()
-        pairs = torch.empty(m, dtype=torch.int64, device=dev)
-        pairs_sorted = torch.empty(m, dtype=torch.int64, device=dev)
+        pairs = L.scratch('pairs', m, torch.int64, dev)
+        pairs_sorted = L.scratch('pairs_sorted', m, torch.int64, dev)
         L.call('dc_graph_edges', L.ptr(self.slice_ptr), L.ptr(self.ell_idx), n, None, L.ptr(pairs), st)
         bits = 32 + max(1, int(n).bit_length())
         L.call_with_temp('dc_sort_keys', dev, L.ptr(pairs), L.ptr(pairs_sorted), m, 32, bits, after=(st,))
-        del pairs
         indeg = torch.empty(n, dtype=torch.int32, device=dev)
         sw = torch.zeros(_n_slices(n), dtype=torch.int32, device=dev)
         L.call('dc_transpose_widths', L.ptr(pairs_sorted), m, n, L.ptr(indeg), L.ptr(sw), st)
@@ -255,7 +261,8 @@ class Graph(object):
         L.call('dc_transpose_fill', L.ptr(pairs_sorted), m, n, L.ptr(sp), L.ptr(idx_t), st)
         self._transposed = Graph(self.map, sp, idx_t, n, None, mode='transposed', symmetric=False)
         self._transposed._in_degree = indeg
-        self._transposed._transposed = self
+        # no back reference: a reference cycle would leave multi-GB graphs to the cyclic garbage collector,
+        # whose timing makes the caching allocator fall back to cudaMalloc at random
         return self._transposed
 
     # ---- import -------------------------------------------------------------------------------
@@ -326,10 +333,11 @@ def search(points, query=None, k=None, r=None, cell=None):
         k = int(k)
         sp = torch.arange(ns + 1, dtype=torch.int64, device=dev) * (L.SLICE * k)
         idx = torch.empty(max(ns * L.SLICE * k, 1), dtype=torch.int32, device=dev)
-        d2 = torch.empty(max(ns * L.SLICE * k, 1), dtype=torch.float64, device=dev)
         L.call('dc_knn', L.ptr(smap.P), L.ptr(smap.keys), n, L.ptr(Q), L.ptr(qkeys), nq, spec, L.ptr(smap.cell_start),
-               k, float(r) if r else 0.0, L.ptr(idx), L.ptr(d2), st)
-        return Graph(smap, sp, idx, nq, k, q_order=qorder, ell_d2=d2, mode='knn', symmetric=False, k=k, r=r)
+               k, float(r) if r else 0.0, L.ptr(idx), None, st)
+        g = Graph(smap, sp, idx, nq, k, q_order=qorder, ell_d2=None, mode='knn', symmetric=False, k=k, r=r)
+        g._Q = None if self_query else Q
+        return g
     counts = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
     sw = torch.zeros(max(ns, 1), dtype=torch.int32, device=dev)
     L.call('dc_radius_count', L.ptr(smap.P), L.ptr(smap.keys), n, L.ptr(Q), L.ptr(qkeys), nq, spec,

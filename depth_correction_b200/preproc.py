@@ -11,6 +11,7 @@ Plane neighbourhoods (RANSAC planes, preproc.py:218-243) are out of scope.
 import numpy as np
 import torch
 
+from . import _lib as _L
 from .config import NeighborhoodType
 from .depth_cloud import DepthCloud
 from .filters import filter_depth, filter_eigenvalue_ratios, filter_eigenvalues, filter_valid_neighbors, within_bounds
@@ -243,9 +244,37 @@ def establish_neighborhoods(dataset=None, clouds=None, poses=None, cloud=None, c
     assert cloud is not None
     if cfg.nn_type != NeighborhoodType.ball:
         raise NotImplementedError('plane neighbourhoods (RANSAC) are out of scope of the B200 hot path')
-    pts = cloud.to_points().detach()
+    pts = _initial_map_points(cloud)
     graph = search(pts, None, k=cfg.nn_k, r=cfg.nn_r)
     return Neighborhoods(graph)
+
+
+def _initial_map_points(cloud):
+    """Points of the (uncorrected) global cloud the graph is built on.  For a lazy cloud on the GPU every scan is
+    moved to the map frame by one dc_world_points launch (fp64 from the stored records); any other cloud goes
+    through the staged to_points()."""
+    scans = getattr(cloud, '_scans', None)
+    if not (isinstance(cloud, GlobalCloud) and scans and cloud._model is None and scans[0].depth.is_cuda
+            and not any(f in cloud.__dict__ for f in ('vps', 'dirs', 'depth'))):
+        return cloud.to_points().detach()
+    dev = scans[0].depth.device
+    poses = cloud.poses_tensor().detach().to(device=dev, dtype=torch.float64).contiguous()
+    out = torch.empty((cloud.size(), 3), dtype=torch.float64, device=dev)
+    st = _L.stream()
+    first = 0
+    keep = []
+    for i, c in enumerate(scans):
+        n = len(c)
+        vps = c.vps.detach()
+        vps = None if vps.shape[0] != n else vps.contiguous()
+        if vps is None and bool(c.vps.any()):
+            vps = c.vps.detach().expand(n, 3).contiguous()
+        dirs, depth = c.dirs.detach().contiguous(), c.depth.detach().contiguous()
+        keep += [vps, dirs, depth]
+        _L.call('dc_world_points', _L.ptr(vps), _L.ptr(dirs), _L.ptr(depth), _L.dtype_code(depth.dtype), n,
+                _L.ptr(poses[i]), _L.ptr(out[first:first + n]), st)
+        first += n
+    return out
 
 
 def compute_neighborhood_features(dataset=None, clouds=None, poses=None, model=None, pose_corrections=None, cloud=None,

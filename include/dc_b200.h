@@ -109,6 +109,10 @@ int dc_knn(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const
 /* order every kNN row by (d^2, index) in place: cKDTree.query returns distance-sorted rows
  * (nearest_neighbors.py:48); needed only when the reference layout is exported */
 int dc_knn_sort_rows(int k, int32_t* ell_idx, double* ell_d2, int64_t nq, void* stream);
+/* squared distances of a kNN graph recomputed from the records (bit-identical to the ones the selection
+ * compared); the training path calls dc_knn with ell_d2 == NULL and never needs them */
+int dc_knn_distances(const void* P, const void* Q, int k, const int32_t* ell_idx, int64_t nq, double* ell_d2,
+                     void* stream);
 
 /* export to the reference layout: out[order_q[row], c] = order_p[ell(row, c)] (int64, -1 padding), K columns */
 int dc_ell_to_padded(const int64_t* slice_ptr, const int32_t* ell_idx, int64_t nq,
@@ -204,6 +208,10 @@ int dc_features_backward(const void* points, int dtype, int64_t n, const int64_t
 int dc_eigh3(const void* cov, int dtype, int64_t n, void* eigvals, void* eigvecs, void* stream);
 int dc_eigh3_backward(const void* eigvals, const void* eigvecs, int dtype, int64_t n, const void* geigvals,
                       const void* geigvecs, void* gcov, void* stream);
+/* points of one scan in the map frame, out[n,3] fp64 = R (vp + depth dir) + t with pose = fp64 4x4 row-major
+ * (device): cloud.transform(pose).to_points() for the initial global cloud (preproc.py:108-119,180).  vps may be NULL. */
+int dc_world_points(const void* vps, const void* dirs, const void* depth, int dtype, int64_t n, const double* pose,
+                    double* out, void* stream);
 /* normals = -sign(dirs . v0) v0, inc = arccos(|dirs . n|) or arccos(-dirs . n)  (depth_cloud.py:401-424) */
 int dc_normals_angles(const void* dirs, const void* eigvecs, int dtype, int64_t n, int use_normal_sign, void* normals,
                       void* inc_angles, void* stream);
