@@ -304,7 +304,8 @@ def run_ours(args):
     alg = {   # algorithmic bytes per launch: every array once per pass, gathers assumed L2-served
         'dc_step_points': n_resident * (36 + 32),
         'dc_step_forward': idx_fwd + n_resident * (32 + 4 + 8 + 64),
-        'dc_step_backward': idx_bwd + n_resident * (32 + 36),
+        'dc_step_backward': idx_bwd + n_resident * (32 + 4 + 24),
+        'dc_step_chain': n_resident * (24 + 36),
     }
     peak, peak_src = peaks()
     kern = {k: v for k, v in kernel_ms.items() if k in alg}

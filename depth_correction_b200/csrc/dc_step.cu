@@ -45,7 +45,7 @@ __global__ void pack_records_kernel(const T* __restrict__ vps, const T* __restri
                                     typename vec4_of<T>::type* __restrict__ rec_vp, uint32_t* __restrict__ rec_meta) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= count) return;
-  const int64_t s = inv_order[first + i];
+  const int64_t s = inv_order ? (int64_t)inv_order[first + i] : first + i;   // NULL: keep the original order
   typename vec4_of<T>::type a, b;
   a.x = dirs[3 * i]; a.y = dirs[3 * i + 1]; a.z = dirs[3 * i + 2]; a.w = depth[i];
   if (vps) { b.x = vps[3 * i]; b.y = vps[3 * i + 1]; b.z = vps[3 * i + 2]; }
@@ -312,53 +312,39 @@ extern "C" int dc_step_forward(const void* points, const uint32_t* rec_meta, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pass C: gather-form backward.  Row j of the TRANSPOSED graph lists every i with j in N(i), so
+// Pass C: backward in two atomic-free stages.
+//
+// C1 (sorted space, gather form).  Row j of the TRANSPOSED graph lists every i with j in N(i), so
 //   g_j = sum_i u_i (alpha_i v_i v_i^T + beta_i I)(p_j - m_i)
-// needs no atomics on per-point data.  g_j is chained in registers through p_j = R_s (vp + d' dir) + t_s:
-//   dL/dw_k, dL/de_k   block reduction -> one atomic per block and term
-//   dL/dT_s (3x4)      warp-segmented reduction over the scan ids present in the warp -> atomics
+// is a gather over 64-byte stash records; g_j is written to the point's ORIGINAL position (24 bytes).
+//
+// C2 (original order = scan-major, fully coalesced).  g_j is chained through p_j = R_s (vp + d' dir) + t_s
+// to dL/dw_k, dL/de_k and the 3x4 pose gradient.  Blocks are aligned to scans (block table built once on
+// the host), so all threads of a block belong to one scan and a plain block reduction yields one partial
+// record per block -- no atomics, no per-scan scatter.
+//
+// C3.  Partial records are summed in a fixed order per scan (pose gradients) and over all blocks (model
+// gradients): the gradients are bitwise reproducible.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double dc_warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-// Persistent kernel: every warp walks slices (32 rows) with a grid stride.  Per-scan pose gradients are
-// accumulated in shared memory (acc[n_scans][12], shared-memory atomics spread over scan ids) and flushed
-// to global memory once per block; model gradients stay in registers until the end of the loop.
-// acc_scans == 0 selects the fallback for very many scans: warp-segmented reduction + global atomics.
-#define BWD_THREADS 256
-
-template <typename T>
-__global__ void __launch_bounds__(BWD_THREADS)
-step_backward_kernel(const dc_point* __restrict__ P, const typename vec4_of<T>::type* __restrict__ rec_dir,
-                     const typename vec4_of<T>::type* __restrict__ rec_vp, const uint32_t* __restrict__ rec_meta, int64_t n,
-                     const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ ell_idx,
-                     const dc_stash* __restrict__ stash, const double* __restrict__ upstream,
-                     const double* __restrict__ poses, dc_model model, double* __restrict__ dw,
-                     double* __restrict__ dexp, double* __restrict__ dposes, int acc_scans) {
-  extern __shared__ double acc[];
+__global__ void __launch_bounds__(STEP_THREADS)
+step_backward_gather_kernel(const dc_point* __restrict__ P, int64_t n, const int64_t* __restrict__ slice_ptr,
+                            const int32_t* __restrict__ ell_idx, const dc_stash* __restrict__ stash,
+                            const double* __restrict__ upstream, const int32_t* __restrict__ order,
+                            double* __restrict__ g_out) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= n) return;
   const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < acc_scans * 12; i += BWD_THREADS) acc[i] = 0.0;
-  __syncthreads();
-  double gw_sum[DC_MAX_TERMS], ge_sum[DC_MAX_TERMS];
-#pragma unroll
-  for (int k = 0; k < DC_MAX_TERMS; ++k) { gw_sum[k] = 0.0; ge_sum[k] = 0.0; }
-  const int64_t n_slices = (n + DC_SLICE - 1) / DC_SLICE;
-  const int64_t warp0 = (blockIdx.x * (int64_t)BWD_THREADS + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * BWD_THREADS) >> 5;
-  for (int64_t slice = warp0; slice < n_slices; slice += n_warps) {
-  const int64_t row = slice * DC_SLICE + lane;
-  const bool live = row < n;
+  const int64_t base = slice_ptr[row >> 5];
+  const int width = (int)((slice_ptr[(row >> 5) + 1] - base) >> 5);
+  const int32_t* col = ell_idx + base + lane;
+  const dc_point pj = dc_ld_point(P + row);
+  const int self = (int)row;
   double gx = 0, gy = 0, gz = 0;
-  dc_point pj;
-  pj.x = pj.y = pj.z = 0.0;
-  if (live) {
-    const int64_t base = slice_ptr[row >> 5];
-    const int width = (int)((slice_ptr[(row >> 5) + 1] - base) >> 5);
-    const int32_t* col = ell_idx + base + lane;
-    pj = dc_ld_point(P + row);
-    const int self = (int)row;
 #define DC_BWD(i_)                                                                       \
   {                                                                                      \
     const int ii = (i_) >= 0 ? (i_) : self;                                              \
@@ -371,140 +357,142 @@ step_backward_kernel(const dc_point* __restrict__ P, const typename vec4_of<T>::
     const double a = u * s1.z * (s0.w * ex + s1.x * ey + s1.y * ez), b = u * s1.w;       \
     gx += a * s0.w + b * ex; gy += a * s1.x + b * ey; gz += a * s1.y + b * ez;           \
   }
-    int c = 0;
-    for (; c + 2 <= width; c += 2) {
-      const int i0 = __ldg(col + (c + 0) * DC_SLICE), i1 = __ldg(col + (c + 1) * DC_SLICE);
-      DC_BWD(i0) DC_BWD(i1)
-    }
-    for (; c < width; ++c) {
-      const int i0 = __ldg(col + c * DC_SLICE);
-      DC_BWD(i0)
-    }
-#undef DC_BWD
+  int c = 0;
+  for (; c + 4 <= width; c += 4) {
+    const int i0 = __ldg(col + (c + 0) * DC_SLICE), i1 = __ldg(col + (c + 1) * DC_SLICE);
+    const int i2 = __ldg(col + (c + 2) * DC_SLICE), i3 = __ldg(col + (c + 3) * DC_SLICE);
+    DC_BWD(i0) DC_BWD(i1) DC_BWD(i2) DC_BWD(i3)
   }
-  // ---- chain rule through the point's own record
-  double gw[DC_MAX_TERMS], ge[DC_MAX_TERMS];
+  for (; c < width; ++c) {
+    const int i0 = __ldg(col + c * DC_SLICE);
+    DC_BWD(i0)
+  }
+#undef DC_BWD
+  double* o = g_out + 3 * (size_t)order[row];
+  o[0] = gx; o[1] = gy; o[2] = gz;
+}
+
+extern "C" int dc_step_backward(const void* points, int64_t n, const int64_t* slice_ptr_t, const int32_t* ell_idx_t,
+                                const double* stash, const double* upstream_pp, const int32_t* order, double* g_out,
+                                void* stream) {
+  if (n <= 0) return DC_OK;
+  const int blocks = dc_blocks(n, STEP_THREADS);
+  step_backward_gather_kernel<<<blocks, STEP_THREADS, 0, (cudaStream_t)stream>>>((const dc_point*)points, n, slice_ptr_t, ell_idx_t,
+                                                                                (const dc_stash*)stash, upstream_pp, order, g_out);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+#define CHAIN_THREADS 256
+#define CHAIN_REC (12 + 2 * DC_MAX_TERMS)   // doubles per partial record: pose 3x4, dw, dexp
+
+template <typename T>
+__global__ void __launch_bounds__(CHAIN_THREADS)
+step_chain_kernel(const double* __restrict__ g, const typename vec4_of<T>::type* __restrict__ rec_dir,
+                  const typename vec4_of<T>::type* __restrict__ rec_vp, const uint32_t* __restrict__ rec_meta,
+                  const int32_t* __restrict__ block_scan, const int64_t* __restrict__ block_start,
+                  const int32_t* __restrict__ block_count, const double* __restrict__ poses, dc_model model,
+                  int want_exp, double* __restrict__ partials) {
+  const int scan = block_scan[blockIdx.x];
+  const int64_t first = block_start[blockIdx.x];
+  const int count = block_count[blockIdx.x];
+  const double* Tm = poses + 12 * (size_t)scan;
+  const double r00 = Tm[0], r01 = Tm[1], r02 = Tm[2], r10 = Tm[4], r11 = Tm[5], r12 = Tm[6], r20 = Tm[8], r21 = Tm[9], r22 = Tm[10];
+  double acc[CHAIN_REC];
 #pragma unroll
-  for (int k = 0; k < DC_MAX_TERMS; ++k) { gw[k] = 0.0; ge[k] = 0.0; }
-  double gT[12];
-#pragma unroll
-  for (int k = 0; k < 12; ++k) gT[k] = 0.0;
-  int scan = -1;
-  if (live) {
-    const typename vec4_of<T>::type a = rec_dir[row], b = rec_vp[row];
-    const uint32_t meta = rec_meta[row];
-    scan = (int)(meta >> 2);
-    const double* Tm = poses + 12 * (size_t)scan;
+  for (int k = 0; k < CHAIN_REC; ++k) acc[k] = 0.0;
+  for (int t = threadIdx.x; t < count; t += CHAIN_THREADS) {
+    const int64_t i = first + t;
+    const typename vec4_of<T>::type a = rec_dir[i], b = rec_vp[i];
+    const uint32_t meta = rec_meta[i];
+    const double gx = g[3 * i], gy = g[3 * i + 1], gz = g[3 * i + 2];
     const bool mm = (model.kind != DC_MODEL_NONE) && (meta & DC_PT_MODEL_MASK);
     double pw[DC_MAX_TERMS];
     const double d0 = (double)a.w, gam = (double)b.w;
     const double d = dc_correct_depth(model, mm, d0, gam, pw);
     const double dx = (double)a.x, dy = (double)a.y, dz = (double)a.z;
     // d L / d d' = (R dir) . g
-    const double gd = (Tm[0] * dx + Tm[1] * dy + Tm[2] * dz) * gx + (Tm[4] * dx + Tm[5] * dy + Tm[6] * dz) * gy +
-                      (Tm[8] * dx + Tm[9] * dy + Tm[10] * dz) * gz;
+    const double gd = (r00 * dx + r01 * dy + r02 * dz) * gx + (r10 * dx + r11 * dy + r12 * dz) * gy +
+                      (r20 * dx + r21 * dy + r22 * dz) * gz;
     if (mm) {
       const double f = (model.kind == DC_MODEL_SCALED_POLYNOMIAL ? -d0 : -1.0) * gd;
-      for (int k = 0; k < model.n_terms; ++k) {
-        gw[k] = f * pw[k];
-        if (dexp) ge[k] = f * model.w[k] * dc_pow_exp_dlog(gam, model.e[k], pw[k]);
+#pragma unroll
+      for (int k = 0; k < DC_MAX_TERMS; ++k) {
+        if (k < model.n_terms) {
+          acc[12 + k] += f * pw[k];
+          if (want_exp) acc[12 + DC_MAX_TERMS + k] += f * model.w[k] * dc_pow_exp_dlog(gam, model.e[k], pw[k]);
+        }
       }
     }
     const double x = (double)b.x + d * dx, y = (double)b.y + d * dy, z = (double)b.z + d * dz;
-    gT[0] = gx * x; gT[1] = gx * y; gT[2] = gx * z; gT[3] = gx;
-    gT[4] = gy * x; gT[5] = gy * y; gT[6] = gy * z; gT[7] = gy;
-    gT[8] = gz * x; gT[9] = gz * y; gT[10] = gz * z; gT[11] = gz;
+    acc[0] += gx * x; acc[1] += gx * y; acc[2] += gx * z; acc[3] += gx;
+    acc[4] += gy * x; acc[5] += gy * y; acc[6] += gy * z; acc[7] += gy;
+    acc[8] += gz * x; acc[9] += gz * y; acc[10] += gz * z; acc[11] += gz;
   }
+  __shared__ double red[CHAIN_THREADS / 32][CHAIN_REC];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < DC_MAX_TERMS; ++k) { gw_sum[k] += gw[k]; ge_sum[k] += ge[k]; }
-  // ---- pose gradients
-  if (dposes && acc_scans > 0) {
-    if (live) {
-#pragma unroll
-      for (int k = 0; k < 12; ++k) atomicAdd(acc + 12 * scan + k, gT[k]);
-    }
-  } else if (dposes) {
-    // fallback: segmented by scan id inside the warp, one global atomic per scan and entry
-    unsigned int remaining = __ballot_sync(0xffffffffu, live);
-    while (remaining) {
-      const int leader = __ffs(remaining) - 1;
-      const int s = __shfl_sync(0xffffffffu, scan, leader);
-      const bool mine = live && scan == s;
-#pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        const double v = dc_warp_sum(mine ? gT[k] : 0.0);
-        if (lane == 0) atomicAdd(dposes + 12 * (size_t)s + k, v);
-      }
-      remaining &= ~__ballot_sync(0xffffffffu, mine);
-    }
+  for (int k = 0; k < CHAIN_REC; ++k) {
+    const double v = dc_warp_sum(acc[k]);
+    if (lane == 0) red[wid][k] = v;
   }
-  }   // slice loop
-  // ---- model gradients: registers -> warp shuffle -> shared -> one atomic per block and term
-  if (model.kind != DC_MODEL_NONE && dw) {
-    __shared__ double red[BWD_THREADS / 32][2 * DC_MAX_TERMS];
-    for (int k = 0; k < model.n_terms; ++k) {
-      const double a = dc_warp_sum(gw_sum[k]);
-      const double b = dexp ? dc_warp_sum(ge_sum[k]) : 0.0;
-      if (lane == 0) { red[threadIdx.x >> 5][k] = a; red[threadIdx.x >> 5][DC_MAX_TERMS + k] = b; }
-    }
-    __syncthreads();
-    if (threadIdx.x < model.n_terms) {
-      double a = 0.0, b = 0.0;
-      for (int wv = 0; wv < BWD_THREADS / 32; ++wv) { a += red[wv][threadIdx.x]; b += red[wv][DC_MAX_TERMS + threadIdx.x]; }
-      atomicAdd(dw + threadIdx.x, a);
-      if (dexp) atomicAdd(dexp + threadIdx.x, b);
-    }
-  }
-  if (dposes && acc_scans > 0) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < acc_scans * 12; i += BWD_THREADS) {
-      const double v = acc[i];
-      if (v != 0.0) atomicAdd(dposes + i, v);
-    }
+  __syncthreads();
+  if (threadIdx.x < CHAIN_REC) {
+    double v = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < CHAIN_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
+    partials[(size_t)blockIdx.x * CHAIN_REC + threadIdx.x] = v;
   }
 }
 
-extern "C" int dc_step_backward(const void* points, const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta,
-                                int dtype, int64_t n, const int64_t* slice_ptr_t, const int32_t* ell_idx_t,
-                                const double* stash, const double* upstream_pp, const double* poses, int n_scans,
-                                int model_kind, const double* w, const double* exponent, int n_terms, double* dw,
-                                double* dexponent, double* dposes, void* stream) {
-  if (n <= 0) return DC_OK;
-  if (n_terms < 0 || n_terms > DC_MAX_TERMS) return dc_set_error(DC_ERR_ARG, "dc_step_backward: too many polynomial terms");
+// one block: pose gradients per scan (blocks of a scan are contiguous), model gradients over all blocks
+__global__ void __launch_bounds__(256)
+step_chain_reduce_kernel(const double* __restrict__ partials, int n_blocks, const int32_t* __restrict__ scan_block_first,
+                         int n_scans, int n_terms, double* __restrict__ dw, double* __restrict__ dexp,
+                         double* __restrict__ dposes) {
+  for (int idx = threadIdx.x; idx < n_scans * 12; idx += 256) {
+    const int s = idx / 12, k = idx - 12 * s;
+    double v = 0.0;
+    for (int b = scan_block_first[s]; b < scan_block_first[s + 1]; ++b) v += partials[(size_t)b * CHAIN_REC + k];
+    dposes[idx] += v;
+  }
+  __shared__ double red[256];
+  for (int k = 0; k < 2 * n_terms; ++k) {
+    const int col = 12 + (k < n_terms ? k : DC_MAX_TERMS + (k - n_terms));
+    double* out = k < n_terms ? dw : dexp;
+    if (!out) continue;
+    double v = 0.0;
+    for (int b = threadIdx.x; b < n_blocks; b += 256) v += partials[(size_t)b * CHAIN_REC + col];
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[k < n_terms ? k : k - n_terms] += red[0];
+    __syncthreads();
+  }
+}
+
+extern "C" int dc_step_chain(const double* g, const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta, int dtype,
+                             const int32_t* block_scan, const int64_t* block_start, const int32_t* block_count,
+                             int n_blocks, const int32_t* scan_block_first, const double* poses, int n_scans,
+                             int model_kind, const double* w, const double* exponent, int n_terms, double* partials,
+                             double* dw, double* dexponent, double* dposes, void* stream) {
+  if (n_blocks <= 0) return DC_OK;
+  if (n_terms < 0 || n_terms > DC_MAX_TERMS) return dc_set_error(DC_ERR_ARG, "dc_step_chain: too many polynomial terms");
   dc_model m = {model_kind, n_terms, w, exponent};
   cudaStream_t st = (cudaStream_t)stream;
-  // persistent grid: a multiple of the SM count (148 on B200), resident blocks limited by the pose accumulators
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    DC_CUDA_CHECK(cudaGetDevice(&dev));
-    DC_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
-  size_t smem = (size_t)n_scans * 12 * sizeof(double);
-  int acc_scans = n_scans;
-  if (!dposes || smem > 200 * 1024) { smem = 0; acc_scans = 0; }
-  int per_sm = 4;
-  if (smem > 0) {
-    const int fit = (int)((220 * 1024) / (smem + 1024));
-    per_sm = fit < 1 ? 1 : (fit > 4 ? 4 : fit);
-  }
-  const int64_t n_slices = (n + DC_SLICE - 1) / DC_SLICE;
-  int64_t blocks = (int64_t)sm_count * per_sm;
-  const int64_t need = (n_slices + BWD_THREADS / 32 - 1) / (BWD_THREADS / 32);
-  if (blocks > need) blocks = need;
-  if (dtype == DC_F32) {
-    if (smem > 48 * 1024)
-      DC_CUDA_CHECK(cudaFuncSetAttribute(step_backward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    step_backward_kernel<float><<<(int)blocks, BWD_THREADS, smem, st>>>((const dc_point*)points, (const float4*)rec_dir, (const float4*)rec_vp,
-                                                                        rec_meta, n, slice_ptr_t, ell_idx_t, (const dc_stash*)stash,
-                                                                        upstream_pp, poses, m, dw, dexponent, dposes, acc_scans);
-  } else {
-    if (smem > 48 * 1024)
-      DC_CUDA_CHECK(cudaFuncSetAttribute(step_backward_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    step_backward_kernel<double><<<(int)blocks, BWD_THREADS, smem, st>>>((const dc_point*)points, (const double4*)rec_dir, (const double4*)rec_vp,
-                                                                         rec_meta, n, slice_ptr_t, ell_idx_t, (const dc_stash*)stash,
-                                                                         upstream_pp, poses, m, dw, dexponent, dposes, acc_scans);
-  }
+  const int want_exp = dexponent != nullptr;
+  if (dtype == DC_F32)
+    step_chain_kernel<float><<<n_blocks, CHAIN_THREADS, 0, st>>>(g, (const float4*)rec_dir, (const float4*)rec_vp, rec_meta, block_scan,
+                                                                 block_start, block_count, poses, m, want_exp, partials);
+  else
+    step_chain_kernel<double><<<n_blocks, CHAIN_THREADS, 0, st>>>(g, (const double4*)rec_dir, (const double4*)rec_vp, rec_meta, block_scan,
+                                                                  block_start, block_count, poses, m, want_exp, partials);
+  DC_LAUNCH_CHECK();
+  step_chain_reduce_kernel<<<1, 256, 0, st>>>(partials, n_blocks, scan_block_first, n_scans, model_kind != DC_MODEL_NONE ? n_terms : 0,
+                                              dw, dexponent, dposes);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

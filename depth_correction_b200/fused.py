@@ -18,6 +18,9 @@ from . import _lib as L
 
 __all__ = ['StepState', 'fused_loss', 'model_kind_of']
 
+CHAIN_CHUNK = 2048                      # rows per block of the chain stage (256 threads x 8)
+CHAIN_REC = 12 + 2 * L.MAX_TERMS        # doubles per partial record (dc_step.cu)
+
 
 def model_kind_of(model):
     if model is None:
@@ -54,8 +57,11 @@ class StepState(object):
         self.rec_dir = torch.empty((n, 4), dtype=dt, device=dev)
         self.rec_vp = torch.empty((n, 4), dtype=dt, device=dev)
         self.rec_meta = torch.empty(n, dtype=torch.int32, device=dev)
+        # second copy of the records in the caller's (scan-major) order for the chain stage of the backward pass
+        self.rec_dir_o = torch.empty((n, 4), dtype=dt, device=dev)
+        self.rec_vp_o = torch.empty((n, 4), dtype=dt, device=dev)
+        self.rec_meta_o = torch.empty(n, dtype=torch.int32, device=dev)
         first = 0
-        keep = []
         for s, c in enumerate(clouds):
             cnt = len(c)
             assert c.depth.dtype == dt and c.dirs.is_cuda
@@ -64,17 +70,35 @@ class StepState(object):
             depth = c.depth.detach().reshape(-1).contiguous()
             inc = None if c.inc_angles is None else c.inc_angles.detach().reshape(-1).to(dt).contiguous()
             mm = None if c.mask is None else c.mask.detach().to(torch.uint8).contiguous()
-            keep += [dirs, vps, depth, inc, mm]
+            # temporaries are released to the caching allocator in stream order, after the kernels below
             L.call('dc_pack_records', L.ptr(vps), L.ptr(dirs), L.ptr(depth), L.ptr(inc), L.ptr(mm), None, self.code,
                    first, cnt, s, L.ptr(smap.inv_order), L.ptr(self.rec_dir), L.ptr(self.rec_vp), L.ptr(self.rec_meta), st)
+            L.call('dc_pack_records', L.ptr(vps), L.ptr(dirs), L.ptr(depth), L.ptr(inc), L.ptr(mm), None, self.code,
+                   first, cnt, s, None, L.ptr(self.rec_dir_o), L.ptr(self.rec_vp_o), L.ptr(self.rec_meta_o), st)
             first += cnt
-        torch.cuda.current_stream().synchronize()   # `keep` temporaries may be freed after this point
         self.has_inc = all(c.inc_angles is not None for c in clouds)
         self.P = torch.empty((n, 4), dtype=torch.float64, device=dev)
         self.stash = torch.empty((n, 8), dtype=torch.float64, device=dev)
         self.loss_pp = torch.empty(n, dtype=torch.float64, device=dev)
+        self.g = torch.empty((n, 3), dtype=torch.float64, device=dev)       # dL/dp per point, original order
         self.n_blocks = ((n + 31) // 32 * 32 + 127) // 128
         self.partials = torch.zeros(2 * self.n_blocks + 2, dtype=torch.float64, device=dev)
+        # block table of the chain stage: blocks are aligned to scans (CHAIN_CHUNK rows each)
+        import numpy as np
+        sz = np.asarray(sizes, dtype=np.int64)
+        nb = (sz + CHAIN_CHUNK - 1) // CHAIN_CHUNK
+        scan_first = np.concatenate([[0], np.cumsum(sz)])
+        blk_first = np.concatenate([[0], np.cumsum(nb)]).astype(np.int32)
+        blk_scan = np.repeat(np.arange(len(sz), dtype=np.int32), nb)
+        within = np.arange(int(nb.sum()), dtype=np.int64) - np.repeat(blk_first[:-1].astype(np.int64), nb)
+        blk_start = np.repeat(scan_first[:-1], nb) + within * CHAIN_CHUNK
+        blk_count = np.minimum(np.repeat(sz, nb) - within * CHAIN_CHUNK, CHAIN_CHUNK).astype(np.int32)
+        self.chain_blocks = int(nb.sum())
+        self.blk_scan = torch.as_tensor(blk_scan, device=dev)
+        self.blk_start = torch.as_tensor(blk_start, device=dev)
+        self.blk_count = torch.as_tensor(blk_count, device=dev)
+        self.scan_blk_first = torch.as_tensor(blk_first, device=dev)
+        self.chain_partials = torch.empty(max(self.chain_blocks, 1) * CHAIN_REC, dtype=torch.float64, device=dev)
         self._mask_key = None
         self.generation = 0
 
@@ -152,9 +176,12 @@ class _FusedStep(torch.autograd.Function):
         upstream = None
         if raw:
             upstream = grads[0].to(torch.float64).contiguous()
-        L.call('dc_step_backward', L.ptr(state.P), L.ptr(state.rec_dir), L.ptr(state.rec_vp), L.ptr(state.rec_meta),
-               state.code, state.n, L.ptr(gt.slice_ptr), L.ptr(gt.ell_idx), L.ptr(state.stash), L.ptr(upstream),
-               L.ptr(poses12), S, model_kind, L.ptr(wv), L.ptr(ev), n_terms, L.ptr(dw), L.ptr(dexp), L.ptr(dposes), st)
+        L.call('dc_step_backward', L.ptr(state.P), state.n, L.ptr(gt.slice_ptr), L.ptr(gt.ell_idx), L.ptr(state.stash),
+               L.ptr(upstream), L.ptr(ctx.graph.map.order), L.ptr(state.g), st)
+        L.call('dc_step_chain', L.ptr(state.g), L.ptr(state.rec_dir_o), L.ptr(state.rec_vp_o), L.ptr(state.rec_meta_o),
+               state.code, L.ptr(state.blk_scan), L.ptr(state.blk_start), L.ptr(state.blk_count), state.chain_blocks,
+               L.ptr(state.scan_blk_first), L.ptr(poses12), S, model_kind, L.ptr(wv), L.ptr(ev), n_terms,
+               L.ptr(state.chain_partials), L.ptr(dw), L.ptr(dexp), L.ptr(dposes), st)
         scale = None if raw else grads[0][0]
         w_shape, e_shape, p_shape, p_dtype, p_dev = ctx.shapes
         gw = ge = None

@@ -158,7 +158,8 @@ int dc_transpose_fill(const uint64_t* pairs_sorted, int64_t n_edges, int64_t n_c
  * poses: fp64 [S,12] row-major 3x4 (already corrected, see dc_pose_compose).
  * ------------------------------------------------------------------------------------------- */
 
-/* pack rows of one scan into sorted space: row i of the scan is global row `first + i` */
+/* pack rows of one scan: row i of the scan is global row `first + i` and lands at inv_order[first + i]
+ * (sorted space), or at first + i when inv_order == NULL (original order, used by dc_step_chain) */
 int dc_pack_records(const void* vps, const void* dirs, const void* depth, const void* inc_angles,
                     const uint8_t* model_mask, const uint8_t* loss_mask, int dtype, int64_t first, int64_t count,
                     int scan_id, const int32_t* inv_order, void* rec_dir, void* rec_vp, uint32_t* rec_meta,
@@ -180,14 +181,23 @@ int dc_step_forward(const void* points, const uint32_t* rec_meta, int64_t n, con
                     const int32_t* ell_idx, int loss_kind, int flags, double* loss_pp, double* stash, double* eigvals,
                     double* loss_sum, void* partials, size_t partials_bytes, void* stream);
 
-/* pass C: g_j = sum_{i : j in N(i)} A_i (p_j - m_i) over the TRANSPOSED graph, chained to
- * dw[n_terms], dexponent[n_terms] (NULL to skip) and dposes[S,12]; outputs are ACCUMULATED (caller zeroes).
- * upstream_pp: optional per-point upstream gradient in sorted space (NULL = 1 for every row). */
-int dc_step_backward(const void* points, const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta, int dtype,
-                     int64_t n, const int64_t* slice_ptr_t, const int32_t* ell_idx_t,
-                     const double* stash, const double* upstream_pp, const double* poses, int n_scans, int model_kind,
-                     const double* w, const double* exponent, int n_terms, double* dw, double* dexponent,
-                     double* dposes, void* stream);
+/* pass C1: g_j = sum_{i : j in N(i)} u_i A_i (p_j - m_i), a gather over the TRANSPOSED graph (sorted space),
+ * written to the point's ORIGINAL row: g_out fp64 [n,3].  upstream_pp: optional per-point upstream gradient
+ * in sorted space (NULL = 1 for every row).  No atomics. */
+int dc_step_backward(const void* points, int64_t n, const int64_t* slice_ptr_t, const int32_t* ell_idx_t,
+                     const double* stash, const double* upstream_pp, const int32_t* order, double* g_out, void* stream);
+
+/* pass C2 + C3: chain g (original = scan-major order) through p = R_s (vp + d' dir) + t_s to dw[n_terms],
+ * dexponent[n_terms] (NULL to skip) and dposes[S,12]; outputs are ACCUMULATED (caller zeroes).
+ * Records are the dc_pack_records layout packed with inv_order == NULL (original order).  The block table
+ * aligns blocks to scans: block b covers rows [block_start[b], block_start[b] + block_count[b]) of scan
+ * block_scan[b]; blocks of scan s are [scan_block_first[s], scan_block_first[s+1]).  partials: scratch of
+ * n_blocks * (12 + 2*DC_MAX_TERMS) doubles.  Block reductions + fixed-order final sums: deterministic. */
+int dc_step_chain(const double* g, const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta, int dtype,
+                  const int32_t* block_scan, const int64_t* block_start, const int32_t* block_count, int n_blocks,
+                  const int32_t* scan_block_first, const double* poses, int n_scans, int model_kind, const double* w,
+                  const double* exponent, int n_terms, double* partials, double* dw, double* dexponent, double* dposes,
+                  void* stream);
 
 /* SE(3) correction T_s = P_s * Delta(delta_s): create_corrected_poses (eval.py:68-82) +
  * xyz_axis_angle_to_matrix (transform.py:68-78).  poses fp64 [S,16]; deltas fp64 [n_deltas,6] with
