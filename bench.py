@@ -138,7 +138,8 @@ def one_step(dc, clouds, poses, deltas, model, cfg, ns=None, timers=None, local=
         cloud = dc.global_cloud(clouds=clouds, model=model, poses=p0)
         feats = dc.compute_neighborhood_features(cloud=cloud, neighborhoods=ns, cfg=cfg)
         feats.step_state()                       # pack the scan records in sorted order
-        ns.graph.transposed()                    # reverse lists for the gather-form backward
+        # (the reverse lists of the gather-form backward are built by the library once a graph has served
+        #  more than fused.TRANSPOSE_AFTER backward passes; a graph that is searched anew every step never does)
     e1.record()
     model.zero_grad(set_to_none=True)
     deltas.grad = None
@@ -298,14 +299,14 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (live CUDA-event durations of the timed region)
     g = ns.graph
-    gt = g.transposed()
     idx_fwd = g.ell_idx.numel() * 4
-    idx_bwd = gt.ell_idx.numel() * 4
+    idx_bwd = g._transposed.ell_idx.numel() * 4 if g._transposed is not None else idx_fwd
     alg = {   # algorithmic bytes per launch: every array once per pass, gathers assumed L2-served
         'dc_step_points': n_resident * (36 + 32),
         'dc_step_forward': idx_fwd + n_resident * (32 + 4 + 8 + 64),
-        'dc_step_backward': idx_bwd + n_resident * (32 + 4 + 24),
-        'dc_step_chain': n_resident * (24 + 36),
+        'dc_step_backward': idx_bwd + n_resident * (32 + 4 + 24),           # gather form (transposed graph)
+        'dc_step_backward_scatter': idx_fwd + n_resident * (64 + 24 + 24),  # scatter form: stash, g zero + g reduce
+        'dc_step_chain': n_resident * (24 + 36 + 4),
     }
     peak, peak_src = peaks()
     kern = {k: v for k, v in kernel_ms.items() if k in alg}

@@ -372,6 +372,59 @@ step_backward_gather_kernel(const dc_point* __restrict__ P, int64_t n, const int
   o[0] = gx; o[1] = gy; o[2] = gz;
 }
 
+// C1, scatter form (no transposed graph needed): row i walks its own neighbour list and adds
+// u_i A_i (p_j - m_i) to g_j with fire-and-forget fp64 reductions (RED.E.ADD.F64, addresses spread over
+// all points -> no hot spots).  Used for the first backward passes on an asymmetric (kNN) graph, before
+// building the transpose has paid off; g is accumulated in SORTED space and must be zeroed by the caller.
+__global__ void __launch_bounds__(STEP_THREADS)
+step_backward_scatter_kernel(const dc_point* __restrict__ P, int64_t n, const int64_t* __restrict__ slice_ptr,
+                             const int32_t* __restrict__ ell_idx, const dc_stash* __restrict__ stash,
+                             const double* __restrict__ upstream, double* __restrict__ g_sorted) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t base = slice_ptr[row >> 5];
+  const int width = (int)((slice_ptr[(row >> 5) + 1] - base) >> 5);
+  const int32_t* col = ell_idx + base + lane;
+  double4 s0, s1;
+  dc_ld256(stash + row, s0.x, s0.y, s0.z, s0.w);
+  dc_ld256(reinterpret_cast<const char*>(stash + row) + 32, s1.x, s1.y, s1.z, s1.w);
+  double u = upstream ? upstream[row] : 1.0;
+  const double ua = u * s1.z, ub = u * s1.w;
+  if (ua == 0.0 && ub == 0.0) return;        // masked-out / inactive loss term: nothing to scatter
+#define DC_SCAT(j_)                                                                  \
+  if ((j_) >= 0) {                                                                   \
+    const dc_point pj = dc_ld_point(P + (j_));                                       \
+    const double ex = pj.x - s0.x, ey = pj.y - s0.y, ez = pj.z - s0.z;               \
+    const double a = ua * (s0.w * ex + s1.x * ey + s1.y * ez);                       \
+    double* o = g_sorted + 3 * (size_t)(j_);                                         \
+    atomicAdd(o, a * s0.w + ub * ex);                                                \
+    atomicAdd(o + 1, a * s1.x + ub * ey);                                            \
+    atomicAdd(o + 2, a * s1.y + ub * ez);                                            \
+  }
+  int c = 0;
+  for (; c + 4 <= width; c += 4) {
+    const int j0 = __ldg(col + (c + 0) * DC_SLICE), j1 = __ldg(col + (c + 1) * DC_SLICE);
+    const int j2 = __ldg(col + (c + 2) * DC_SLICE), j3 = __ldg(col + (c + 3) * DC_SLICE);
+    DC_SCAT(j0) DC_SCAT(j1) DC_SCAT(j2) DC_SCAT(j3)
+  }
+  for (; c < width; ++c) {
+    const int j0 = __ldg(col + c * DC_SLICE);
+    DC_SCAT(j0)
+  }
+#undef DC_SCAT
+}
+
+extern "C" int dc_step_backward_scatter(const void* points, int64_t n, const int64_t* slice_ptr, const int32_t* ell_idx,
+                                        const double* stash, const double* upstream_pp, double* g_sorted, void* stream) {
+  if (n <= 0) return DC_OK;
+  const int blocks = dc_blocks(n, STEP_THREADS);
+  step_backward_scatter_kernel<<<blocks, STEP_THREADS, 0, (cudaStream_t)stream>>>((const dc_point*)points, n, slice_ptr, ell_idx,
+                                                                                 (const dc_stash*)stash, upstream_pp, g_sorted);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
 extern "C" int dc_step_backward(const void* points, int64_t n, const int64_t* slice_ptr_t, const int32_t* ell_idx_t,
                                 const double* stash, const double* upstream_pp, const int32_t* order, double* g_out,
                                 void* stream) {
@@ -388,7 +441,8 @@ extern "C" int dc_step_backward(const void* points, int64_t n, const int64_t* sl
 
 template <typename T>
 __global__ void __launch_bounds__(CHAIN_THREADS)
-step_chain_kernel(const double* __restrict__ g, const typename vec4_of<T>::type* __restrict__ rec_dir,
+step_chain_kernel(const double* __restrict__ g, const int32_t* __restrict__ g_index,
+                  const typename vec4_of<T>::type* __restrict__ rec_dir,
                   const typename vec4_of<T>::type* __restrict__ rec_vp, const uint32_t* __restrict__ rec_meta,
                   const int32_t* __restrict__ block_scan, const int64_t* __restrict__ block_start,
                   const int32_t* __restrict__ block_count, const double* __restrict__ poses, dc_model model,
@@ -405,7 +459,8 @@ step_chain_kernel(const double* __restrict__ g, const typename vec4_of<T>::type*
     const int64_t i = first + t;
     const typename vec4_of<T>::type a = rec_dir[i], b = rec_vp[i];
     const uint32_t meta = rec_meta[i];
-    const double gx = g[3 * i], gy = g[3 * i + 1], gz = g[3 * i + 2];
+    const size_t gi = g_index ? (size_t)g_index[i] : (size_t)i;   // g in sorted space (scatter form) or in place
+    const double gx = g[3 * gi], gy = g[3 * gi + 1], gz = g[3 * gi + 2];
     const bool mm = (model.kind != DC_MODEL_NONE) && (meta & DC_PT_MODEL_MASK);
     double pw[DC_MAX_TERMS];
     const double d0 = (double)a.w, gam = (double)b.w;
@@ -474,7 +529,7 @@ step_chain_reduce_kernel(const double* __restrict__ partials, int n_blocks, cons
   }
 }
 
-extern "C" int dc_step_chain(const double* g, const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta, int dtype,
+extern "C" int dc_step_chain(const double* g, const int32_t* g_index, const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta, int dtype,
                              const int32_t* block_scan, const int64_t* block_start, const int32_t* block_count,
                              int n_blocks, const int32_t* scan_block_first, const double* poses, int n_scans,
                              int model_kind, const double* w, const double* exponent, int n_terms, double* partials,
@@ -485,10 +540,10 @@ extern "C" int dc_step_chain(const double* g, const void* rec_dir, const void* r
   cudaStream_t st = (cudaStream_t)stream;
   const int want_exp = dexponent != nullptr;
   if (dtype == DC_F32)
-    step_chain_kernel<float><<<n_blocks, CHAIN_THREADS, 0, st>>>(g, (const float4*)rec_dir, (const float4*)rec_vp, rec_meta, block_scan,
+    step_chain_kernel<float><<<n_blocks, CHAIN_THREADS, 0, st>>>(g, g_index, (const float4*)rec_dir, (const float4*)rec_vp, rec_meta, block_scan,
                                                                  block_start, block_count, poses, m, want_exp, partials);
   else
-    step_chain_kernel<double><<<n_blocks, CHAIN_THREADS, 0, st>>>(g, (const double4*)rec_dir, (const double4*)rec_vp, rec_meta, block_scan,
+    step_chain_kernel<double><<<n_blocks, CHAIN_THREADS, 0, st>>>(g, g_index, (const double4*)rec_dir, (const double4*)rec_vp, rec_meta, block_scan,
                                                                   block_start, block_count, poses, m, want_exp, partials);
   DC_LAUNCH_CHECK();
   step_chain_reduce_kernel<<<1, 256, 0, st>>>(partials, n_blocks, scan_block_first, n_scans, model_kind != DC_MODEL_NONE ? n_terms : 0,

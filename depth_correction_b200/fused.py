@@ -18,6 +18,7 @@ from . import _lib as L
 
 __all__ = ['StepState', 'fused_loss', 'model_kind_of']
 
+TRANSPOSE_AFTER = 2                     # backward passes served by the scatter form before a kNN graph is transposed
 CHAIN_CHUNK = 2048                      # rows per block of the chain stage (256 threads x 8)
 CHAIN_REC = 12 + 2 * L.MAX_TERMS        # doubles per partial record (dc_step.cu)
 
@@ -169,16 +170,35 @@ class _FusedStep(torch.autograd.Function):
         dev = state.device
         st = L.stream()
         S = state.n_scans
-        gt = ctx.graph.transposed()
+        # Transposed graph policy: radius graphs are their own transpose.  For kNN graphs building the reverse
+        # lists costs about as much as three backward passes, so the first TRANSPOSE_AFTER backward passes on a
+        # graph use the scatter form and the transpose is built once the graph is evidently being reused.
+        graph = ctx.graph
+        graph._bwd_calls = getattr(graph, '_bwd_calls', 0) + 1
+        if graph.symmetric:
+            gt = graph
+        elif graph._transposed is not None or graph._bwd_calls > TRANSPOSE_AFTER:
+            gt = graph.transposed()
+        else:
+            gt = None
         dw = torch.zeros(max(n_terms, 1), dtype=torch.float64, device=dev)
         dexp = torch.zeros(max(n_terms, 1), dtype=torch.float64, device=dev) if ctx.exp_grad else None
         dposes = torch.zeros((S, 12), dtype=torch.float64, device=dev)
         upstream = None
         if raw:
             upstream = grads[0].to(torch.float64).contiguous()
-        L.call('dc_step_backward', L.ptr(state.P), state.n, L.ptr(gt.slice_ptr), L.ptr(gt.ell_idx), L.ptr(state.stash),
-               L.ptr(upstream), L.ptr(ctx.graph.map.order), L.ptr(state.g), st)
-        L.call('dc_step_chain', L.ptr(state.g), L.ptr(state.rec_dir_o), L.ptr(state.rec_vp_o), L.ptr(state.rec_meta_o),
+        g_index = None
+        if gt is not None:
+            # gather form over the transposed graph: atomic-free, deterministic
+            L.call('dc_step_backward', L.ptr(state.P), state.n, L.ptr(gt.slice_ptr), L.ptr(gt.ell_idx), L.ptr(state.stash),
+                   L.ptr(upstream), L.ptr(graph.map.order), L.ptr(state.g), st)
+        else:
+            # scatter form over the forward graph (L2 reductions): no transpose needed yet
+            state.g.zero_()
+            L.call('dc_step_backward_scatter', L.ptr(state.P), state.n, L.ptr(graph.slice_ptr), L.ptr(graph.ell_idx),
+                   L.ptr(state.stash), L.ptr(upstream), L.ptr(state.g), st)
+            g_index = graph.map.inv_order
+        L.call('dc_step_chain', L.ptr(state.g), L.ptr(g_index), L.ptr(state.rec_dir_o), L.ptr(state.rec_vp_o), L.ptr(state.rec_meta_o),
                state.code, L.ptr(state.blk_scan), L.ptr(state.blk_start), L.ptr(state.blk_count), state.chain_blocks,
                L.ptr(state.scan_blk_first), L.ptr(poses12), S, model_kind, L.ptr(wv), L.ptr(ev), n_terms,
                L.ptr(state.chain_partials), L.ptr(dw), L.ptr(dexp), L.ptr(dposes), st)

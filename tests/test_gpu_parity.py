@@ -296,8 +296,11 @@ def test_fused_step_vs_reference_golden(dc, dev, golden, tag, own_search):
         nb = ns[0].cpu().numpy()
         assert nb.shape == g['neighbors'].shape and np.array_equal(nb, g['neighbors'])
     assert feats.fusable()
+    if not own_search:
+        feats._graph.transposed()      # force the gather-form backward; a fresh kNN graph starts with the scatter form
     loss, loss_cloud = _run_loss(dc, inp, feats, dev)
     loss.backward()
+    assert own_search or feats._graph.symmetric or feats._graph._transposed is not None
     # sqrt variants amplify the +-1e-17 eigenvalue noise of rank-deficient neighbourhoods (sqrt'(x) ~ 1e9) in the
     # reference itself (its own CPU re-run differs from the golden by ~5e-7), so they get the north-star tolerance
     tol, gtol = (RTOL, RTOL) if inp['sqrt'] and inp['loss'] == 'min_eigval_loss' else (1e-9, 1e-8)
