@@ -69,6 +69,8 @@ SIGNATURES = {
     'dc_transpose_widths': [_P, _L, _L, _P, _P, _P],
     'dc_transpose_fill': [_P, _L, _L, _P, _P, _P],
     'dc_pack_records': [_P, _P, _P, _P, _P, _P, _I, _L, _L, _I, _P, _P, _P, _P, _P],
+    'dc_pack_records_batched': [_P, _P, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+    'dc_world_points_batched': [_P, _P, _I, _L, _I, _P, _P, _P],
     'dc_set_loss_mask': [_P, _L, _P, _P, _P],
     'dc_step_points': [_P, _P, _P, _I, _L, _P, _I, _I, _P, _P, _I, _P, _P],
     'dc_step_forward': [_P, _P, _L, _P, _P, _I, _I, _P, _P, _P, _P, _P, _SZ, _P],

@@ -79,6 +79,102 @@ extern "C" int dc_pack_records(const void* vps, const void* dirs, const void* de
   return DC_OK;
 }
 
+// All scans in one launch: tbl[s] = {vps, dirs, depth, inc_angles, model_mask} device addresses of scan s (0 = absent),
+// first[s] = global row of its first point.  Writes the sorted-space copy (through inv_order) and, optionally, the
+// original-order copy used by the chain stage of the backward pass.
+struct dc_scan_ptrs {
+  unsigned long long vps, dirs, depth, inc, mask;
+};
+
+__device__ __forceinline__ int dc_find_scan(const int64_t* __restrict__ first, int n_scans, int64_t i) {
+  int lo = 0, hi = n_scans;      // largest s with first[s] <= i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(first + mid) <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <typename T>
+__global__ void pack_records_batched_kernel(const dc_scan_ptrs* __restrict__ tbl, const int64_t* __restrict__ first,
+                                            int n_scans, int64_t n, const int32_t* __restrict__ inv_order,
+                                            typename vec4_of<T>::type* __restrict__ rec_dir,
+                                            typename vec4_of<T>::type* __restrict__ rec_vp, uint32_t* __restrict__ rec_meta,
+                                            typename vec4_of<T>::type* __restrict__ rec_dir_o,
+                                            typename vec4_of<T>::type* __restrict__ rec_vp_o, uint32_t* __restrict__ rec_meta_o) {
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const int s = dc_find_scan(first, n_scans, g);
+  const int64_t i = g - first[s];
+  const dc_scan_ptrs p = tbl[s];
+  const T* vps = reinterpret_cast<const T*>(p.vps);
+  const T* dirs = reinterpret_cast<const T*>(p.dirs);
+  const T* depth = reinterpret_cast<const T*>(p.depth);
+  const T* inc = reinterpret_cast<const T*>(p.inc);
+  const uint8_t* mask = reinterpret_cast<const uint8_t*>(p.mask);
+  typename vec4_of<T>::type a, b;
+  a.x = dirs[3 * i]; a.y = dirs[3 * i + 1]; a.z = dirs[3 * i + 2]; a.w = depth[i];
+  if (vps) { b.x = vps[3 * i]; b.y = vps[3 * i + 1]; b.z = vps[3 * i + 2]; }
+  else { b.x = 0; b.y = 0; b.z = 0; }
+  b.w = inc ? inc[i] : (T)0;
+  const uint32_t meta = ((uint32_t)s << 2) | ((!mask || mask[i]) ? DC_PT_MODEL_MASK : 0u) | DC_PT_LOSS_MASK;
+  const int64_t d = inv_order[g];
+  rec_dir[d] = a; rec_vp[d] = b; rec_meta[d] = meta;
+  if (rec_dir_o) { rec_dir_o[g] = a; rec_vp_o[g] = b; rec_meta_o[g] = meta; }
+}
+
+extern "C" int dc_pack_records_batched(const void* scan_ptr_table, const int64_t* first, int n_scans, int64_t n, int dtype,
+                                       const int32_t* inv_order, void* rec_dir, void* rec_vp, uint32_t* rec_meta,
+                                       void* rec_dir_o, void* rec_vp_o, uint32_t* rec_meta_o, void* stream) {
+  if (n <= 0) return DC_OK;
+  if (n_scans < 1 || n_scans >= (1 << 30)) return dc_set_error(DC_ERR_ARG, "dc_pack_records_batched: bad scan count");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = dc_blocks(n, 256);
+  const dc_scan_ptrs* tbl = (const dc_scan_ptrs*)scan_ptr_table;
+  if (dtype == DC_F32)
+    pack_records_batched_kernel<float><<<blocks, 256, 0, st>>>(tbl, first, n_scans, n, inv_order, (float4*)rec_dir, (float4*)rec_vp,
+                                                               rec_meta, (float4*)rec_dir_o, (float4*)rec_vp_o, rec_meta_o);
+  else
+    pack_records_batched_kernel<double><<<blocks, 256, 0, st>>>(tbl, first, n_scans, n, inv_order, (double4*)rec_dir, (double4*)rec_vp,
+                                                                rec_meta, (double4*)rec_dir_o, (double4*)rec_vp_o, rec_meta_o);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+// Map-frame points of ALL scans in one launch (batched form of dc_world_points): out[g] = R_s (vp + depth dir) + t_s
+// in fp64, poses = fp64 [S,16] row-major 4x4.
+template <typename T>
+__global__ void world_points_batched_kernel(const dc_scan_ptrs* __restrict__ tbl, const int64_t* __restrict__ first,
+                                            int n_scans, int64_t n, const double* __restrict__ poses, double* __restrict__ out) {
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const int s = dc_find_scan(first, n_scans, g);
+  const int64_t i = g - first[s];
+  const dc_scan_ptrs p = tbl[s];
+  const T* vps = reinterpret_cast<const T*>(p.vps);
+  const T* dirs = reinterpret_cast<const T*>(p.dirs);
+  const T* depth = reinterpret_cast<const T*>(p.depth);
+  const double* Tm = poses + 16 * (size_t)s;
+  const double d = (double)depth[i];
+  double x = d * (double)dirs[3 * i], y = d * (double)dirs[3 * i + 1], z = d * (double)dirs[3 * i + 2];
+  if (vps) { x += (double)vps[3 * i]; y += (double)vps[3 * i + 1]; z += (double)vps[3 * i + 2]; }
+  out[3 * g] = Tm[0] * x + Tm[1] * y + Tm[2] * z + Tm[3];
+  out[3 * g + 1] = Tm[4] * x + Tm[5] * y + Tm[6] * z + Tm[7];
+  out[3 * g + 2] = Tm[8] * x + Tm[9] * y + Tm[10] * z + Tm[11];
+}
+
+extern "C" int dc_world_points_batched(const void* scan_ptr_table, const int64_t* first, int n_scans, int64_t n, int dtype,
+                                       const double* poses, double* out, void* stream) {
+  if (n <= 0) return DC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = dc_blocks(n, 256);
+  const dc_scan_ptrs* tbl = (const dc_scan_ptrs*)scan_ptr_table;
+  if (dtype == DC_F32) world_points_batched_kernel<float><<<blocks, 256, 0, st>>>(tbl, first, n_scans, n, poses, out);
+  else world_points_batched_kernel<double><<<blocks, 256, 0, st>>>(tbl, first, n_scans, n, poses, out);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
 __global__ void set_loss_mask_kernel(const uint8_t* __restrict__ loss_mask, int64_t n, const int32_t* __restrict__ order,
                                      uint32_t* __restrict__ rec_meta) {
   const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

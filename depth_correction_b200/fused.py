@@ -36,6 +36,29 @@ def model_kind_of(model):
     raise NotImplementedError('fused step supports Polynomial / ScaledPolynomial models, got %s' % name)
 
 
+def scan_table(clouds, dt):
+    """Device table of per-scan tensor addresses for the batched kernels: (tbl int64 [S,5] = {vps, dirs, depth,
+    inc_angles, model mask} (0 = absent), first int64 [S+1], keep-alive list of the tensors the table points to)."""
+    rows, keep, first = [], [], [0]
+    dev = clouds[0].depth.device
+    for c in clouds:
+        cnt = len(c)
+        assert c.depth.dtype == dt and c.dirs.is_cuda
+        dirs = c.dirs.detach().reshape(-1, 3).contiguous()
+        vps = c.vps.detach()
+        vps = vps.to(dt).contiguous() if vps.shape[0] == cnt else vps.to(dt).expand(cnt, 3).contiguous()
+        depth = c.depth.detach().reshape(-1).contiguous()
+        inc = None if c.inc_angles is None else c.inc_angles.detach().reshape(-1).to(dt).contiguous()
+        mm = None if c.mask is None else c.mask.detach().to(torch.uint8).contiguous()
+        keep += [dirs, vps, depth, inc, mm]
+        rows.append([vps.data_ptr(), dirs.data_ptr(), depth.data_ptr(), 0 if inc is None else inc.data_ptr(),
+                     0 if mm is None else mm.data_ptr()])
+        first.append(first[-1] + cnt)
+    tbl = torch.tensor(rows, dtype=torch.int64).to(dev, non_blocking=True)
+    first_t = torch.tensor(first, dtype=torch.int64).to(dev, non_blocking=True)
+    return tbl, first_t, keep
+
+
 class StepState(object):
     def __init__(self, graph, clouds):
         """graph: Graph over the initial global cloud; clouds: per-scan local DepthClouds (in scan order)."""
@@ -62,21 +85,11 @@ class StepState(object):
         self.rec_dir_o = torch.empty((n, 4), dtype=dt, device=dev)
         self.rec_vp_o = torch.empty((n, 4), dtype=dt, device=dev)
         self.rec_meta_o = torch.empty(n, dtype=torch.int32, device=dev)
-        first = 0
-        for s, c in enumerate(clouds):
-            cnt = len(c)
-            assert c.depth.dtype == dt and c.dirs.is_cuda
-            dirs = c.dirs.detach().reshape(-1, 3).contiguous()
-            vps = c.vps.detach().to(dt).expand(cnt, 3).contiguous()
-            depth = c.depth.detach().reshape(-1).contiguous()
-            inc = None if c.inc_angles is None else c.inc_angles.detach().reshape(-1).to(dt).contiguous()
-            mm = None if c.mask is None else c.mask.detach().to(torch.uint8).contiguous()
-            # temporaries are released to the caching allocator in stream order, after the kernels below
-            L.call('dc_pack_records', L.ptr(vps), L.ptr(dirs), L.ptr(depth), L.ptr(inc), L.ptr(mm), None, self.code,
-                   first, cnt, s, L.ptr(smap.inv_order), L.ptr(self.rec_dir), L.ptr(self.rec_vp), L.ptr(self.rec_meta), st)
-            L.call('dc_pack_records', L.ptr(vps), L.ptr(dirs), L.ptr(depth), L.ptr(inc), L.ptr(mm), None, self.code,
-                   first, cnt, s, None, L.ptr(self.rec_dir_o), L.ptr(self.rec_vp_o), L.ptr(self.rec_meta_o), st)
-            first += cnt
+        # one launch for all scans (temporaries are released to the caching allocator in stream order)
+        tbl, first, _keep = scan_table(clouds, dt)
+        L.call('dc_pack_records_batched', L.ptr(tbl), L.ptr(first), len(clouds), n, self.code, L.ptr(smap.inv_order),
+               L.ptr(self.rec_dir), L.ptr(self.rec_vp), L.ptr(self.rec_meta), L.ptr(self.rec_dir_o), L.ptr(self.rec_vp_o),
+               L.ptr(self.rec_meta_o), st)
         self.has_inc = all(c.inc_angles is not None for c in clouds)
         self.P = torch.empty((n, 4), dtype=torch.float64, device=dev)
         self.stash = torch.empty((n, 8), dtype=torch.float64, device=dev)

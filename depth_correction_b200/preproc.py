@@ -15,7 +15,7 @@ from . import _lib as _L
 from .config import NeighborhoodType
 from .depth_cloud import DepthCloud
 from .filters import filter_depth, filter_eigenvalue_ratios, filter_eigenvalues, filter_valid_neighbors, within_bounds
-from .fused import StepState, model_kind_of
+from .fused import StepState, model_kind_of, scan_table
 from .graph import Graph, SortedMap, search
 from .transform import xyz_axis_angle_to_matrix
 
@@ -258,22 +258,13 @@ def _initial_map_points(cloud):
             and not any(f in cloud.__dict__ for f in ('vps', 'dirs', 'depth'))):
         return cloud.to_points().detach()
     dev = scans[0].depth.device
-    poses = cloud.poses_tensor().detach().to(device=dev, dtype=torch.float64).contiguous()
-    out = torch.empty((cloud.size(), 3), dtype=torch.float64, device=dev)
-    st = _L.stream()
-    first = 0
-    keep = []
-    for i, c in enumerate(scans):
-        n = len(c)
-        vps = c.vps.detach()
-        vps = None if vps.shape[0] != n else vps.contiguous()
-        if vps is None and bool(c.vps.any()):
-            vps = c.vps.detach().expand(n, 3).contiguous()
-        dirs, depth = c.dirs.detach().contiguous(), c.depth.detach().contiguous()
-        keep += [vps, dirs, depth]
-        _L.call('dc_world_points', _L.ptr(vps), _L.ptr(dirs), _L.ptr(depth), _L.dtype_code(depth.dtype), n,
-                _L.ptr(poses[i]), _L.ptr(out[first:first + n]), st)
-        first += n
+    dt = scans[0].depth.dtype
+    poses = cloud.poses_tensor().detach().to(device=dev, dtype=torch.float64).reshape(len(scans), 16).contiguous()
+    n = cloud.size()
+    out = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    tbl, first, _keep = scan_table(scans, dt)
+    _L.call('dc_world_points_batched', _L.ptr(tbl), _L.ptr(first), len(scans), n, _L.dtype_code(dt), _L.ptr(poses),
+            _L.ptr(out), _L.stream())
     return out
 
 

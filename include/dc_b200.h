@@ -164,6 +164,15 @@ int dc_pack_records(const void* vps, const void* dirs, const void* depth, const 
                     const uint8_t* model_mask, const uint8_t* loss_mask, int dtype, int64_t first, int64_t count,
                     int scan_id, const int32_t* inv_order, void* rec_dir, void* rec_vp, uint32_t* rec_meta,
                     void* stream);
+/* batched forms over all scans in one launch.  scan_ptr_table: device array [n_scans][5] of uint64 device
+ * addresses {vps, dirs, depth, inc_angles, model_mask} (0 = absent); first: int64 [n_scans+1] global row of the
+ * first point of every scan.  dc_pack_records_batched writes the sorted-space copy (through inv_order) and, when
+ * rec_*_o are given, the original-order copy; dc_world_points_batched writes out[n,3] fp64 with poses fp64 [S,16]. */
+int dc_pack_records_batched(const void* scan_ptr_table, const int64_t* first, int n_scans, int64_t n, int dtype,
+                            const int32_t* inv_order, void* rec_dir, void* rec_vp, uint32_t* rec_meta, void* rec_dir_o,
+                            void* rec_vp_o, uint32_t* rec_meta_o, void* stream);
+int dc_world_points_batched(const void* scan_ptr_table, const int64_t* first, int n_scans, int64_t n, int dtype,
+                            const double* poses, double* out, void* stream);
 /* overwrite the DC_PT_LOSS_MASK bit from a global-order mask (NULL = all true) */
 int dc_set_loss_mask(const uint8_t* loss_mask, int64_t n, const int32_t* order, uint32_t* rec_meta, void* stream);
 
