@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdcb200.so')
+LIB_PATH = os.environ.get('DC_B200_LIB') or os.path.join(_HERE, 'libdcb200.so')   # env override: kernel-variant experiments
 
 DC_F32, DC_F64 = 0, 1
 MODEL_NONE, MODEL_POLYNOMIAL, MODEL_SCALED_POLYNOMIAL = 0, 1, 2

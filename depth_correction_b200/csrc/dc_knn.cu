@@ -19,7 +19,12 @@
 #include "dc_grid.cuh"
 
 #define KNN_THREADS 128
+#ifndef KNN_BINS
 #define KNN_BINS 64
+#endif
+#ifndef KNN_MIN_BLOCKS
+#define KNN_MIN_BLOCKS 6
+#endif
 
 __device__ __forceinline__ bool knn_less(double a, int ja, double b, int jb) { return a < b || (a == b && ja < jb); }
 
@@ -50,7 +55,7 @@ __device__ __forceinline__ void knn_scan(const dc_grid& g, const uint64_t* __res
   }
 }
 
-__global__ void __launch_bounds__(KNN_THREADS)
+__global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_BLOCKS)
 knn_select_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
                   const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
                   const int32_t* __restrict__ cell_start, int k, double r2cap, int max_ring,
