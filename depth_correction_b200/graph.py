@@ -8,6 +8,7 @@ memory and tiny glue (permutation inverse, scalar read-backs at setup time).
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -294,7 +295,7 @@ def _knn_cell_size(points, k, r, bounds):
         c0 = max(max(h - l for l, h in zip(lo, hi)) / 256.0, 1e-9)
     # a disc of radius c on a surface with `occ` points per c^2 holds pi * occ points: occ ~ 0.45 k makes the
     # first ring of cells (guaranteed reach c) contain the k nearest for a typical query
-    target = max(0.45 * k, 2.0)
+    target = max(float(os.environ.get('DC_KNN_OCC', 0.45)) * k, 2.0)
     for _ in range(4):
         occ = SortedMap.occupancy_of(points, lo, hi, c0)
         if 0.8 * target <= occ <= 1.25 * target:
