@@ -229,9 +229,11 @@ def run_ours(args):
         prof = cProfile.Profile()
         prof.enable()
     t0.record()
+    torch.cuda.nvtx.range_push('timed_steps')      # ncu --nvtx --nvtx-include "timed_steps/" profiles exactly this region
     for _ in range(args.steps):
         loss, ns = one_step(dc, clouds, poses, deltas, model, cfg, timers=timers, local=local)
         gl = loss.detach()
+    torch.cuda.nvtx.range_pop()
     t1.record()
     sync()
     if prof is not None:
