@@ -8,25 +8,17 @@
 // passes and the selection is exact.  Rows are emitted UNSORTED (the step kernels only need the set);
 // dc_knn_sort_rows orders them by distance when the reference layout is exported.
 //
-// Two cooperating code paths write the same result:
-//  * warp path (the common case): one warp per slice of 32 queries.  Queries are cell-sorted, so the slice
-//    splits into a few groups that share a grid cell and therefore the same 3x3x3 block of candidate cells.
-//    The block (9 contiguous runs of the sorted map, <= 256 points) is staged once per group into shared
-//    memory with coalesced 256-bit loads and then held in registers (8 candidates per lane).  For every
-//    query of the group the lanes evaluate their candidates in parallel, build a 64-bin warp histogram with
-//    shared-memory integer atomics, find the boundary bin with one warp scan and compact the selected
-//    indices into a shared output tile with ballots.  No divergence, no per-thread state.
-//  * thread path (fallback, same algorithm per thread): queries whose first ring does not contain k
-//    candidates inside its guaranteed radius (sparse regions: the block of cells has to grow), groups with
-//    more than 256 candidates (very dense cells), k > 64, or when the caller wants the distances stored.
+// One query per thread (see knn_thread_query).  Two alternatives were built, were bit-exact, and lost on lidar maps
+// (profiles/r1c_knn_experiments.md): a warp-cooperative kernel (lanes = queries, the union of the candidate cells of a
+// slice staged once in shared memory as fp32 offsets with an fp64 tie-break; consecutive queries share too few
+// candidates -- union 1.6x the own set -- and every warp pays for its sparsest lane), and skipping rings from the
+// cell-table population with smaller cells (the scan is bound by per-row latency and divergence, not by candidates).
 #include "dc_common.cuh"
 #include "dc_grid.cuh"
 
 #define KNN_THREADS 128
 #define KNN_WARPS (KNN_THREADS / 32)
 #define KNN_BINS 64
-#define KNN_CAP 256          // candidates per cell group held in registers by the warp path (8 per lane)
-#define KNN_WARP_KMAX 64     // largest k served by the warp path (output tile in shared memory)
 
 __device__ __forceinline__ bool knn_less(double a, int ja, double b, int jb) { return a < b || (a == b && ja < jb); }
 
@@ -214,7 +206,6 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
   }
 }
 
-// thread-only kernel (k > KNN_WARP_KMAX, or the caller wants ell_d2)
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_thread_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
                   const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
@@ -245,219 +236,6 @@ knn_thread_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Warp path + thread fallback (see the header comment).
-// Shared memory per block: thread-path histograms | per warp: candidate xyz, candidate index, warp histogram,
-// output tile [32 queries][ks] with ks = k | 1 (odd stride: conflict-free column writes and row reads).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double knn_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
-__global__ void __launch_bounds__(KNN_THREADS)
-knn_warp_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
-                const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
-                const int32_t* __restrict__ cell_start, int k, double r2cap, int max_ring,
-                int32_t* __restrict__ ell_idx) {
-  extern __shared__ __align__(16) unsigned char knn_smem[];
-  const int ks = k | 1;
-  unsigned short* hist = reinterpret_cast<unsigned short*>(knn_smem);                       // [BINS][THREADS]
-  unsigned char* wbase = knn_smem + sizeof(unsigned short) * KNN_BINS * KNN_THREADS;
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t per_warp = sizeof(double) * 3 * KNN_CAP + sizeof(int) * KNN_CAP + sizeof(int) * KNN_BINS + sizeof(int) * 32 * ks;
-  unsigned char* wmem = wbase + per_warp * wid;
-  double* cxyz = reinterpret_cast<double*>(wmem);                                           // [3][CAP]
-  int* cjs = reinterpret_cast<int*>(wmem + sizeof(double) * 3 * KNN_CAP);                   // [CAP]
-  int* whist = cjs + KNN_CAP;                                                               // [BINS]
-  int* tile = whist + KNN_BINS;                                                             // [32][ks]
-
-  const int64_t slice = blockIdx.x * (int64_t)KNN_WARPS + wid;
-  const int64_t q = slice * DC_SLICE + lane;
-  if (nq <= 0 || slice > ((nq - 1) >> 5)) return;          // whole warp out of range (no block-wide sync is used)
-  const bool valid = q < nq;
-  dc_point pq;
-  pq.x = pq.y = pq.z = 0.0;
-  pq.tag = 0;
-  unsigned long long key = ~0ull;
-  if (valid) { pq = dc_ld_point(Q + q); key = qkeys[q]; }
-  int cnt = 0;                         // neighbours emitted for this lane's own query
-  unsigned int slow_mask = 0u;         // queries left to the thread path
-  const unsigned int lt_mask = (1u << lane) - 1u;
-  const double slack_cell = g.cell * (1.0 - 1e-9);
-  const bool last = max_ring <= 1;
-  const double reach2 = slack_cell * slack_cell;
-  const double bound2 = last ? r2cap : fmin(reach2, r2cap);
-  const double scale1 = (double)KNN_BINS / bound2;
-
-  unsigned int pending = __ballot_sync(0xffffffffu, valid);
-  while (pending) {
-    const int leader = __ffs(pending) - 1;
-    const unsigned long long key_l = __shfl_sync(0xffffffffu, key, leader);
-    const unsigned int group = __ballot_sync(0xffffffffu, valid && key == key_l) & pending;
-    pending &= ~group;
-    int c0, c1, c2;
-    dc_key_coords(g, key_l, c0, c1, c2);
-    // ---- the 9 candidate runs of the 3x3x3 block, one per lane
-    int lo = 0, hi = 0;
-    if (lane < 9) dc_row_range(g, pkeys, n, cell_start, c0 - 1, c0 + 1, c1 + (lane % 3) - 1, c2 + (lane / 3) - 1, lo, hi);
-    const int len = hi - lo;
-    int pre = len;                     // inclusive warp scan
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, pre, o);
-      if (lane >= o) pre += v;
-    }
-    const int total = __shfl_sync(0xffffffffu, pre, 31);
-    pre -= len;                        // exclusive
-    if (total > KNN_CAP) { slow_mask |= group; continue; }
-    // ---- stage the block into shared memory (coalesced 256-bit loads), then 8 candidates per lane in registers
-    __syncwarp();
-    for (int r = 0; r < 9; ++r) {
-      const int lo_r = __shfl_sync(0xffffffffu, lo, r), len_r = __shfl_sync(0xffffffffu, len, r);
-      const int pre_r = __shfl_sync(0xffffffffu, pre, r);
-      for (int l = lane; l < len_r; l += 32) {
-        const dc_point p = dc_ld_point(P + lo_r + l);
-        cxyz[pre_r + l] = p.x;
-        cxyz[KNN_CAP + pre_r + l] = p.y;
-        cxyz[2 * KNN_CAP + pre_r + l] = p.z;
-        cjs[pre_r + l] = lo_r + l;
-      }
-    }
-    __syncwarp();
-    double cx[8], cy[8], cz[8];
-    int cj[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int t = lane + 32 * u;
-      const bool have = t < total;
-      cx[u] = have ? cxyz[t] : 0.0;
-      cy[u] = have ? cxyz[KNN_CAP + t] : 0.0;
-      cz[u] = have ? cxyz[2 * KNN_CAP + t] : 0.0;
-      cj[u] = have ? cjs[t] : -1;
-    }
-    // ---- every query of the group, one after the other, all lanes on its candidates
-    unsigned int gm = group;
-    while (gm) {
-      const int ql = __ffs(gm) - 1;
-      gm &= gm - 1u;
-      dc_point qq;
-      qq.x = knn_shfl(pq.x, ql); qq.y = knn_shfl(pq.y, ql); qq.z = knn_shfl(pq.z, ql);
-      double d2[8];
-      int bin[8];
-      unsigned int inb = 0u;           // bit u: candidate u of this lane is inside the bound
-      int n_in = 0;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        dc_point c;
-        c.x = cx[u]; c.y = cy[u]; c.z = cz[u];
-        d2[u] = dc_dist2(c, qq);
-        const bool in = cj[u] >= 0 && d2[u] < bound2;
-        if (in) inb |= 1u << u;
-        n_in += __popc(__ballot_sync(0xffffffffu, in));
-      }
-      if (n_in < k && !last) {         // the covered radius does not hold k candidates: grow the block per thread
-        slow_mask |= 1u << ql;
-        continue;
-      }
-      int* col = tile + ql * ks;
-      int e = 0;                       // warp-uniform number of indices emitted for this query
-      if (n_in <= k) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const bool pr = (inb >> u) & 1u;
-          const unsigned int bal = __ballot_sync(0xffffffffu, pr);
-          if (pr) col[e + __popc(bal & lt_mask)] = cj[u];
-          e += __popc(bal);
-        }
-      } else {
-        // ---- warp histogram of d2 (64 bins, two per lane), boundary bin by one warp scan
-        whist[lane] = 0;
-        whist[lane + 32] = 0;
-        __syncwarp();
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          bin[u] = knn_bin(d2[u], scale1);
-          if ((inb >> u) & 1u) atomicAdd(&whist[bin[u]], 1);
-        }
-        __syncwarp();
-        const int h0 = whist[2 * lane], h1 = whist[2 * lane + 1];
-        int cum = h0 + h1;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, cum, o);
-          if (lane >= o) cum += v;
-        }
-        const int bl = __ffs(__ballot_sync(0xffffffffu, cum >= k)) - 1;      // n_in > k: some lane qualifies
-        const int excl_b = __shfl_sync(0xffffffffu, cum - h0 - h1, bl);
-        const int h0_b = __shfl_sync(0xffffffffu, h0, bl), h1_b = __shfl_sync(0xffffffffu, h1, bl);
-        int b1, c_lo, cnt1;
-        if (excl_b + h0_b >= k) { b1 = 2 * bl; c_lo = excl_b; cnt1 = h0_b; }
-        else { b1 = 2 * bl + 1; c_lo = excl_b + h0_b; cnt1 = h1_b; }
-        // ---- everything below the boundary bin
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const bool pr = ((inb >> u) & 1u) && bin[u] < b1;
-          const unsigned int bal = __ballot_sync(0xffffffffu, pr);
-          if (pr) col[e + __popc(bal & lt_mask)] = cj[u];
-          e += __popc(bal);
-        }
-        const int t = k - c_lo;        // 1 <= t <= cnt1 of the boundary bin belong to the k nearest
-        if (t == cnt1) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const bool pr = ((inb >> u) & 1u) && bin[u] == b1;
-            const unsigned int bal = __ballot_sync(0xffffffffu, pr);
-            if (pr) col[e + __popc(bal & lt_mask)] = cj[u];
-            e += __popc(bal);
-          }
-        } else {
-          // rank the boundary bin by (d2, index): t rounds of a warp arg-min
-          unsigned int open = 0u;
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (((inb >> u) & 1u) && bin[u] == b1) open |= 1u << u;
-          for (int s = 0; s < t; ++s) {
-            double bd = INFINITY;
-            int bj = 0x7fffffff;
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (((open >> u) & 1u) && knn_less(d2[u], cj[u], bd, bj)) { bd = d2[u]; bj = cj[u]; }
-            double md = bd;
-            int mj = bj;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const double od = __shfl_xor_sync(0xffffffffu, md, o);
-              const int oj = __shfl_xor_sync(0xffffffffu, mj, o);
-              if (knn_less(od, oj, md, mj)) { md = od; mj = oj; }
-            }
-            if (bj == mj) {            // this lane owns the winner (indices are unique)
-#pragma unroll
-              for (int u = 0; u < 8; ++u)
-                if (((open >> u) & 1u) && cj[u] == mj) open &= ~(1u << u);
-            }
-            if (lane == 0) col[e] = mj;
-            ++e;
-          }
-        }
-      }
-      if (lane == ql) cnt = e;
-    }
-  }
-  __syncwarp();
-  // ---- thread path for the queries the warp path handed over
-  if ((slow_mask >> lane) & 1u) {
-    int c0, c1, c2;
-    dc_key_coords(g, key, c0, c1, c2);
-    int* col = tile + lane * ks;
-    cnt = 0;
-    knn_thread_query(P, pkeys, n, g, cell_start, pq, c0, c1, c2, k, r2cap, max_ring, 1, hist + threadIdx.x,
-                     [&](int j, double) { col[cnt++] = j; });
-  }
-  __syncwarp();
-  // ---- flush the tile: coalesced 128-byte rows of the sliced-ELL layout
-  int32_t* out = ell_idx + slice * (int64_t)k * DC_SLICE + lane;
-  const int* col = tile + lane * ks;
-  for (int c = 0; c < k; ++c) out[(int64_t)c * DC_SLICE] = (valid && c < cnt) ? col[c] : -1;
-}
-
 extern "C" int dc_knn(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
                       const dc_grid_spec* spec, const int32_t* cell_start, int k, double r, int32_t* ell_idx,
                       double* ell_d2, void* stream) {
@@ -479,28 +257,9 @@ extern "C" int dc_knn(const void* P, const uint64_t* pkeys, int64_t n, const voi
   if (max_ring < 1) max_ring = 1;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n_slices = (nq + DC_SLICE - 1) / DC_SLICE;
-  // The warp path wins on maps of uniform density; on lidar maps (density varies by orders of magnitude: 40% of
-  // the cell groups exceed 256 candidates and a third of the queries need a second ring) the thread path is
-  // faster, so it is the default.  DC_KNN_PATH=warp selects the warp path.
-  const char* path = getenv("DC_KNN_PATH");
-  const bool use_warp = path && path[0] == 'w';
-  if (ell_d2 || k > KNN_WARP_KMAX || !use_warp) {
-    const int blocks = dc_blocks(n_slices * DC_SLICE, KNN_THREADS);
-    knn_thread_kernel<<<blocks, KNN_THREADS, 0, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq, g, cell_start, k,
-                                                      r2cap, max_ring, ell_idx, ell_d2);
-  } else {
-    const int ks = k | 1;
-    const size_t per_warp = sizeof(double) * 3 * KNN_CAP + sizeof(int) * KNN_CAP + sizeof(int) * KNN_BINS + sizeof(int) * 32 * ks;
-    const size_t smem = sizeof(unsigned short) * KNN_BINS * KNN_THREADS + per_warp * KNN_WARPS;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-      DC_CUDA_CHECK(cudaFuncSetAttribute(knn_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
-    }
-    const int blocks = (int)((n_slices + KNN_WARPS - 1) / KNN_WARPS);
-    knn_warp_kernel<<<blocks, KNN_THREADS, smem, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq, g, cell_start, k,
-                                                       r2cap, max_ring, ell_idx);
-  }
+  const int blocks = dc_blocks(n_slices * DC_SLICE, KNN_THREADS);
+  knn_thread_kernel<<<blocks, KNN_THREADS, 0, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq, g, cell_start, k,
+                                                    r2cap, max_ring, ell_idx, ell_d2);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

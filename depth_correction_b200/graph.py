@@ -60,8 +60,14 @@ class SortedMap(object):
             spec.origin[a] = lo[a] - 1e-3 * cell
             spec.dims[a] = int(math.floor((hi[a] - spec.origin[a]) / cell)) + 1
             ext.append(hi[a] - lo[a])
-        # fastest key digit = shortest extent, slowest = longest (slabs along the trajectory stay contiguous)
-        axes = sorted(range(3), key=lambda a: (ext[a], a))
+        # Fastest key digit = LONGEST extent: surfaces of a mapped corridor / street run along the trajectory, so a
+        # row of cells along that axis is one long contiguous run of the sorted map and 32 consecutive queries
+        # share (almost) the same block of candidate cells (what the segment kNN kernel stages once per warp).
+        # DC_AXIS_ORDER=short restores shortest-first.
+        if os.environ.get('DC_AXIS_ORDER', 'long')[0] == 's':
+            axes = sorted(range(3), key=lambda a: (ext[a], a))
+        else:
+            axes = sorted(range(3), key=lambda a: (-ext[a], a))
         for i, a in enumerate(axes):
             spec.axis[i] = a
         n_cells = int(spec.dims[0]) * int(spec.dims[1]) * int(spec.dims[2])
@@ -293,9 +299,9 @@ def _knn_cell_size(points, k, r, bounds):
         c0 = float(r)
     else:
         c0 = max(max(h - l for l, h in zip(lo, hi)) / 256.0, 1e-9)
-    # a disc of radius c on a surface with `occ` points per c^2 holds pi * occ points: occ ~ 0.45 k makes the
-    # first ring of cells (guaranteed reach c) contain the k nearest for a typical query
-    target = max(float(os.environ.get('DC_KNN_OCC', 0.45)) * k, 2.0)
+    # a disc of radius c on a surface with `occ` points per c^2 holds pi * occ points; the mean occupancy is dominated
+    # by sparse cells (a typical QUERY sits in a cell 2x as full), measured optimum on lidar maps: occ ~ 0.3 k
+    target = max(float(os.environ.get('DC_KNN_OCC', 0.3)) * k, 2.0)
     for _ in range(4):
         occ = SortedMap.occupancy_of(points, lo, hi, c0)
         if 0.8 * target <= occ <= 1.25 * target:

@@ -105,6 +105,59 @@ def test_nn_large_random_vs_ckdtree(dc, dev):
             assert torch.equal(dist.cpu(), d_ref)
 
 
+def _corridor_world_points(n_scans, rings, azimuths):
+    from depth_correction_b200.synthetic import make_sequence
+    scans, poses, _ = make_sequence('corridor', n_scans=n_scans, pattern='os0-128', seed=3, rings=rings, azimuths=azimuths)
+    out = []
+    for s, T in zip(scans, poses):
+        out.append(s['points'].astype(np.float64) @ T[:3, :3].T + T[:3, 3])
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize('cell', [None, 0.05, 0.23])
+def test_knn_lidar_map_vs_ckdtree(dc, dev, cell):
+    """Lidar-shaped map (density varies by orders of magnitude, points on planes, fp64 world coordinates) with
+    the automatic cell size, much smaller and much larger cells: ring skipping / growth must reproduce cKDTree."""
+    from oracle import oracle
+    from depth_correction_b200.graph import search
+    pts = _corridor_world_points(5, 64, 512)
+    p = torch.as_tensor(pts, device=dev)
+    p64 = torch.as_tensor(pts)
+    for kw in (dict(k=32, r=0.4), dict(k=12), dict(k=48, r=0.25)):
+        g = search(p, None, cell=cell, **kw)
+        idx, dist = g.neighbors(), g.distances()
+        d_ref, i_ref = oracle.nearest_neighbors(p64, **kw)
+        assert torch.equal(idx.cpu(), i_ref), (cell, kw)
+        assert torch.equal(dist.cpu(), d_ref), (cell, kw)
+
+
+def test_knn_duplicates_and_sparse_tail(dc, dev):
+    """Exact duplicates (more than 8 ties in the boundary bin -> second histogram level / repeated minimum) and a
+    sparse tail (ring growth, ring skipping from the cell table): distances bit-exact vs cKDTree; indices are
+    validated through the distances they realise (tie order is implementation defined)."""
+    from oracle import oracle
+    rng = np.random.default_rng(11)
+    c = rng.uniform(-5, 5, (50, 3))
+    pts = (c[rng.integers(0, 50, 60000)] + rng.normal(0, 0.2, (60000, 3))).astype(np.float32)
+    pts[1000:1400] = pts[:400]                       # exact duplicates
+    pts[2000:2040] = pts[0]                          # 41 copies of one location
+    pts[3000:3200] = rng.uniform(-40, 40, (200, 3)).astype(np.float32)     # isolated points far from everything
+    p = torch.as_tensor(pts, device=dev)
+    p64 = torch.as_tensor(pts.astype(np.float64))
+    for kw in (dict(k=16), dict(k=32, r=0.3), dict(k=5, r=0.05)):
+        dist, idx = dc.nearest_neighbors(p, p, **kw)
+        d_ref, i_ref = oracle.nearest_neighbors(p64, **kw)
+        assert torch.equal(dist.cpu(), d_ref), kw
+        idx = idx.cpu()
+        assert torch.equal(idx >= 0, i_ref >= 0)
+        df = p64[idx.clamp(min=0)] - p64[:, None, :]
+        realised = (df * df).sum(dim=2).sqrt()
+        fin = idx >= 0
+        assert torch.allclose(realised[fin], d_ref[fin], rtol=1e-14, atol=0.0), kw    # (torch may contract / reorder the sum)
+        srt = idx.sort(dim=1).values
+        assert ((srt[:, 1:] != srt[:, :-1]) | (srt[:, 1:] < 0)).all(), 'a neighbour is listed twice'
+
+
 def test_graph_roundtrip_and_transpose(dc, dev, golden):
     from depth_correction_b200.graph import Graph, SortedMap, search
     g = golden('nn')
