@@ -50,7 +50,7 @@ SIGNATURES = {
     'dc_bounds': [_P, _I, _L, _P, _P, _P],
     'dc_cell_keys': [_P, _I, _L, _SPEC, _P, _P, _P],
     'dc_sort_pairs': [_P, _P, _P, _P, _L, _I, _P, _SZP, _P],
-    'dc_gather_points': [_P, _I, _P, _L, _P, _P],
+    'dc_gather_points': [_P, _I, _P, _L, _P, _P, _P],
     'dc_cell_table': [_P, _L, _L, _P, _P],
     'dc_radius_count': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _D, _P, _P, _P],
     'dc_ell_offsets': [_P, _L, _P, _P, _SZP, _P],
@@ -85,6 +85,7 @@ SIGNATURES = {
     'dc_eigh3_backward': [_P, _P, _I, _L, _P, _P, _P, _P],
     'dc_normals_angles': [_P, _P, _I, _L, _I, _P, _P, _P],
     'dc_world_points': [_P, _P, _P, _I, _L, _P, _P, _P],
+    'dc_from_points': [_P, _P, _I, _L, _P, _P, _P, _P],
 }
 
 for _name, _args in SIGNATURES.items():
@@ -111,6 +112,16 @@ def ptr(t):
 
 def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def upload(host, dtype, device):
+    """Small host table -> device without draining the stream: a pageable cudaMemcpy waits for everything already
+    queued, a copy from pinned memory (torch's caching host allocator recycles the staging block in stream order) is
+    just another stream operation."""
+    t = torch.as_tensor(host, dtype=dtype)
+    if torch.device(device).type != 'cuda':
+        return t
+    return t.pin_memory().to(device, non_blocking=True)
 
 
 def dtype_code(dt):

@@ -256,3 +256,37 @@ extern "C" int dc_world_points(const void* vps, const void* dirs, const void* de
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// DepthCloud.from_points (depth_cloud.py:592-638): dirs = (x - vp) / |x - vp| where the depth is positive,
+// depth = |x - vp|, in the cloud's own dtype.  One launch, no host synchronisation (the reference's boolean-mask
+// assignment `dirs[valid] = ...` costs a nonzero() + device sync per scan).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void from_points_kernel(const T* __restrict__ pts, const T* __restrict__ vps, int64_t n, T* __restrict__ dirs,
+                                   T* __restrict__ depth, T* __restrict__ vps_out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T vx = 0, vy = 0, vz = 0;
+  if (vps) { vx = vps[3 * i]; vy = vps[3 * i + 1]; vz = vps[3 * i + 2]; }
+  T dx = pts[3 * i] - vx, dy = pts[3 * i + 1] - vy, dz = pts[3 * i + 2] - vz;
+  const T d = sqrt(dx * dx + dy * dy + dz * dz);
+  if (d > (T)0) { dx /= d; dy /= d; dz /= d; }      // NaN depth: left as is, like the reference's mask
+  dirs[3 * i] = dx; dirs[3 * i + 1] = dy; dirs[3 * i + 2] = dz;
+  depth[i] = d;
+  if (vps_out) { vps_out[3 * i] = vx; vps_out[3 * i + 1] = vy; vps_out[3 * i + 2] = vz; }
+}
+
+extern "C" int dc_from_points(const void* points, const void* vps, int dtype, int64_t n, void* dirs, void* depth,
+                              void* vps_out, void* stream) {
+  if (n <= 0) return DC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DC_F32)
+    from_points_kernel<float><<<dc_blocks(n, 256), 256, 0, st>>>((const float*)points, (const float*)vps, n, (float*)dirs,
+                                                                 (float*)depth, (float*)vps_out);
+  else
+    from_points_kernel<double><<<dc_blocks(n, 256), 256, 0, st>>>((const double*)points, (const double*)vps, n, (double*)dirs,
+                                                                  (double*)depth, (double*)vps_out);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}

@@ -181,7 +181,7 @@ extern "C" int dc_ell_offsets(const int32_t* slice_width, int64_t n_slices, int6
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void gather_points_kernel(const T* __restrict__ pts, const int32_t* __restrict__ order, int64_t n,
-                                     dc_point* __restrict__ out) {
+                                     dc_point* __restrict__ out, int32_t* __restrict__ inv_order) {
   const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (s >= n) return;
   const int64_t o = order[s];
@@ -189,16 +189,17 @@ __global__ void gather_points_kernel(const T* __restrict__ pts, const int32_t* _
   p.x = (double)pts[3 * o]; p.y = (double)pts[3 * o + 1]; p.z = (double)pts[3 * o + 2];
   p.tag = o;
   out[s] = p;
+  if (inv_order) inv_order[o] = (int32_t)s;
 }
 
 extern "C" int dc_gather_points(const void* pts, int dtype, const int32_t* order, int64_t n, void* sorted_points,
-                                void* stream) {
+                                int32_t* inv_order, void* stream) {
   if (n <= 0) return DC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DC_F32)
-    gather_points_kernel<float><<<dc_blocks(n, 256), 256, 0, st>>>((const float*)pts, order, n, (dc_point*)sorted_points);
+    gather_points_kernel<float><<<dc_blocks(n, 256), 256, 0, st>>>((const float*)pts, order, n, (dc_point*)sorted_points, inv_order);
   else
-    gather_points_kernel<double><<<dc_blocks(n, 256), 256, 0, st>>>((const double*)pts, order, n, (dc_point*)sorted_points);
+    gather_points_kernel<double><<<dc_blocks(n, 256), 256, 0, st>>>((const double*)pts, order, n, (dc_point*)sorted_points, inv_order);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

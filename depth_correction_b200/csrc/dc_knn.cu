@@ -63,7 +63,8 @@ template <typename Emit>
 __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
                                                  const dc_grid& g, const int32_t* __restrict__ cell_start,
                                                  const dc_point& pq, int c0, int c1, int c2, int k, double r2cap,
-                                                 int max_ring, int first_ring, unsigned short* h, Emit&& emit) {
+                                                 int max_ring, int first_ring, unsigned short* h, double* ld, int* lj,
+                                                 Emit&& emit) {
   const double slack_cell = g.cell * (1.0 - 1e-9);
   // ---- 1. ring growth + level-1 histogram
   int rho = first_ring;
@@ -134,10 +135,10 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
   const unsigned int t = (unsigned int)k - c_lo;     // how many of the cnt2 boundary candidates are neighbours
   const bool take_all = (t == cnt2);
   const bool use_list = !take_all && cnt2 <= 8u;
-  double bd[8];
-  int bj[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { bd[i] = INFINITY; bj[i] = 0x7fffffff; }
+  // The (<= 8) candidates of the boundary bin are only collected during the scan (shared-memory column of this
+  // thread) and ranked afterwards with the warp converged: ranking inside the scan ran one lane at a time and
+  // cost 17 % of all instructions of the kernel.
+  int nb = 0;
   knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
     if (d2 < bound2) {
       const double s = d2 * scale1;
@@ -156,13 +157,10 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
         if (boundary) {
           if (take_all) {
             emit(j, d2);
-          } else if (use_list) {
-#pragma unroll
-            for (int i = 7; i >= 0; --i) {
-              const bool lt_prev = (i > 0) ? knn_less(d2, j, bd[i > 0 ? i - 1 : 0], bj[i > 0 ? i - 1 : 0]) : false;
-              if (lt_prev) { bd[i] = bd[i > 0 ? i - 1 : 0]; bj[i] = bj[i > 0 ? i - 1 : 0]; }
-              else if (knn_less(d2, j, bd[i], bj[i])) { bd[i] = d2; bj[i] = j; }
-            }
+          } else if (use_list && nb < 8) {
+            ld[nb * KNN_THREADS] = d2;
+            lj[nb * KNN_THREADS] = j;
+            ++nb;
           }
         }
       }
@@ -170,9 +168,20 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
   });
   if (take_all) return;
   if (use_list) {
+    double bd[8];
+    int bj[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if ((unsigned int)i < t) emit(bj[i], bd[i]);
+    for (int i = 0; i < 8; ++i) {
+      bd[i] = i < nb ? ld[i * KNN_THREADS] : INFINITY;
+      bj[i] = i < nb ? lj[i * KNN_THREADS] : 0x7fffffff;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      unsigned int rank = 0u;          // candidates of the bin that precede candidate i in (d2, index) order
+#pragma unroll
+      for (int m = 0; m < 8; ++m) rank += knn_less(bd[m], bj[m], bd[i], bj[i]) ? 1u : 0u;
+      if (i < nb && rank < t) emit(bj[i], bd[i]);
+    }
     return;
   }
   // more than 8 candidates share the boundary sub-bin (exact ties / duplicates): repeated minimum
@@ -212,6 +221,8 @@ knn_thread_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
                   const int32_t* __restrict__ cell_start, int k, double r2cap, int max_ring,
                   int32_t* __restrict__ ell_idx, double* __restrict__ ell_d2) {
   __shared__ unsigned short hist[KNN_BINS][KNN_THREADS];
+  __shared__ double list_d[8][KNN_THREADS];
+  __shared__ int list_j[8][KNN_THREADS];
   const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int32_t* out_j = ell_idx + (q >> 5) * (int64_t)k * DC_SLICE + lane;
@@ -222,6 +233,7 @@ knn_thread_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
     int c0, c1, c2;
     dc_key_coords(g, qkeys[q], c0, c1, c2);
     knn_thread_query(P, pkeys, n, g, cell_start, pq, c0, c1, c2, k, r2cap, max_ring, 1, &hist[0][threadIdx.x],
+                     &list_d[0][threadIdx.x], &list_j[0][threadIdx.x],
                      [&](int j, double d2) {
                        out_j[(int64_t)cnt * DC_SLICE] = j;
                        if (out_d) out_d[(int64_t)cnt * DC_SLICE] = d2;

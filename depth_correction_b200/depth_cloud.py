@@ -20,6 +20,7 @@ import torch
 from .nearest_neighbors import ball_angle_to_distance, nearest_neighbors
 from .graph import search
 from . import ops
+from . import _lib as L
 from .utils import covs, trace
 
 __all__ = ['DepthCloud']
@@ -432,9 +433,24 @@ class DepthCloud(object):
         assert isinstance(pts, torch.Tensor)
         if vps is not None:
             vps = torch.as_tensor(vps, dtype=dtype, device=device)
-        else:
+            assert vps.shape == pts.shape
+        if pts.is_cuda and pts.dim() == 2 and pts.shape[1] == 3 and pts.dtype in (torch.float32, torch.float64) \
+                and not pts.requires_grad and (vps is None or not vps.requires_grad):
+            # one kernel, no host synchronisation (dc_from_points)
+            n = pts.shape[0]
+            src = pts.contiguous()
+            dirs = torch.empty_like(src)
+            depth = torch.empty((n, 1), dtype=src.dtype, device=src.device)
+            vps_out = torch.empty_like(src)
+            L.call('dc_from_points', L.ptr(src), L.ptr(vps.contiguous()) if vps is not None else None,
+                   L.dtype_code(src.dtype), n, L.ptr(dirs), L.ptr(depth), L.ptr(vps_out), L.stream())
+            kwargs = {'vps': vps_out, 'depth': depth, 'dirs': dirs}
+            if normals is not None:
+                kwargs['normals'] = torch.as_tensor(normals, dtype=dtype, device=device)
+            return DepthCloud(**kwargs)
+        # host-side container construction (CPU tensors, or points that carry autograd history)
+        if vps is None:
             vps = torch.zeros_like(pts)
-        assert vps.shape == pts.shape
         dirs = pts - vps
         depth = dirs.norm(dim=-1, keepdim=True)
         valid = depth[:, 0] > 0.0

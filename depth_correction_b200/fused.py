@@ -54,8 +54,9 @@ def scan_table(clouds, dt):
         rows.append([vps.data_ptr(), dirs.data_ptr(), depth.data_ptr(), 0 if inc is None else inc.data_ptr(),
                      0 if mm is None else mm.data_ptr()])
         first.append(first[-1] + cnt)
-    tbl = torch.tensor(rows, dtype=torch.int64).to(dev, non_blocking=True)
-    first_t = torch.tensor(first, dtype=torch.int64).to(dev, non_blocking=True)
+    both = L.upload(rows + [[f, 0, 0, 0, 0] for f in first], torch.int64, dev)      # one copy for both tables
+    tbl = both[:len(rows)]
+    first_t = both[len(rows):, 0].contiguous()
     return tbl, first_t, keep
 
 
@@ -108,10 +109,13 @@ class StepState(object):
         blk_start = np.repeat(scan_first[:-1], nb) + within * CHAIN_CHUNK
         blk_count = np.minimum(np.repeat(sz, nb) - within * CHAIN_CHUNK, CHAIN_CHUNK).astype(np.int32)
         self.chain_blocks = int(nb.sum())
-        self.blk_scan = torch.as_tensor(blk_scan, device=dev)
-        self.blk_start = torch.as_tensor(blk_start, device=dev)
-        self.blk_count = torch.as_tensor(blk_count, device=dev)
-        self.scan_blk_first = torch.as_tensor(blk_first, device=dev)
+        nbk = self.chain_blocks
+        tab = L.upload(np.concatenate([blk_start, blk_scan.astype(np.int64), blk_count.astype(np.int64),
+                                       blk_first.astype(np.int64)]), torch.int64, dev)    # one async copy
+        self.blk_start = tab[:nbk]
+        self.blk_scan = tab[nbk:2 * nbk].to(torch.int32)
+        self.blk_count = tab[2 * nbk:3 * nbk].to(torch.int32)
+        self.scan_blk_first = tab[3 * nbk:].to(torch.int32)
         self.chain_partials = torch.empty(max(self.chain_blocks, 1) * CHAIN_REC, dtype=torch.float64, device=dev)
         self._mask_key = None
         self.generation = 0

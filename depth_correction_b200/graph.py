@@ -115,9 +115,9 @@ class SortedMap(object):
             L.call('dc_cell_keys', L.ptr(points), code, n, ctypes.byref(self.spec), L.ptr(keys), L.ptr(ids), st)
             L.call_with_temp('dc_sort_pairs', dev, L.ptr(keys), L.ptr(self.keys), L.ptr(ids), L.ptr(self.order), n,
                              self.key_bits, after=(st,))
-            L.call('dc_gather_points', L.ptr(points), code, L.ptr(self.order), n, L.ptr(self.P), st)
         self.inv_order = torch.empty(n, dtype=torch.int32, device=dev)
-        self.inv_order[self.order.long()] = torch.arange(n, dtype=torch.int32, device=dev)
+        if n > 0:
+            L.call('dc_gather_points', L.ptr(points), code, L.ptr(self.order), n, L.ptr(self.P), L.ptr(self.inv_order), st)
         self.cell_start = None
         if 0 < self.n_cells <= DENSE_TABLE_MAX_CELLS and n > 0:
             self.cell_start = torch.empty(self.n_cells + 1, dtype=torch.int32, device=dev)
@@ -139,7 +139,7 @@ class SortedMap(object):
             L.call('dc_cell_keys', L.ptr(query), code, nq, ctypes.byref(self.spec), L.ptr(keys), L.ptr(ids), st)
             L.call_with_temp('dc_sort_pairs', dev, L.ptr(keys), L.ptr(qkeys), L.ptr(ids), L.ptr(qorder), nq,
                              self.key_bits, after=(st,))
-            L.call('dc_gather_points', L.ptr(query), code, L.ptr(qorder), nq, L.ptr(Q), st)
+            L.call('dc_gather_points', L.ptr(query), code, L.ptr(qorder), nq, L.ptr(Q), None, st)
         return Q, qkeys, qorder
 
     def occupancy(self):
@@ -291,11 +291,23 @@ class Graph(object):
         return Graph(smap, sp, idx, n, K, mode='imported', symmetric=False)
 
 
+# (k, r, dtype, device) -> (n, cell, occupancy target) of the last estimate: a map that is searched again (training loops
+# rebuild the graph of the same scans after pose updates) starts from the previous cell size and usually needs one
+# confirming pass instead of three
+_cell_hint = {}
+
+
 def _knn_cell_size(points, k, r, bounds):
-    """Cell edge for kNN search: aim at ~k/4 points per occupied cell (surface-like data puts ~9
-    occupied cells in a 3x3x3 block), estimated from one coarse sort."""
+    """Cell edge for kNN search: aim at ~0.3 k points per occupied cell, estimated from key-only sorts."""
     lo, hi = bounds
-    if r:
+    hint_key = (int(k), float(r) if r else None, points.dtype, str(points.device))
+    hint = _cell_hint.get(hint_key)
+    if hint is not None and 0.8 * hint[0] <= points.shape[0] <= 1.25 * hint[0] \
+            and hint[2] == os.environ.get('DC_KNN_OCC', '0.3'):
+        c0 = hint[1]
+        if 0.95 * hint[0] <= points.shape[0] <= 1.05 * hint[0]:
+            return c0           # same map size: the cell size only steers speed, never the result
+    elif r:
         c0 = float(r)
     else:
         c0 = max(max(h - l for l, h in zip(lo, hi)) / 256.0, 1e-9)
@@ -310,6 +322,7 @@ def _knn_cell_size(points, k, r, bounds):
         if r and c0 > r:
             c0 = float(r)
             break
+    _cell_hint[hint_key] = (points.shape[0], c0, os.environ.get('DC_KNN_OCC', '0.3'))
     return c0
 
 

@@ -78,8 +78,9 @@ int dc_cell_keys(const void* pts, int dtype, int64_t n, const dc_grid_spec* spec
 int dc_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const int32_t* ids_in, int32_t* ids_out, int64_t n,
                   int end_bit, void* temp, size_t* temp_bytes, void* stream);
 
-/* sorted[s] = {double(pts[order[s]]), tag = order[s]}   (32-byte records) */
-int dc_gather_points(const void* pts, int dtype, const int32_t* order, int64_t n, void* sorted_points, void* stream);
+/* sorted[s] = {double(pts[order[s]]), tag = order[s]}   (32-byte records); inv_order[order[s]] = s when given */
+int dc_gather_points(const void* pts, int dtype, const int32_t* order, int64_t n, void* sorted_points,
+                     int32_t* inv_order, void* stream);
 
 /* dense table cell_start[c] = first sorted position with key >= c, c in [0, n_cells] (optional accelerator) */
 int dc_cell_table(const uint64_t* keys_sorted, int64_t n, int64_t n_cells, int32_t* cell_start, void* stream);
@@ -237,6 +238,10 @@ int dc_eigh3_backward(const void* eigvals, const void* eigvecs, int dtype, int64
  * (device): cloud.transform(pose).to_points() for the initial global cloud (preproc.py:108-119,180).  vps may be NULL. */
 int dc_world_points(const void* vps, const void* dirs, const void* depth, int dtype, int64_t n, const double* pose,
                     double* out, void* stream);
+/* DepthCloud.from_points (depth_cloud.py:592-638): dirs[n,3] = (points - vps) / depth where depth > 0,
+ * depth[n] = |points - vps|, vps_out[n,3] = vps (zeros when vps == NULL; vps_out may be NULL).  Cloud dtype. */
+int dc_from_points(const void* points, const void* vps, int dtype, int64_t n, void* dirs, void* depth, void* vps_out,
+                   void* stream);
 /* normals = -sign(dirs . v0) v0, inc = arccos(|dirs . n|) or arccos(-dirs . n)  (depth_cloud.py:401-424) */
 int dc_normals_angles(const void* dirs, const void* eigvecs, int dtype, int64_t n, int use_normal_sign, void* normals,
                       void* inc_angles, void* stream);
