@@ -205,14 +205,36 @@ extern "C" int dc_gather_points(const void* pts, int dtype, const int32_t* order
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void cell_table_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t n_cells, int32_t* cell_start) {
-  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c > n_cells) return;
-  cell_start[c] = (int32_t)dc_lower_bound(keys, n, (uint64_t)c);
+// cell_start[c] = first sorted position with key >= c, for c = 0 .. n_cells.  Position s "owns" the cells
+// (key[s-1], key[s]] (and position n the cells above the last key); a warp fills the gaps of its 32 positions
+// cooperatively, so a long run of empty cells costs one coalesced sweep instead of one thread's serial loop
+// (the previous version did a 23-step binary search for each of the ~14 M cells of the bench grid).
+__global__ void cell_table_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t n_cells, int32_t* __restrict__ cell_start) {
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;     // 0 .. n (inclusive), rounded up to a warp
+  const int lane = threadIdx.x & 31;
+  int64_t first = 0, last = -1;      // cells first .. last get the value s
+  if (s <= n) {
+    first = s == 0 ? 0 : (int64_t)keys[s - 1] + 1;
+    last = s == n ? n_cells : (int64_t)keys[s];
+  }
+  const int64_t len = last - first + 1;
+  if (len > 0 && len <= 4) {         // the common case: a handful of empty cells between occupied ones
+    for (int64_t c = first; c <= last; ++c) cell_start[c] = (int32_t)s;
+  }
+  unsigned int big = __ballot_sync(0xffffffffu, len > 4);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1u;
+    const int64_t f = __shfl_sync(0xffffffffu, first, src), l = __shfl_sync(0xffffffffu, last, src);
+    const int32_t v = (int32_t)__shfl_sync(0xffffffffu, s, src);
+    for (int64_t c = f + lane; c <= l; c += 32) cell_start[c] = v;
+  }
 }
 
 extern "C" int dc_cell_table(const uint64_t* keys_sorted, int64_t n, int64_t n_cells, int32_t* cell_start, void* stream) {
-  cell_table_kernel<<<dc_blocks(n_cells + 1, 256), 256, 0, (cudaStream_t)stream>>>(keys_sorted, n, n_cells, cell_start);
+  if (n_cells < 0 || n < 0) return dc_set_error(DC_ERR_ARG, "dc_cell_table: negative size");
+  const int64_t threads = ((n + 1 + 31) / 32) * 32;
+  cell_table_kernel<<<dc_blocks(threads, 256), 256, 0, (cudaStream_t)stream>>>(keys_sorted, n, n_cells, cell_start);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

@@ -35,7 +35,8 @@ __device__ __forceinline__ void knn_scan(const dc_grid& g, const uint64_t* __res
     for (int e1 = -rho; e1 <= rho; ++e1) {
       int lo, hi;
       dc_row_range(g, pkeys, n, cell_start, c0 - rho, c0 + rho, c1 + e1, c2 + e2, lo, hi);
-      // four independent candidate loads in flight per thread (the loop is latency bound otherwise)
+      // four independent candidate loads in flight per thread (the loop is latency bound otherwise; a software
+      // pipeline with eight in flight cost registers / occupancy and was 30 % slower)
       int j = lo;
       for (; j + 4 <= hi; j += 4) {
         const dc_point p0 = dc_ld_point(P + j), p1 = dc_ld_point(P + j + 1);
@@ -63,8 +64,7 @@ template <typename Emit>
 __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
                                                  const dc_grid& g, const int32_t* __restrict__ cell_start,
                                                  const dc_point& pq, int c0, int c1, int c2, int k, double r2cap,
-                                                 int max_ring, int first_ring, unsigned short* h, double* ld, int* lj,
-                                                 Emit&& emit) {
+                                                 int max_ring, int first_ring, unsigned short* h, Emit&& emit) {
   const double slack_cell = g.cell * (1.0 - 1e-9);
   // ---- 1. ring growth + level-1 histogram
   int rho = first_ring;
@@ -135,8 +135,8 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
   const unsigned int t = (unsigned int)k - c_lo;     // how many of the cnt2 boundary candidates are neighbours
   const bool take_all = (t == cnt2);
   const bool use_list = !take_all && cnt2 <= 8u;
-  // The (<= 8) candidates of the boundary bin are only collected during the scan (shared-memory column of this
-  // thread) and ranked afterwards with the warp converged: ranking inside the scan ran one lane at a time and
+  // The (<= 8) candidates of the boundary bin are only collected during the scan (in this thread's histogram
+  // column, which is no longer needed) and ranked afterwards with the warp converged: ranking inside the scan ran one lane at a time and
   // cost 17 % of all instructions of the kernel.
   int nb = 0;
   knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
@@ -158,8 +158,16 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
           if (take_all) {
             emit(j, d2);
           } else if (use_list && nb < 8) {
-            ld[nb * KNN_THREADS] = d2;
-            lj[nb * KNN_THREADS] = j;
+            // the histogram is dead by now: entry nb lives in this thread's counters 6 nb .. 6 nb + 5
+            // (four 16-bit pieces of d2, two of j), which keeps the block at 16 KB of shared memory
+            const unsigned long long u = (unsigned long long)__double_as_longlong(d2);
+            unsigned short* e = h + 6 * nb * KNN_THREADS;
+            e[0] = (unsigned short)u;
+            e[KNN_THREADS] = (unsigned short)(u >> 16);
+            e[2 * KNN_THREADS] = (unsigned short)(u >> 32);
+            e[3 * KNN_THREADS] = (unsigned short)(u >> 48);
+            e[4 * KNN_THREADS] = (unsigned short)j;
+            e[5 * KNN_THREADS] = (unsigned short)((unsigned int)j >> 16);
             ++nb;
           }
         }
@@ -172,8 +180,12 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
     int bj[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      bd[i] = i < nb ? ld[i * KNN_THREADS] : INFINITY;
-      bj[i] = i < nb ? lj[i * KNN_THREADS] : 0x7fffffff;
+      const unsigned short* e = h + 6 * i * KNN_THREADS;
+      const unsigned long long u = (unsigned long long)e[0] | ((unsigned long long)e[KNN_THREADS] << 16) |
+                                   ((unsigned long long)e[2 * KNN_THREADS] << 32) | ((unsigned long long)e[3 * KNN_THREADS] << 48);
+      const int j = (int)((unsigned int)e[4 * KNN_THREADS] | ((unsigned int)e[5 * KNN_THREADS] << 16));
+      bd[i] = i < nb ? __longlong_as_double((long long)u) : INFINITY;
+      bj[i] = i < nb ? j : 0x7fffffff;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -221,8 +233,6 @@ knn_thread_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
                   const int32_t* __restrict__ cell_start, int k, double r2cap, int max_ring,
                   int32_t* __restrict__ ell_idx, double* __restrict__ ell_d2) {
   __shared__ unsigned short hist[KNN_BINS][KNN_THREADS];
-  __shared__ double list_d[8][KNN_THREADS];
-  __shared__ int list_j[8][KNN_THREADS];
   const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int32_t* out_j = ell_idx + (q >> 5) * (int64_t)k * DC_SLICE + lane;
@@ -233,7 +243,6 @@ knn_thread_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
     int c0, c1, c2;
     dc_key_coords(g, qkeys[q], c0, c1, c2);
     knn_thread_query(P, pkeys, n, g, cell_start, pq, c0, c1, c2, k, r2cap, max_ring, 1, &hist[0][threadIdx.x],
-                     &list_d[0][threadIdx.x], &list_j[0][threadIdx.x],
                      [&](int j, double d2) {
                        out_j[(int64_t)cnt * DC_SLICE] = j;
                        if (out_d) out_d[(int64_t)cnt * DC_SLICE] = d2;

@@ -158,6 +158,18 @@ def test_knn_duplicates_and_sparse_tail(dc, dev):
         assert ((srt[:, 1:] != srt[:, :-1]) | (srt[:, 1:] < 0)).all(), 'a neighbour is listed twice'
 
 
+def test_cell_table_is_lower_bound_of_sorted_keys(dc, dev):
+    """cell_start[c] = first sorted position whose key is >= c (long empty runs, empty head / tail, one point)."""
+    from depth_correction_b200.graph import SortedMap
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([rng.normal(0, 0.05, (3000, 3)), rng.normal(0, 0.05, (2000, 3)) + [40.0, 3.0, -2.0],
+                          [[-7.0, -7.0, -7.0]]]).astype(np.float32)
+    for p, cell in ((pts, 0.11), (pts[:1], 0.5), (pts, 3.0)):
+        smap = SortedMap(torch.as_tensor(p, device=dev), cell)
+        ref = torch.searchsorted(smap.keys, torch.arange(smap.n_cells + 1, device=dev, dtype=torch.int64))
+        assert torch.equal(smap.cell_start.long(), ref)
+
+
 def test_graph_roundtrip_and_transpose(dc, dev, golden):
     from depth_correction_b200.graph import Graph, SortedMap, search
     g = golden('nn')
