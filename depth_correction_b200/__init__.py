@@ -14,7 +14,7 @@ from .model import BaseModel, Polynomial, ScaledPolynomial, load_model, model_by
 from .loss import Reduction, batch_loss, create_loss, fused_sum_count, loss_by_name, min_eigval_loss, reduce, trace_loss
 from .parallel import LocalMap, SlabPartitioner, reduce_step
 from .filters import (filter_depth, filter_eigenvalue, filter_eigenvalue_ratio, filter_eigenvalue_ratios,
-                      filter_eigenvalues, filter_valid_neighbors, within_bounds)
+                      filter_eigenvalues, filter_shadow_points, filter_valid_neighbors, within_bounds)
 from .filters_grid import filter_grid
 from .preproc import (GlobalCloud, Neighborhoods, compute_neighborhood_features, establish_neighborhoods,
                       filtered_cloud, global_cloud, global_cloud_mask, local_feature_cloud, offset_cloud)

@@ -86,6 +86,9 @@ SIGNATURES = {
     'dc_normals_angles': [_P, _P, _I, _L, _I, _P, _P, _P],
     'dc_world_points': [_P, _P, _P, _I, _L, _P, _P, _P],
     'dc_from_points': [_P, _P, _I, _L, _P, _P, _P, _P],
+    'dc_voxel_keys': [_P, _I, _L, _D, _P, _I, _P, _P, _P, _P],
+    'dc_voxel_pick': [_P, _P, _L, _P, _I, _I, _P, _P, _P, _P],
+    'dc_shadow_mask': [_P, _P, _I, _P, _P, _L, _I, _D, _D, _P, _P, _P, _P],
 }
 
 for _name, _args in SIGNATURES.items():

@@ -3,8 +3,10 @@ import torch
 
 from .depth_cloud import DepthCloud
 
+from . import _lib as L
+
 __all__ = ['filter_depth', 'filter_eigenvalue', 'filter_eigenvalue_ratio', 'filter_eigenvalue_ratios',
-           'filter_eigenvalues', 'filter_valid_neighbors', 'within_bounds']
+           'filter_eigenvalues', 'filter_shadow_points', 'filter_valid_neighbors', 'within_bounds']
 
 
 def within_bounds(x, min=None, max=None, bounds=None, log_variable=None):
@@ -79,3 +81,35 @@ def filter_eigenvalue_ratios(cloud, bounds, only_mask=False, log=False):
     else:
         mask = torch.ones((cloud.size(),), dtype=torch.bool, device=cloud.device())
     return mask if only_mask else cloud[mask]
+
+
+def filter_shadow_points(cloud, angle_bounds, only_mask=False, log=False):
+    """Remove shadow points (filters.py:257-309): bound the minimum and maximum angle, at the point, between the
+    ray back to the viewpoint and the directions to its neighbours among neighbouring BEAMS (dir_neighbors).
+
+    One kernel (dc_shadow_mask) instead of the reference's [N,K,3] temporaries.  `only_mask=True` returns the mask
+    (the reference returns the flag itself there, filters.py:303-304 -- a bug no caller relies on)."""
+    import math
+    assert cloud.vps is not None
+    assert cloud.dir_neighbors is not None
+    lo, hi = angle_bounds[0], angle_bounds[1]
+    if lo is None or not (lo >= 0.0):
+        lo = 0.0
+    if hi is None or not (hi <= math.pi):
+        hi = math.pi
+    x = cloud.get_points().detach().contiguous()
+    if not x.is_cuda:
+        raise RuntimeError('filter_shadow_points needs a CUDA cloud; there is no CPU fallback')
+    n = x.shape[0]
+    vps = cloud.vps.detach().to(x.dtype).expand(n, 3).contiguous()
+    nb = cloud.dir_neighbors.contiguous()
+    w = None if cloud.dir_neighbor_weights is None else cloud.dir_neighbor_weights.to(torch.float32).contiguous()
+    keep = torch.empty(n, dtype=torch.uint8, device=x.device)
+    L.call('dc_shadow_mask', L.ptr(x), L.ptr(vps), L.dtype_code(x.dtype), L.ptr(nb), L.ptr(w), n, nb.shape[1], float(lo), float(hi),
+           L.ptr(keep), None, None, L.stream())
+    mask = keep.bool()
+    if log:
+        print('%.3f = %i / %i points kept (shadow points removed).' % (mask.double().mean(), mask.sum(), mask.numel()))
+    if only_mask:
+        return mask
+    return cloud[mask]

@@ -14,7 +14,8 @@ import torch
 from . import _lib as _L
 from .config import NeighborhoodType
 from .depth_cloud import DepthCloud
-from .filters import filter_depth, filter_eigenvalue_ratios, filter_eigenvalues, filter_valid_neighbors, within_bounds
+from .filters import (filter_depth, filter_eigenvalue_ratios, filter_eigenvalues, filter_shadow_points,
+                      filter_valid_neighbors, within_bounds)
 from .fused import StepState, model_kind_of, scan_table
 from .graph import Graph, SortedMap, search
 from .transform import xyz_axis_angle_to_matrix
@@ -159,14 +160,14 @@ class GlobalCloud(DepthCloud):
 
 
 def filtered_cloud(cloud, cfg):
-    """Depth filter of preproc.py:25-32.  The voxel-grid filter (`filter_grid`, a Python dict over all
-    points in the reference) belongs to the per-scan preprocessing row of SURVEY.md section 8(f)."""
+    """Depth and voxel-grid filters of preproc.py:25-32."""
+    from .filters_grid import filter_grid
     if ((cfg.min_depth is not None and cfg.min_depth > 0.0)
             or (cfg.max_depth is not None and cfg.max_depth < float('inf'))):
         cloud = filter_depth(cloud, min=cfg.min_depth, max=cfg.max_depth, log=cfg.log_filters)
-    if getattr(cfg, 'grid_res', 0.0) and cfg.grid_res > 0.0:
-        from .filters_grid import filter_grid
-        cloud = filter_grid(cloud, grid_res=cfg.grid_res, keep='first')
+    if cfg.grid_res > 0.0:
+        rng = np.random.default_rng(cfg.random_seed)
+        cloud = filter_grid(cloud, grid_res=cfg.grid_res, keep='random', log=cfg.log_filters, rng=rng)
     return cloud
 
 
@@ -179,7 +180,8 @@ def local_feature_cloud(cloud, cfg):
             cloud = DepthCloud.from_points(cloud, dtype=cfg.numpy_float_type(), device=cfg.device)
     assert isinstance(cloud, DepthCloud)
     if getattr(cfg, 'shadow_angle_bounds', None):
-        raise NotImplementedError('shadow-point filter: SURVEY.md section 8(f) row 1 (not built yet)')
+        cloud.update_dir_neighbors(angle=cfg.shadow_neighborhood_angle)
+        cloud = filter_shadow_points(cloud, list(cfg.shadow_angle_bounds), log=cfg.log_filters)
     cloud.update_all(k=cfg.nn_k, r=cfg.nn_r)
     if cfg.eigenvalue_bounds:
         if cloud.mask is None:

@@ -246,6 +246,30 @@ int dc_from_points(const void* points, const void* vps, int dtype, int64_t n, vo
 int dc_normals_angles(const void* dirs, const void* eigvecs, int dtype, int64_t n, int use_normal_sign, void* normals,
                       void* inc_angles, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Per-scan preprocessing filters.
+ *
+ * filter_grid (filters.py:24-82): one survivor per occupied voxel of edge grid_res.
+ *   dc_voxel_keys: position t of the sequence (seq[t], or n-1-t when reversed, or t) -> 63-bit voxel key of that
+ *     point (floor(x / grid_res) per axis in the cloud's dtype, biased 21-bit fields), ids[t] = t; *bad counts
+ *     points whose cell index does not fit (|index| >= 2^20) or is NaN.
+ *   (dc_sort_pairs on 63 bits groups the voxels; positions stay ascending inside a group.)
+ *   dc_voxel_pick: for the last entry of every group: out_val = point index of the survivor (the LAST position
+ *     of the voxel in the sequence, as the reference's dict keeps the last value), out_key = first position of
+ *     the voxel in the sequence (dict order) or the survivor's index (preserve_order); 2^32 / -1 elsewhere;
+ *     *count += number of voxels.  A second dc_sort_pairs on 33 bits of out_key orders the survivors.
+ * filter_shadow_points (filters.py:257-309): keep[i] = min_k a_ik >= angle_lo && max_k a_ik <= angle_hi with
+ *   a_ik = angle at x_i between (vp_i - x_i) and (x_nbr - x_i) over the direction-space neighbours; invalid
+ *   neighbours (weight != 1) count as (angle_lo + angle_hi) / 2.  angle_min / angle_max [n] optional outputs.
+ * ------------------------------------------------------------------------------------------- */
+int dc_voxel_keys(const void* points, int dtype, int64_t n, double grid_res, const int32_t* seq, int reversed,
+                  uint64_t* keys, int32_t* ids, int32_t* bad, void* stream);
+int dc_voxel_pick(const uint64_t* keys_sorted, const int32_t* ids_sorted, int64_t n, const int32_t* seq, int reversed,
+                  int preserve_order, uint64_t* out_key, int32_t* out_val, int32_t* count, void* stream);
+int dc_shadow_mask(const void* points, const void* vps, int dtype, const int64_t* dir_neighbors,
+                   const float* dir_neighbor_weights, int64_t n, int K, double angle_lo, double angle_hi, uint8_t* keep,
+                   void* angle_min, void* angle_max, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,6 +194,42 @@ def gen_misc(ref):
     print('misc.npz')
 
 
+def gen_filters(ref):
+    """filter_grid (filters.py:24-82) for every keep mode / order, and filter_shadow_points (filters.py:257-309)."""
+    scans, _, _ = make_sequence('corridor', n_scans=1, pattern='os0-32', seed=21)
+    pts = scans[0]['points']                                  # float32 [n,3], sensor frame
+    out = {'points': pts}
+    for dt, tag in ((np.float32, 'f32'), (np.float64, 'f64')):
+        x = pts.astype(dt)
+        for keep in ('first', 'last', 'random'):
+            for po in (False, True):
+                rng = np.random.default_rng(135)
+                ind = quiet(ref.filters.filter_grid, x, 0.2, only_mask=True, keep=keep, preserve_order=po, rng=rng)
+                out['grid_%s_%s_%d' % (tag, keep, int(po))] = np.asarray(ind, dtype=np.int64)
+    # two consecutive draws from ONE generator (the reference's module-level default_rng is stateful)
+    rng = np.random.default_rng(7)
+    out['grid_two_draws_a'] = np.asarray(quiet(ref.filters.filter_grid, pts, 0.35, only_mask=True, keep='random', rng=rng), dtype=np.int64)
+    out['grid_two_draws_b'] = np.asarray(quiet(ref.filters.filter_grid, pts, 0.35, only_mask=True, keep='random', rng=rng), dtype=np.int64)
+    # shadow points: a wall behind a thin pole seen from the origin produces mixed-depth beams
+    rng = np.random.default_rng(5)
+    az = rng.uniform(-0.6, 0.6, 4000)
+    el = rng.uniform(-0.3, 0.3, 4000)
+    d = np.where(np.abs(az) < 0.05, 2.0, 6.0) / np.cos(az) + 0.01 * rng.standard_normal(4000)
+    edge = (np.abs(np.abs(az) - 0.05) < 0.004)
+    d[edge] = rng.uniform(2.0, 6.0, edge.sum())               # mixed pixels along the occlusion boundary
+    sp = (d[:, None] * np.stack([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)], 1)).astype(np.float32)
+    out['shadow_points'] = sp
+    for tag, bounds in (('a', [0.0873, None]), ('b', [0.2, 2.8])):
+        cloud = ref.DepthCloud.from_points(torch.as_tensor(sp.astype(np.float64)))
+        cloud.update_dir_neighbors(angle=0.02)
+        cloud.loss = torch.arange(len(sp), dtype=torch.float64)[:, None]
+        kept = quiet(ref.filters.filter_shadow_points, cloud, list(bounds))
+        out['shadow_kept_' + tag] = kept.loss[:, 0].numpy().astype(np.int64)
+        out['shadow_K_' + tag] = np.asarray(cloud.dir_neighbors.shape[1])
+    np.savez_compressed(os.path.join(OUT, 'filters.npz'), **out)
+    print('filters.npz', {k: v.shape for k, v in out.items() if k.startswith('grid_f32') or k.startswith('shadow_kept')})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
@@ -202,6 +238,7 @@ def main():
     gen_features(ref)
     gen_steps(ref)
     gen_misc(ref)
+    gen_filters(ref)
 
 
 if __name__ == '__main__':

@@ -224,6 +224,56 @@ def valid_neighbor_mask(neighbors, min_valid):
 # ----------------------------------------------------------------------------------------
 # Losses (loss.py:125-150, 216-370)
 # ----------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------
+# per-scan preprocessing filters
+# ----------------------------------------------------------------------------------------
+def filter_grid(x, grid_res, keep='random', preserve_order=False, rng=None):
+    """filters.py:24-82: one point per occupied voxel -> kept indices (int64 array).
+
+    The reference zips voxel keys (tuples of floor(x / grid_res), computed in x's own dtype) with the
+    point indices of a sequence (reversed for 'first', shuffled by `rng` for 'random') into a dict: the
+    LAST index of every key survives, and the dict yields them in the order the keys were FIRST seen
+    (or sorted, with preserve_order)."""
+    x = np.asarray(x)
+    n = len(x)
+    vox = np.floor(x / grid_res).astype(np.int64)
+    seq = np.arange(n)
+    if keep == 'first':
+        seq = seq[::-1]
+    elif keep == 'random':
+        seq = np.arange(n)
+        rng.shuffle(seq)
+    vox = vox[seq]
+    _, inv = np.unique(vox, axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    n_vox = int(inv.max()) + 1 if n else 0
+    pos = np.arange(n)
+    first = np.full(n_vox, n, dtype=np.int64)
+    last = np.full(n_vox, -1, dtype=np.int64)
+    np.minimum.at(first, inv, pos)
+    np.maximum.at(last, inv, pos)
+    kept = seq[last]
+    return np.sort(kept) if preserve_order else kept[np.argsort(first, kind='stable')]
+
+
+def shadow_mask(points, vps, dir_neighbors, dir_neighbor_weights, angle_bounds):
+    """filters.py:257-309 -> bool mask of the points that are kept."""
+    lo, hi = angle_bounds
+    if lo is None or not (lo >= 0.0):
+        lo = 0.0
+    if hi is None or not (hi <= np.pi):
+        hi = np.pi
+    x = torch.as_tensor(points, dtype=F64)
+    o = torch.as_tensor(vps, dtype=F64).expand_as(x)
+    nb = torch.as_tensor(dir_neighbors)
+    to_vp = (o - x)[:, None, :]
+    to_nb = x[nb] - x[:, None, :]
+    cos = torch.nn.functional.cosine_similarity(to_vp, to_nb, dim=-1)
+    ang = torch.acos(cos)
+    ang[torch.as_tensor(dir_neighbor_weights) != 1.0] = 0.5 * (lo + hi)
+    return (ang.amin(dim=-1) >= lo) & (ang.amax(dim=-1) <= hi)
+
+
 def reduce(x, reduction='mean', only_finite=False, skip_nans=False):
     if only_finite:
         x = x[x.isfinite()]

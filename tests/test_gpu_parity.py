@@ -464,3 +464,60 @@ def test_local_feature_cloud_vs_reference(dc, dev, golden):
         inc = c.inc_angles.cpu().numpy()
         ok = g['scan%d_mask' % i] & c.mask.cpu().numpy()
         assert np.max(np.abs(inc[ok] - g['scan%d_inc_angles' % i][ok])) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# per-scan preprocessing filters
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_filter_grid_matches_reference(dc, dev, golden, dtype):
+    """Same survivors in the same order as the reference's dict walk, for every keep mode / order."""
+    g = golden('filters')
+    tag = 'f32' if dtype == np.float32 else 'f64'
+    x = torch.as_tensor(g['points'].astype(dtype), device=dev)
+    for keep in ('first', 'last', 'random'):
+        for po in (False, True):
+            ind = dc.filter_grid(x, 0.2, only_mask=True, keep=keep, preserve_order=po, rng=np.random.default_rng(135))
+            assert ind.dtype == torch.int64
+            assert np.array_equal(ind.cpu().numpy(), g['grid_%s_%s_%d' % (tag, keep, int(po))]), (keep, po)
+    rng = np.random.default_rng(7)            # a stateful generator advances exactly like the reference's
+    x32 = torch.as_tensor(g['points'], device=dev)
+    assert np.array_equal(dc.filter_grid(x32, 0.35, only_mask=True, keep='random', rng=rng).cpu().numpy(), g['grid_two_draws_a'])
+    assert np.array_equal(dc.filter_grid(x32, 0.35, only_mask=True, keep='random', rng=rng).cpu().numpy(), g['grid_two_draws_b'])
+    # DepthCloud in -> DepthCloud out (slicing keeps the source fields)
+    cloud = dc.DepthCloud.from_points(x32)
+    kept = dc.filter_grid(cloud, 0.2, keep='first', preserve_order=True)
+    assert len(kept) == len(g['grid_f32_first_1'])
+
+
+def test_filter_grid_full_scan_vs_oracle(dc, dev):
+    """Full-resolution scan (131 k points, hundreds of points per voxel near the sensor), negative coordinates."""
+    from oracle import oracle
+    from depth_correction_b200.synthetic import make_sequence
+    scans, _, _ = make_sequence('corridor', n_scans=1, pattern='os0-128', seed=2)
+    pts = scans[0]['points']
+    x = torch.as_tensor(pts, device=dev)
+    for keep, po, res in (('random', False, 0.2), ('first', False, 0.1), ('last', True, 0.5)):
+        ours = dc.filter_grid(x, res, only_mask=True, keep=keep, preserve_order=po, rng=np.random.default_rng(3))
+        ref = oracle.filter_grid(pts, np.float32(res), keep=keep, preserve_order=po, rng=np.random.default_rng(3))
+        assert np.array_equal(ours.cpu().numpy(), ref), (keep, po, res)
+    with pytest.raises(ValueError):
+        dc.filter_grid(torch.full((4, 3), float('nan'), device=dev), 0.2, only_mask=True)
+    assert len(dc.filter_grid(torch.zeros((0, 3), device=dev), 0.2, only_mask=True)) == 0
+
+
+def test_shadow_filter_matches_reference(dc, dev, golden):
+    g = golden('filters')
+    sp = torch.as_tensor(g['shadow_points'].astype(np.float64), device=dev)
+    for tag, bounds in (('a', [0.0873, None]), ('b', [0.2, 2.8])):
+        cloud = dc.DepthCloud.from_points(sp)
+        cloud.update_dir_neighbors(angle=0.02)
+        assert cloud.dir_neighbors.shape[1] == int(g['shadow_K_' + tag])
+        mask = dc.filter_shadow_points(cloud, list(bounds), only_mask=True)
+        assert np.array_equal(torch.nonzero(mask)[:, 0].cpu().numpy(), g['shadow_kept_' + tag]), tag
+        assert len(dc.filter_shadow_points(cloud, list(bounds))) == len(g['shadow_kept_' + tag])
+    # through local_feature_cloud (preproc.py:44-47)
+    cfg = dc.Config(nn_k=0, nn_r=0.3, shadow_angle_bounds=[0.0873, None], shadow_neighborhood_angle=0.02,
+                    eigenvalue_ratio_bounds=[])
+    out = dc.local_feature_cloud(dc.DepthCloud.from_points(sp), cfg)
+    assert len(out) == len(g['shadow_kept_a']) and out.eigvals is not None

@@ -111,3 +111,31 @@ def test_oracle_live_against_reference():
         d1, i1 = oracle.nearest_neighbors(pts, **kw)
         assert torch.equal(i0, i1)
         assert (d0 is None and d1 is None) or torch.equal(d0, d1)
+
+
+def test_filter_grid_against_reference(golden):
+    """Oracle restatement of filter_grid vs the reference's dict walk: every keep mode, both orders, both dtypes,
+    and two consecutive draws from one generator."""
+    g = golden('filters')
+    pts = g['points']
+    for dt, tag in ((np.float32, 'f32'), (np.float64, 'f64')):
+        for keep in ('first', 'last', 'random'):
+            for po in (False, True):
+                ind = oracle.filter_grid(pts.astype(dt), 0.2, keep=keep, preserve_order=po, rng=np.random.default_rng(135))
+                assert np.array_equal(ind, g['grid_%s_%s_%d' % (tag, keep, int(po))]), (tag, keep, po)
+    rng = np.random.default_rng(7)
+    assert np.array_equal(oracle.filter_grid(pts, 0.35, keep='random', rng=rng), g['grid_two_draws_a'])
+    assert np.array_equal(oracle.filter_grid(pts, 0.35, keep='random', rng=rng), g['grid_two_draws_b'])
+
+
+def test_shadow_filter_against_reference(golden):
+    g = golden('filters')
+    sp = torch.as_tensor(g['shadow_points'].astype(np.float64))
+    vps, dirs, depth = oracle.from_points(sp)
+    r = float(np.sqrt(2.0 * (1.0 - np.cos(0.02))))          # ball_angle_to_distance, nearest_neighbors.py:15-19
+    _, nb = oracle.nearest_neighbors(dirs, r=r)
+    w = (nb >= 0).float()
+    for tag, bounds in (('a', [0.0873, None]), ('b', [0.2, 2.8])):
+        assert nb.shape[1] == int(g['shadow_K_' + tag])
+        keep = oracle.shadow_mask(sp, vps, nb, w, bounds)
+        assert np.array_equal(torch.nonzero(keep)[:, 0].numpy(), g['shadow_kept_' + tag]), tag
