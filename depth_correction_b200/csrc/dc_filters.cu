@@ -133,3 +133,54 @@ extern "C" int dc_shadow_mask(const void* points, const void* vps, int dtype, co
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Neighbourhood statistics of global_cloud_mask (depth_cloud.py:330-354): weighted mean depth and weighted mean
+// distance of the neighbours' viewpoints from their weighted mean, one pass over the padded lists (the reference
+// materialises vps[neighbors] = [N,K,3] and three more [N,K] temporaries).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void neighbor_stats_kernel(const T* __restrict__ depth, const T* __restrict__ vps, const int64_t* __restrict__ nbr,
+                                      const float* __restrict__ w, int64_t n, int K, T* __restrict__ mean_depth,
+                                      T* __restrict__ mean_vp_dist) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t* row = nbr + i * (int64_t)K;
+  const float* wr = w ? w + i * (int64_t)K : nullptr;
+  T ws = 0, ds = 0, mx = 0, my = 0, mz = 0;
+  for (int c = 0; c < K; ++c) {
+    const int64_t j0 = row[c];
+    const T wt = wr ? (T)wr[c] : (j0 >= 0 ? (T)1 : (T)0);
+    const int64_t j = j0 >= 0 ? j0 : j0 + n;         // torch indexing wraps negative indices (their weight is 0)
+    ws += wt;
+    ds += wt * depth[j];
+    if (vps) { mx += wt * vps[3 * j]; my += wt * vps[3 * j + 1]; mz += wt * vps[3 * j + 2]; }
+  }
+  if (mean_depth) mean_depth[i] = ds / ws;
+  if (!mean_vp_dist) return;
+  mx /= ws; my /= ws; mz /= ws;
+  T acc = 0;
+  for (int c = 0; c < K; ++c) {
+    const int64_t j0 = row[c];
+    const T wt = wr ? (T)wr[c] : (j0 >= 0 ? (T)1 : (T)0);
+    const int64_t j = j0 >= 0 ? j0 : j0 + n;
+    const T dx = vps[3 * j] - mx, dy = vps[3 * j + 1] - my, dz = vps[3 * j + 2] - mz;
+    acc += wt * sqrt(dx * dx + dy * dy + dz * dz);
+  }
+  mean_vp_dist[i] = acc / ws;
+}
+
+extern "C" int dc_neighbor_stats(const void* depth, const void* vps, int dtype, const int64_t* neighbors, const float* weights,
+                                 int64_t n, int K, void* mean_depth, void* mean_vp_dist, void* stream) {
+  if (n <= 0) return DC_OK;
+  if (mean_vp_dist && !vps) return dc_set_error(DC_ERR_ARG, "dc_neighbor_stats: mean_vp_dist needs vps");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DC_F32)
+    neighbor_stats_kernel<float><<<dc_blocks(n, 128), 128, 0, st>>>((const float*)depth, (const float*)vps, neighbors, weights, n, K,
+                                                                    (float*)mean_depth, (float*)mean_vp_dist);
+  else
+    neighbor_stats_kernel<double><<<dc_blocks(n, 128), 128, 0, st>>>((const double*)depth, (const double*)vps, neighbors, weights, n, K,
+                                                                     (double*)mean_depth, (double*)mean_vp_dist);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}

@@ -338,20 +338,29 @@ class DepthCloud(object):
         assert self.dirs is not None and self.neighbors is not None
         return trace(ops.neighborhood_mean_cov(self.dirs.contiguous(), self.neighbors, self._kernel_weights(), mean=False, cov=True))
 
+    def _neighbor_stats(self, want_depth, want_vp):
+        """One pass over the neighbour lists (dc_neighbor_stats) instead of [N,K(,3)] temporaries."""
+        n = self.size()
+        depth = self.depth.detach().reshape(-1).contiguous()
+        if not depth.is_cuda:
+            raise RuntimeError('neighbourhood statistics need a CUDA cloud; there is no CPU fallback')
+        nb = self.neighbors.contiguous()
+        w = self._kernel_weights()
+        w = None if w is None else w.detach().reshape(nb.shape).to(torch.float32).contiguous()
+        vps = self.vps.detach().to(depth.dtype).expand(n, 3).contiguous() if want_vp else None
+        md = torch.empty(n, dtype=depth.dtype, device=depth.device) if want_depth else None
+        mv = torch.empty(n, dtype=depth.dtype, device=depth.device) if want_vp else None
+        L.call('dc_neighbor_stats', L.ptr(depth), L.ptr(vps), L.dtype_code(depth.dtype), L.ptr(nb), L.ptr(w), n, nb.shape[1],
+               L.ptr(md), L.ptr(mv), L.stream())
+        return md, mv
+
     def mean_depth(self):
         assert self.neighbors is not None
-        d = self.depth.squeeze(dim=1)
-        w = self.weights.squeeze(dim=2)
-        return (w * d[self.neighbors]).sum(dim=-1) / w.sum(dim=-1)
+        return self._neighbor_stats(True, False)[0]
 
     def mean_vp_dist(self):
         assert self.vps is not None and self.neighbors is not None
-        w = self.weights.squeeze(dim=2)
-        w_sum = w.sum(dim=-1)
-        vps = self.vps[self.neighbors]
-        mean_vp = (w[..., None] * vps).sum(dim=-2) / w_sum[..., None]
-        vp_dists = torch.linalg.norm(vps - mean_vp[:, None], dim=-1)
-        return (w * vp_dists).sum(dim=-1) / w_sum
+        return self._neighbor_stats(False, True)[1]
 
     def vp_dispersion_to_depth2(self):
         return self.vp_dispersion() / self.mean_depth() ** 2

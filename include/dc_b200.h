@@ -270,6 +270,12 @@ int dc_shadow_mask(const void* points, const void* vps, int dtype, const int64_t
                    const float* dir_neighbor_weights, int64_t n, int K, double angle_lo, double angle_hi, uint8_t* keep,
                    void* angle_min, void* angle_max, void* stream);
 
+/* neighbourhood statistics of global_cloud_mask (depth_cloud.py:330-354): mean_depth[n] = sum_k w d[nbr] / sum_k w,
+ * mean_vp_dist[n] = sum_k w |vp[nbr] - mean_vp| / sum_k w (either output may be NULL); neighbors int64 [n,K],
+ * weights float32 [n,K] or NULL (= neighbors >= 0). */
+int dc_neighbor_stats(const void* depth, const void* vps, int dtype, const int64_t* neighbors, const float* weights,
+                      int64_t n, int K, void* mean_depth, void* mean_vp_dist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -230,6 +230,35 @@ def gen_filters(ref):
     print('filters.npz', {k: v.shape for k, v in out.items() if k.startswith('grid_f32') or k.startswith('shadow_kept')})
 
 
+def gen_stats(ref):
+    """Neighbourhood statistics and the loss mask of the GLOBAL cloud (depth_cloud.py:314-354, preproc.py:122-164)."""
+    scans_np, poses, _ = make_sequence('corridor', n_scans=3, pattern='os0-32', seed=17, grid_res=0.15, step=1.5)
+    clouds = []
+    cfg = ref_cfg(ref)
+    for s in scans_np:
+        c = ref.DepthCloud.from_points(torch.as_tensor(s['points'].astype(np.float64)))
+        clouds.append(quiet(ref.local_feature_cloud, c, cfg))
+    poses_t = torch.as_tensor(poses)
+    cloud = quiet(ref.global_cloud, clouds=clouds, model=None, poses=poses_t)
+    quiet(cloud.update_all, r=0.4)
+    out = {'n_scans': np.asarray(len(scans_np)), 'poses': poses}
+    for i, s in enumerate(scans_np):
+        out['scan%d_points' % i] = s['points']
+    for f in ('vp_dispersion', 'dir_dispersion', 'mean_depth', 'mean_vp_dist', 'vp_dispersion_to_depth2', 'vp_dist_to_depth'):
+        out[f] = getattr(cloud, f)().numpy()
+    mcfg = ref_cfg(ref, min_valid_neighbors=8, eigenvalue_bounds=[[0, None, 0.01]], dir_dispersion_bounds=[0.0, 0.02],
+                   vp_dispersion_bounds=[0.05, float('inf')], vp_dispersion_to_depth2_bounds=[0.001, None])
+    out['mask'] = quiet(ref.global_cloud_mask, cloud, cloud.mask.clone(), mcfg).numpy()
+    # the individual criteria, for a readable failure
+    out['mask_start'] = cloud.mask.numpy()
+    out['mask_valid'] = ref.filters.filter_valid_neighbors(cloud, min=8, only_mask=True).numpy()
+    out['mask_eig'] = ref.filters.filter_eigenvalues(cloud, mcfg.eigenvalue_bounds, only_mask=True).numpy()
+    out['mask_ratio'] = ref.filters.filter_eigenvalue_ratios(cloud, mcfg.eigenvalue_ratio_bounds, only_mask=True).numpy()
+    out['eigvals'] = cloud.eigvals.numpy()
+    np.savez_compressed(os.path.join(OUT, 'stats.npz'), **out)
+    print('stats.npz', cloud.neighbors.shape, 'mask keeps', int(out['mask'].sum()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
@@ -239,6 +268,7 @@ def main():
     gen_steps(ref)
     gen_misc(ref)
     gen_filters(ref)
+    gen_stats(ref)
 
 
 if __name__ == '__main__':
