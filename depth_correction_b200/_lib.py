@@ -88,6 +88,10 @@ SIGNATURES = {
     'dc_from_points': [_P, _P, _I, _L, _P, _P, _P, _P],
     'dc_voxel_keys': [_P, _I, _L, _D, _P, _I, _P, _P, _P, _P],
     'dc_voxel_pick': [_P, _P, _L, _P, _I, _I, _P, _P, _P, _P],
+    'dc_icp_forward': [_P, _P, _I, _P, _P, _I, _P, _P, _D, _P, _P, _L, _I, _P, _P, _SZ, _P],
+    'dc_icp_backward': [_P, _P, _I, _P, _P, _I, _P, _P, _D, _P, _P, _L, _I, _P, _P, _P, _P, _P, _P],
+    'dc_f64_sort_keys': [_P, _L, _P, _P, _P],
+    'dc_f64_from_sort_keys': [_P, _L, _P, _P],
     'dc_neighbor_stats': [_P, _P, _I, _P, _P, _L, _I, _P, _P, _P],
     'dc_shadow_mask': [_P, _P, _I, _P, _P, _L, _I, _D, _D, _P, _P, _P, _P],
 }

@@ -263,7 +263,10 @@ def trace_loss(cloud, mask=None, offset=None, sqrt=None, reduction=Reduction.MEA
 
 
 def loss_by_name(name):
-    assert name in ('min_eigval_loss', 'trace_loss'), name
+    assert name in ('min_eigval_loss', 'trace_loss', 'icp_loss'), name
+    if name == 'icp_loss':
+        from .icp import icp_loss
+        return icp_loss
     return globals()[name]
 
 

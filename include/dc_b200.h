@@ -276,6 +276,31 @@ int dc_shadow_mask(const void* points, const void* vps, int dtype, const int64_t
 int dc_neighbor_stats(const void* depth, const void* vps, int dtype, const int64_t* neighbors, const float* weights,
                       int64_t n, int K, void* mean_depth, void* mean_vp_dist, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * ICP-style losses between two consecutive scans (loss.py:373-565).
+ * Correspondences: either explicit index lists sel1 / sel2 (int64 [m]; the reference's precomputed `masks`) or,
+ * with sel1 == NULL, (t, nn[t]) for t < m = n1, kept when dist[t] <= threshold (nn / dist: nearest neighbour of
+ * every point of cloud 1 in cloud 2 from dc_knn with k = 1, fp64 distances).  Points are rounded to float32 first
+ * (loss.py:424-425), arithmetic in fp64.  normals_dtype: dtype of the normal arrays (may differ from the points').
+ *   dc_icp_forward: out4 = {sum_t |n1.(p2-p1)| |n1|, sum_t |n2.(p2-p1)| |n2|, count, sum_t dist[t]} (point-to-plane)
+ *                   or {sum_t |p2-p1|, 0, count, sum_t dist[t]} (point-to-point); partials: >= 32*blocks+16 bytes
+ *                   (blocks = ceil(m/256)), the trailing 16 bytes zero before the first call.
+ *   dc_icp_backward: gradients of coef2[0] * out4[0] + coef2[1] * out4[1] (coef2: 2 doubles on the device),
+ *                   ACCUMULATED into fp64 g_points1 [n1,3], g_points2 [n2,3], g_normals1, g_normals2 (any may be NULL).
+ * dc_f64_sort_keys / dc_f64_from_sort_keys: order-preserving uint64 keys of fp64 values (NaN last, *n_nan counts
+ *   them) and back, for the inlier threshold torch.nanquantile(dists, ratio) via dc_sort_keys.
+ * ------------------------------------------------------------------------------------------- */
+int dc_icp_forward(const void* points1, const void* points2, int dtype, const void* normals1, const void* normals2,
+                   int normals_dtype, const int64_t* nn, const double* dist, double threshold, const int64_t* sel1,
+                   const int64_t* sel2, int64_t m, int point_to_plane, double* out4, void* partials, size_t partials_bytes,
+                   void* stream);
+int dc_icp_backward(const void* points1, const void* points2, int dtype, const void* normals1, const void* normals2,
+                    int normals_dtype, const int64_t* nn, const double* dist, double threshold, const int64_t* sel1,
+                    const int64_t* sel2, int64_t m, int point_to_plane, const double* coef2, double* g_points1,
+                    double* g_points2, double* g_normals1, double* g_normals2, void* stream);
+int dc_f64_sort_keys(const double* x, int64_t n, uint64_t* keys, int32_t* n_nan, void* stream);
+int dc_f64_from_sort_keys(const uint64_t* keys, int64_t n, double* x, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -259,6 +259,53 @@ def gen_stats(ref):
     print('stats.npz', cloud.neighbors.shape, 'mask keeps', int(out['mask'].sum()))
 
 
+def gen_icp(ref):
+    """icp_loss (loss.py:373-565): loss and gradients to the model weights and the poses, point-to-plane and
+    point-to-point, searched and precomputed correspondences.  The reference's scipy branch (differentiable=False)
+    cannot run with gradients (it hands tensors that require grad to cKDTree, loss.py:442), so the search goes
+    through its pytorch3d branch with ref_shim.knn_points_exact standing in for the absent pytorch3d."""
+    from depth_correction.loss import icp_loss
+    scans_np, poses, _ = make_sequence('corridor', n_scans=3, pattern='os0-32', seed=29, grid_res=0.15, step=0.7,
+                                       pose_noise=(0.02, 0.01))
+    cfg = ref_cfg(ref)
+    out = {'n_scans': np.asarray(len(scans_np)), 'poses': poses, 'w': np.array([0.002, -0.001]), 'exponent': np.array([2.0, 4.0])}
+    for i, s in enumerate(scans_np):
+        out['scan%d_points' % i] = s['points']
+
+    def run(p2pl, masks=None):
+        clouds = []
+        for s in scans_np:
+            c = ref.DepthCloud.from_points(torch.as_tensor(s['points'].astype(np.float64)))
+            clouds.append(quiet(ref.local_feature_cloud, c, cfg))
+        model = ref.ScaledPolynomial(w=[0.002, -0.001], exponent=[2.0, 4.0])
+        poses_t = torch.as_tensor(poses).clone().requires_grad_(True)
+        loss, _ = quiet(icp_loss, [clouds], poses=[list(poses_t)], model=model, masks=masks, icp_point_to_plane=p2pl,
+                        icp_inlier_ratio=0.5, differentiable=True)
+        loss.backward()
+        return loss.item(), model.w.grad.numpy().copy(), poses_t.grad.numpy().copy(), clouds
+
+    for tag, p2pl in (('plane', True), ('point', False)):
+        loss, gw, gp, clouds = run(p2pl)
+        out['%s_loss' % tag], out['%s_w_grad' % tag], out['%s_poses_grad' % tag] = np.asarray(loss), gw, gp
+    for i, c in enumerate(clouds):
+        out['scan%d_inc_angles' % i] = c.inc_angles.numpy()
+        out['scan%d_mask' % i] = c.mask.numpy()
+        out['scan%d_normals' % i] = c.normals.numpy()
+    # precomputed correspondences: a boolean mask over scan i and an index list into scan i+1
+    rng = np.random.default_rng(2)
+    masks = []
+    for i in range(len(scans_np) - 1):
+        n1, n2 = len(scans_np[i]['points']), len(scans_np[i + 1]['points'])
+        m1 = rng.random(n1) < 0.3
+        m2 = rng.integers(0, n2, int(m1.sum()))
+        out['mask%d_1' % i], out['mask%d_2' % i] = m1, m2
+        masks.append((torch.as_tensor(m1), torch.as_tensor(m2)))
+    loss, gw, gp, _ = run(True, masks=[masks])
+    out['masked_plane_loss'], out['masked_plane_w_grad'], out['masked_plane_poses_grad'] = np.asarray(loss), gw, gp
+    np.savez_compressed(os.path.join(OUT, 'icp.npz'), **out)
+    print('icp.npz', {k: float(out[k]) for k in ('plane_loss', 'point_loss', 'masked_plane_loss')})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
@@ -269,6 +316,7 @@ def main():
     gen_misc(ref)
     gen_filters(ref)
     gen_stats(ref)
+    gen_icp(ref)
 
 
 if __name__ == '__main__':

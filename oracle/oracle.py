@@ -274,6 +274,38 @@ def shadow_mask(points, vps, dir_neighbors, dir_neighbor_weights, angle_bounds):
     return (ang.amin(dim=-1) >= lo) & (ang.amax(dim=-1) <= hi)
 
 
+# ----------------------------------------------------------------------------------------
+# ICP-style losses
+# ----------------------------------------------------------------------------------------
+def icp_pairs_loss(points, normals=None, inlier_ratio=0.5, point_to_plane=True, masks=None):
+    """loss.py:407-559 for one sequence: mean over consecutive pairs of scans of the point-to-plane
+    (0.5 * (1->2 + 2->1)) or point-to-point distance over the correspondences whose nearest-neighbour
+    distance is within the `inlier_ratio` quantile.  points / normals: lists of [n,3] tensors (world frame);
+    masks: optional list of (bool mask or indices into scan i, indices into scan i+1)."""
+    total = 0.0
+    n_pairs = len(points) - 1
+    for i in range(n_pairs):
+        a, b = points[i].float(), points[i + 1].float()           # loss.py:424-425, 509-510
+        if masks is None:
+            _, idx = cKDTree(b.detach().double().numpy()).query(a.detach().double().numpy(), k=1)
+            idx = torch.as_tensor(idx, dtype=torch.int64)
+            d = ((a - b[idx]) ** 2).sum(dim=-1).sqrt().detach()
+            keep = d <= torch.nanquantile(d, inlier_ratio)
+            sel1, sel2 = torch.nonzero(keep)[:, 0], idx[keep]
+        else:
+            m1, sel2 = torch.as_tensor(masks[i][0]), torch.as_tensor(masks[i][1]).long()
+            sel1 = torch.nonzero(m1)[:, 0] if m1.dtype == torch.bool else m1.long()
+        diff = b[sel2] - a[sel1]
+        if point_to_plane:
+            n1, n2 = normals[i][sel1], normals[i + 1][sel2]
+            d12 = ((n1 * diff).sum(dim=-1, keepdim=True) * n1).norm(dim=-1).mean()
+            d21 = ((n2 * -diff).sum(dim=-1, keepdim=True) * n2).norm(dim=-1).mean()
+            total = total + 0.5 * (d12 + d21)
+        else:
+            total = total + diff.norm(dim=-1).mean()
+    return total / n_pairs
+
+
 def reduce(x, reduction='mean', only_finite=False, skip_nans=False):
     if only_finite:
         x = x[x.isfinite()]

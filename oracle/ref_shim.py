@@ -66,12 +66,30 @@ def install_stubs():
     p3.io = _stub('pytorch3d.io', load_ply=None, load_obj=None, IO=_Dummy)
     p3.structures = _stub('pytorch3d.structures', Meshes=_Dummy, Pointclouds=_Dummy)
     p3.ops = _stub('pytorch3d.ops')
-    p3.ops.knn = _stub('pytorch3d.ops.knn', knn_points=None)
+    p3.ops.knn = _stub('pytorch3d.ops.knn', knn_points=knn_points_exact)
     p3.transforms = _stub('pytorch3d.transforms',
                           axis_angle_to_matrix=_oracle.axis_angle_to_matrix,
                           matrix_to_quaternion=None,
                           quaternion_to_axis_angle=None,
                           axis_angle_to_quaternion=_oracle.axis_angle_to_quaternion)
+
+
+def knn_points_exact(p1, p2, K=1):
+    """Stand-in for pytorch3d.ops.knn.knn_points (not vendored, not installed; the reference's ICP losses call it
+    at loss.py:445, 532 with K=1): batched nearest neighbours of p1 [1,n1,3] in p2 [1,n2,3] -> (squared distances
+    [1,n1,K], indices [1,n1,K], None).  pytorch3d searches by brute force in the tensors' dtype; this stand-in
+    searches exactly (scipy cKDTree on the same values), so it differs from pytorch3d only for float32 near-ties
+    ("parity unpinned" against pytorch3d itself).  Distances stay differentiable like pytorch3d's."""
+    import numpy as np
+    import torch
+    from scipy.spatial import cKDTree
+    assert K == 1 and p1.dim() == 3 and p1.shape[0] == 1
+    a = p1[0].detach().cpu().numpy().astype(np.float64)
+    b = p2[0].detach().cpu().numpy().astype(np.float64)
+    _, idx = cKDTree(b).query(a, k=1)
+    idx = torch.as_tensor(idx, dtype=torch.int64)
+    d2 = ((p1[0] - p2[0][idx]) ** 2).sum(dim=-1)
+    return d2[None, :, None], idx[None, :, None], None
 
 
 def load():

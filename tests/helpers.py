@@ -76,3 +76,15 @@ def well_separated(eigvals, gap=1e-3):
     ev = np.asarray(eigvals)
     scale = np.maximum(np.abs(ev[:, 2]), 1e-300)
     return ((ev[:, 1] - ev[:, 0]) > gap * scale) & ((ev[:, 2] - ev[:, 1]) > gap * scale) & np.isfinite(ev).all(axis=1)
+
+
+def icp_inputs(g):
+    """tests/golden/icp.npz -> per-scan fp64 tensors (float32 values) for the oracle / the CUDA path."""
+    S = int(g['n_scans'])
+    scans = []
+    for i in range(S):
+        scans.append({'points': torch.as_tensor(g['scan%d_points' % i].astype(np.float64)),
+                      'inc_angles': torch.as_tensor(g['scan%d_inc_angles' % i]), 'mask': torch.as_tensor(g['scan%d_mask' % i]),
+                      'normals': torch.as_tensor(g['scan%d_normals' % i])})
+    masks = [(torch.as_tensor(g['mask%d_1' % i]), torch.as_tensor(g['mask%d_2' % i])) for i in range(S - 1)]
+    return scans, torch.as_tensor(g['poses']), torch.as_tensor(g['w']).reshape(1, -1), torch.as_tensor(g['exponent']).reshape(1, -1), masks

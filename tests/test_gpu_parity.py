@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import RTOL, STEP_TAGS, eig_close, rel_err, rel_err_norm, same_neighbor_sets, step_inputs, well_separated
+from helpers import RTOL, STEP_TAGS, eig_close, icp_inputs, rel_err, rel_err_norm, same_neighbor_sets, step_inputs, well_separated
 
 pytestmark = pytest.mark.gpu
 
@@ -557,3 +557,55 @@ def test_global_cloud_statistics_and_mask_match_reference(dc, dev, golden):
     both = resolved & resolved_local
     assert np.array_equal(mask[both], g['mask'][both])
     assert both.mean() > 0.9 and g['mask'][both].sum() > 500
+
+
+# ------------------------------------------------------------------------------------------------
+# ICP-style losses
+# ------------------------------------------------------------------------------------------------
+def _our_icp(dc, dev, g, point_to_plane, use_masks, dtype=torch.float64):
+    scans, poses, w, exponent, masks = icp_inputs(g)
+    clouds = []
+    for s in scans:
+        c = dc.DepthCloud.from_points(s['points'].to(device=dev, dtype=dtype))
+        c.inc_angles = s['inc_angles'].to(device=dev, dtype=dtype)
+        c.mask = s['mask'].to(dev)
+        c.normals = s['normals'].to(device=dev, dtype=dtype)
+        clouds.append(c)
+    model = dc.ScaledPolynomial(w=w.reshape(-1).tolist(), exponent=exponent.reshape(-1).tolist(), device=dev)
+    poses_t = poses.to(dev).clone().requires_grad_(True)
+    mk = [[(a.to(dev), b.to(dev)) for a, b in masks]] if use_masks else None
+    loss, loss_clouds = dc.icp_loss([clouds], poses=[list(poses_t)], model=model, masks=mk, icp_point_to_plane=point_to_plane,
+                                    icp_inlier_ratio=0.5)
+    loss.backward()
+    assert len(loss_clouds) == 1 and len(loss_clouds[0]) == sum(len(c) for c in clouds)
+    return loss.item(), model.w.grad.cpu().numpy(), poses_t.grad.cpu().numpy()
+
+
+@pytest.mark.parametrize('tag,p2pl,use_masks', [('plane', True, False), ('point', False, False), ('masked_plane', True, True)])
+def test_icp_loss_matches_reference(dc, dev, golden, tag, p2pl, use_masks):
+    """icp_loss forward + backward (model weights, poses) against the reference, which evaluates the residuals in
+    float32 (loss.py:424-425; its own rounding is ~1e-6 relative), and against the fp64 oracle."""
+    g = golden('icp')
+    loss, gw, gp = _our_icp(dc, dev, g, p2pl, use_masks)
+    assert abs(loss - float(g[tag + '_loss'])) <= RTOL * abs(float(g[tag + '_loss']))
+    assert rel_err_norm(gw, g[tag + '_w_grad']) < 1e-4
+    assert rel_err_norm(gp, g[tag + '_poses_grad']) < 1e-4
+    from test_oracle import _oracle_icp
+    lo, gwo, gpo = _oracle_icp(g, p2pl, use_masks)
+    assert abs(loss - lo) <= RTOL * abs(lo)
+    assert rel_err_norm(gw, gwo) < RTOL and rel_err_norm(gp, gpo) < RTOL
+    # float32 clouds (the storage type of the B200 path)
+    l32, gw32, gp32 = _our_icp(dc, dev, g, p2pl, use_masks, dtype=torch.float32)
+    assert abs(l32 - lo) <= 1e-4 * abs(lo)
+
+
+def test_icp_by_name_and_quantile(dc, dev):
+    from depth_correction_b200.icp import nanquantile
+    assert dc.loss_by_name('icp_loss') is dc.icp_loss
+    rng = np.random.default_rng(3)
+    x = rng.random(1001)
+    x[::50] = np.nan
+    xt = torch.as_tensor(x, device=dev)
+    for q in (0.0, 0.25, 0.5, 0.9, 1.0):
+        assert nanquantile(xt, q).item() == torch.nanquantile(torch.as_tensor(x), q).item()
+    assert torch.isnan(nanquantile(torch.full((5,), float('nan'), device=dev, dtype=torch.float64), 0.5))

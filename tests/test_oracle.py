@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import oracle, ref_shim
-from helpers import STEP_TAGS, rel_err, rel_err_norm, step_inputs, well_separated
+from helpers import STEP_TAGS, icp_inputs, rel_err, rel_err_norm, step_inputs, well_separated
 
 
 def test_nn_matches_reference_golden(golden):
@@ -139,3 +139,29 @@ def test_shadow_filter_against_reference(golden):
         assert nb.shape[1] == int(g['shadow_K_' + tag])
         keep = oracle.shadow_mask(sp, vps, nb, w, bounds)
         assert np.array_equal(torch.nonzero(keep)[:, 0].numpy(), g['shadow_kept_' + tag]), tag
+
+
+def _oracle_icp(g, point_to_plane, use_masks):
+    scans, poses, w, exponent, masks = icp_inputs(g)
+    w = w.clone().requires_grad_(True)
+    poses = poses.clone().requires_grad_(True)
+    pts, nrm = [], []
+    for s, T in zip(scans, poses):
+        vps, dirs, depth = oracle.from_points(s['points'])
+        d = oracle.correct_depth(depth, s['inc_angles'], s['mask'], w, exponent, scaled=True)
+        local = vps + d * dirs
+        pts.append(local @ T[:3, :3].T + T[:3, 3])
+        nrm.append(s['normals'] @ T[:3, :3].T)
+    loss = oracle.icp_pairs_loss(pts, nrm, 0.5, point_to_plane, masks if use_masks else None)
+    loss.backward()
+    return loss.item(), w.grad.numpy(), poses.grad.numpy()
+
+
+@pytest.mark.parametrize('tag,p2pl,use_masks', [('plane', True, False), ('point', False, False), ('masked_plane', True, True)])
+def test_icp_loss_against_reference(golden, tag, p2pl, use_masks):
+    g = golden('icp')
+    loss, gw, gp = _oracle_icp(g, p2pl, use_masks)
+    # the reference evaluates the residuals in float32 (loss.py:424-425): its own rounding is ~1e-6 relative
+    assert abs(loss - float(g[tag + '_loss'])) <= 1e-5 * abs(float(g[tag + '_loss']))
+    assert rel_err_norm(gw, g[tag + '_w_grad']) < 1e-4
+    assert rel_err_norm(gp, g[tag + '_poses_grad']) < 1e-4
