@@ -39,6 +39,8 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--scans', type=int, default=64, help='scans per GPU (weak scaling)')
     ap.add_argument('--pattern', default='os0-128')
+    ap.add_argument('--scene', default='corridor', choices=['corridor', 'street'],
+                    help='street + --pattern hdl-64 = the KITTI-360-shaped workload of BASELINE.json configs[2]')
     ap.add_argument('--cpu-scans', type=int, default=6, help='scans in the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile', action='store_true', help='small fixed workload for ncu (no baseline, no e2e)')
@@ -108,8 +110,12 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------
+SCENE = 'corridor'
+
+
 def host_scans(n_scans, pattern, first_scan=0):
-    scans, _, poses = make_sequence('corridor', n_scans=n_scans, pattern=pattern, seed=0, first_scan=first_scan)
+    clip = (1.0, 25.0) if SCENE == 'corridor' else (5.0, 80.0)
+    scans, _, poses = make_sequence(SCENE, n_scans=n_scans, pattern=pattern, seed=0, first_scan=first_scan, depth_clip=clip)
     return [s['points'] for s in scans], poses
 
 
@@ -138,8 +144,8 @@ def one_step(dc, clouds, poses, deltas, model, cfg, ns=None, timers=None, local=
         cloud = dc.global_cloud(clouds=clouds, model=model, poses=p0)
         feats = dc.compute_neighborhood_features(cloud=cloud, neighborhoods=ns, cfg=cfg)
         feats.step_state()                       # pack the scan records in sorted order
-        # (the reverse lists of the gather-form backward are built by the library once a graph has served
-        #  more than fused.TRANSPOSE_AFTER backward passes; a graph that is searched anew every step never does)
+        # (the backward runs in the scatter form: one float32 vector reduction per edge on maps of >= 2^20 points,
+        #  fp64 reductions below; DC_BACKWARD=gather selects the deterministic fp64 gather form, fused.py)
     e1.record()
     model.zero_grad(set_to_none=True)
     deltas.grad = None
@@ -168,6 +174,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        # NCCL_DEBUG=VERSION (and WARN) make NCCL print its version banner on stdout, in front of the one JSON line
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() in ('VERSION', 'WARN'):
+            os.environ['NCCL_DEBUG'] = 'NONE'
         dist.init_process_group('nccl', device_id=dev)
     import depth_correction_b200 as dc
     from depth_correction_b200 import _lib as L
@@ -178,7 +187,7 @@ def run_ours(args):
     # weak scaling: every rank ingests `n_scans` consecutive scans of one long corridor (scan-sharded ingestion)
     pts_host, _ = host_scans(n_scans, args.pattern, first_scan=rank * n_scans)
     my_scans = list(range(rank * n_scans, (rank + 1) * n_scans))
-    poses_np = make_poses('corridor', n_scans_total)
+    poses_np = make_poses(SCENE, n_scans_total)
     cfg = dc.Config(nn_k=NN_K, nn_r=NN_R, pose_correction=dc.PoseCorrection.pose)
     pts_pinned = [torch.from_numpy(p).pin_memory() for p in pts_host]
     pts_dev = [p.to(dev, non_blocking=True) for p in pts_pinned]
@@ -260,8 +269,7 @@ def run_ours(args):
     value = n_total / (ms_per_step * 1e-3)
 
     # ---- steady state of a training run: the graph of the last search is REUSED (the reference searches once per
-    # run, preproc.py:168-191 / train.py:172-175); after fused.TRANSPOSE_AFTER backward passes the library has built
-    # the reverse lists and the backward runs in its atomic-free gather form
+    # run, preproc.py:168-191 / train.py:172-175)
     L.profile = None
     for _ in range(4):
         one_step(dc, clouds, poses, deltas, model, cfg, ns=ns, local=local)
@@ -282,6 +290,15 @@ def run_ours(args):
         t = torch.tensor([fixed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         fixed_ms = t.item()
+    # ---- full-size parity property: the gradients of the timed path (fp32 vector-reduction scatter on large maps)
+    # against the deterministic fp64 gather form on the same graph and inputs
+    gw_fast, gd_fast = model.w.grad.detach().clone(), deltas.grad.detach().clone()
+    os.environ['DC_BACKWARD'] = 'gather'
+    one_step(dc, clouds, poses, deltas, model, cfg, ns=ns, local=local)
+    os.environ.pop('DC_BACKWARD')
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+    grad_check = {'w_grad_rel_err_vs_fp64_gather': rel(gw_fast, model.w.grad), 'pose_grad_rel_err_vs_fp64_gather': rel(gd_fast, deltas.grad)}
+    ns.graph._transposed = None          # (release the reverse lists again)
 
     # ---- end-to-end through the public API from pinned HOST buffers (H2D + D2H inside the timed region)
     inc_host = [c.inc_angles.cpu().pin_memory() for c in ingested]
@@ -340,8 +357,9 @@ def run_ours(args):
         'dc_step_points': nr * (36 + 32),
         'dc_step_forward': idx_fwd + nr * (32 + 4 + 8 + 64),
         'dc_step_backward': idx_bwd + nr * (32 + 4 + 24),                   # gather form (transposed graph)
-        'dc_step_backward_scatter': idx_fwd + nr * (64 + 24 + 24),          # scatter form: stash, g zero + g reduce
-        'dc_step_chain': nr * (24 + 36 + 4),
+        # scatter form: stash, g zero + g reduce (float32 x 4 on maps of >= 2^20 points, else fp64 x 3)
+        'dc_step_backward_scatter': idx_fwd + nr * (64 + (32 if nr >= (1 << 20) else 48)),
+        'dc_step_chain': nr * ((16 if nr >= (1 << 20) else 24) + 36 + 4),
     }
     peak, peak_src = peaks()
     traffic = {}
@@ -381,7 +399,7 @@ def run_ours(args):
         'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64 arithmetic on f32 records', 'data': 'synthetic',
-        'config': {'workload': 'corridor, %d full-res %s scans per GPU, kNN k=%d within r=%.1f m, ScaledPolynomial[2,4] + '
+        'config': {'workload': SCENE + ', %d full-res %s scans per GPU, kNN k=%d within r=%.1f m, ScaledPolynomial[2,4] + '
                                'min_eigval_loss(normalization) + per-scan SE(3) corrections' % (n_scans, args.pattern, NN_K, NN_R),
                    'n_points': n_total, 'n_points_per_gpu': n_local, 'n_resident_per_gpu_incl_halo': n_resident, 'k': NN_K, 'r': NN_R,
                    'l2_policy': 'inputs larger than L2 (point + index + stash arrays %.0f MB)' %
@@ -390,7 +408,7 @@ def run_ours(args):
         'search_ms': search_ms, 'first_step_on_new_graph_ms': step_ms,
         'search_points_per_s': n_total / (search_ms * 1e-3),
         'fixed_graph_step_ms': fixed_ms, 'fixed_graph_step_points_per_s': n_total / (fixed_ms * 1e-3),
-        'loss': float(gl.item()),
+        'loss': float(gl.item()), 'grad_check': grad_check,
         'clocks': clocks, 'gpu_launches': launches,
         'e2e': {'value': n_total / e2e_s, 'unit': 'points/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_s * 1e3},
@@ -476,7 +494,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': (ts + tf) * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'corridor, full-res %s scans, kNN k=%d within r=%.1f m, ScaledPolynomial[2,4] + '
+        'config': {'workload': SCENE + ', full-res %s scans, kNN k=%d within r=%.1f m, ScaledPolynomial[2,4] + '
                                'min_eigval_loss(normalization) + per-scan SE(3) corrections; bounded CPU sample: %s'
                                % (args.pattern, NN_K, NN_R, sample), 'n_points': n, 'k': NN_K, 'r': NN_R},
         'search_ms': ts * 1e3, 'fixed_graph_step_ms': tf * 1e3, 'loss': loss,
@@ -487,6 +505,7 @@ def run_reference(args):
 
 if __name__ == '__main__':
     a = parse_args()
+    SCENE = a.scene
     if a.impl == 'reference':
         run_reference(a)
     else:

@@ -75,8 +75,8 @@ SIGNATURES = {
     'dc_step_points': [_P, _P, _P, _I, _L, _P, _I, _I, _P, _P, _I, _P, _P],
     'dc_step_forward': [_P, _P, _L, _P, _P, _I, _I, _P, _P, _P, _P, _P, _SZ, _P],
     'dc_step_backward': [_P, _L, _P, _P, _P, _P, _P, _P, _P],
-    'dc_step_backward_scatter': [_P, _L, _P, _P, _P, _P, _P, _P],
-    'dc_step_chain': [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P],
+    'dc_step_backward_scatter': [_P, _L, _P, _P, _P, _P, _P, _I, _P],
+    'dc_step_chain': [_P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P],
     'dc_pose_compose': [_P, _P, _I, _I, _P, _P],
     'dc_pose_compose_backward': [_P, _P, _I, _I, _P, _P, _P],
     'dc_features': [_P, _I, _L, _P, _P, _I, _P, _P, _P],

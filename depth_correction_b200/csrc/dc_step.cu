@@ -472,10 +472,17 @@ step_backward_gather_kernel(const dc_point* __restrict__ P, int64_t n, const int
 // u_i A_i (p_j - m_i) to g_j with fire-and-forget fp64 reductions (RED.E.ADD.F64, addresses spread over
 // all points -> no hot spots).  Used for the first backward passes on an asymmetric (kNN) graph, before
 // building the transpose has paid off; g is accumulated in SORTED space and must be zeroed by the caller.
+// F32 = true: one 16-byte vector reduction (red.global.add.v4.f32) per edge into a float4 accumulator instead of
+// three fp64 reductions.  The L2 retires ~220 G reductions / s whatever their width (tools/micro/red_bench.cu), so
+// this form is 3x faster; the accumulators then carry fp32 rounding (relative 6e-8 per addition, random sign), which
+// averages out over the >= 1e6 points the chain stage sums -- used for large maps only, see fused.py.
+template <bool F32>
 __global__ void __launch_bounds__(STEP_THREADS)
 step_backward_scatter_kernel(const dc_point* __restrict__ P, int64_t n, const int64_t* __restrict__ slice_ptr,
                              const int32_t* __restrict__ ell_idx, const dc_stash* __restrict__ stash,
-                             const double* __restrict__ upstream, double* __restrict__ g_sorted) {
+                             const double* __restrict__ upstream, void* __restrict__ g_out) {
+  double* g_sorted = reinterpret_cast<double*>(g_out);
+  float4* g_sorted32 = reinterpret_cast<float4*>(g_out);
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (row >= n) return;
   const int lane = threadIdx.x & 31;
@@ -493,10 +500,16 @@ step_backward_scatter_kernel(const dc_point* __restrict__ P, int64_t n, const in
     const dc_point pj = dc_ld_point(P + (j_));                                       \
     const double ex = pj.x - s0.x, ey = pj.y - s0.y, ez = pj.z - s0.z;               \
     const double a = ua * (s0.w * ex + s1.x * ey + s1.y * ez);                       \
-    double* o = g_sorted + 3 * (size_t)(j_);                                         \
-    atomicAdd(o, a * s0.w + ub * ex);                                                \
-    atomicAdd(o + 1, a * s1.x + ub * ey);                                            \
-    atomicAdd(o + 2, a * s1.y + ub * ez);                                            \
+    const double vx = a * s0.w + ub * ex, vy = a * s1.x + ub * ey, vz = a * s1.y + ub * ez; \
+    if (F32) {                                                                       \
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g_sorted32 + (j_)), "f"((float)vx), \
+                   "f"((float)vy), "f"((float)vz), "f"(0.f) : "memory");             \
+    } else {                                                                         \
+      double* o = g_sorted + 3 * (size_t)(j_);                                       \
+      atomicAdd(o, vx);                                                              \
+      atomicAdd(o + 1, vy);                                                          \
+      atomicAdd(o + 2, vz);                                                          \
+    }                                                                                \
   }
   int c = 0;
   for (; c + 4 <= width; c += 4) {
@@ -512,11 +525,16 @@ step_backward_scatter_kernel(const dc_point* __restrict__ P, int64_t n, const in
 }
 
 extern "C" int dc_step_backward_scatter(const void* points, int64_t n, const int64_t* slice_ptr, const int32_t* ell_idx,
-                                        const double* stash, const double* upstream_pp, double* g_sorted, void* stream) {
+                                        const double* stash, const double* upstream_pp, void* g_sorted, int g_dtype,
+                                        void* stream) {
   if (n <= 0) return DC_OK;
   const int blocks = dc_blocks(n, STEP_THREADS);
-  step_backward_scatter_kernel<<<blocks, STEP_THREADS, 0, (cudaStream_t)stream>>>((const dc_point*)points, n, slice_ptr, ell_idx,
-                                                                                 (const dc_stash*)stash, upstream_pp, g_sorted);
+  if (g_dtype == DC_F32)
+    step_backward_scatter_kernel<true><<<blocks, STEP_THREADS, 0, (cudaStream_t)stream>>>((const dc_point*)points, n, slice_ptr, ell_idx,
+                                                                                         (const dc_stash*)stash, upstream_pp, g_sorted);
+  else
+    step_backward_scatter_kernel<false><<<blocks, STEP_THREADS, 0, (cudaStream_t)stream>>>((const dc_point*)points, n, slice_ptr, ell_idx,
+                                                                                          (const dc_stash*)stash, upstream_pp, g_sorted);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
@@ -537,7 +555,7 @@ extern "C" int dc_step_backward(const void* points, int64_t n, const int64_t* sl
 
 template <typename T>
 __global__ void __launch_bounds__(CHAIN_THREADS)
-step_chain_kernel(const double* __restrict__ g, const int32_t* __restrict__ g_index,
+step_chain_kernel(const void* __restrict__ g_any, int g_f32, const int32_t* __restrict__ g_index,
                   const typename vec4_of<T>::type* __restrict__ rec_dir,
                   const typename vec4_of<T>::type* __restrict__ rec_vp, const uint32_t* __restrict__ rec_meta,
                   const int32_t* __restrict__ block_scan, const int64_t* __restrict__ block_start,
@@ -556,7 +574,14 @@ step_chain_kernel(const double* __restrict__ g, const int32_t* __restrict__ g_in
     const typename vec4_of<T>::type a = rec_dir[i], b = rec_vp[i];
     const uint32_t meta = rec_meta[i];
     const size_t gi = g_index ? (size_t)g_index[i] : (size_t)i;   // g in sorted space (scatter form) or in place
-    const double gx = g[3 * gi], gy = g[3 * gi + 1], gz = g[3 * gi + 2];
+    double gx, gy, gz;
+    if (g_f32) {
+      const float4 gv = reinterpret_cast<const float4*>(g_any)[gi];
+      gx = (double)gv.x; gy = (double)gv.y; gz = (double)gv.z;
+    } else {
+      const double* g = reinterpret_cast<const double*>(g_any);
+      gx = g[3 * gi]; gy = g[3 * gi + 1]; gz = g[3 * gi + 2];
+    }
     const bool mm = (model.kind != DC_MODEL_NONE) && (meta & DC_PT_MODEL_MASK);
     double pw[DC_MAX_TERMS];
     const double d0 = (double)a.w, gam = (double)b.w;
@@ -625,7 +650,7 @@ step_chain_reduce_kernel(const double* __restrict__ partials, int n_blocks, cons
   }
 }
 
-extern "C" int dc_step_chain(const double* g, const int32_t* g_index, const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta, int dtype,
+extern "C" int dc_step_chain(const void* g, int g_dtype, const int32_t* g_index, const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta, int dtype,
                              const int32_t* block_scan, const int64_t* block_start, const int32_t* block_count,
                              int n_blocks, const int32_t* scan_block_first, const double* poses, int n_scans,
                              int model_kind, const double* w, const double* exponent, int n_terms, double* partials,
@@ -636,10 +661,10 @@ extern "C" int dc_step_chain(const double* g, const int32_t* g_index, const void
   cudaStream_t st = (cudaStream_t)stream;
   const int want_exp = dexponent != nullptr;
   if (dtype == DC_F32)
-    step_chain_kernel<float><<<n_blocks, CHAIN_THREADS, 0, st>>>(g, g_index, (const float4*)rec_dir, (const float4*)rec_vp, rec_meta, block_scan,
+    step_chain_kernel<float><<<n_blocks, CHAIN_THREADS, 0, st>>>(g, g_dtype == DC_F32, g_index, (const float4*)rec_dir, (const float4*)rec_vp, rec_meta, block_scan,
                                                                  block_start, block_count, poses, m, want_exp, partials);
   else
-    step_chain_kernel<double><<<n_blocks, CHAIN_THREADS, 0, st>>>(g, g_index, (const double4*)rec_dir, (const double4*)rec_vp, rec_meta, block_scan,
+    step_chain_kernel<double><<<n_blocks, CHAIN_THREADS, 0, st>>>(g, g_dtype == DC_F32, g_index, (const double4*)rec_dir, (const double4*)rec_vp, rec_meta, block_scan,
                                                                   block_start, block_count, poses, m, want_exp, partials);
   DC_LAUNCH_CHECK();
   step_chain_reduce_kernel<<<1, 256, 0, st>>>(partials, n_blocks, scan_block_first, n_scans, model_kind != DC_MODEL_NONE ? n_terms : 0,

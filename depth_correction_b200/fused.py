@@ -10,6 +10,7 @@ kernels write (corrected points, backward stash, per-point loss).  `fused_loss` 
 
 as three kernel launches forward+backward-prologue and one backward launch.
 """
+import os
 import weakref
 
 import torch
@@ -19,6 +20,13 @@ from . import _lib as L
 __all__ = ['StepState', 'fused_loss', 'model_kind_of']
 
 TRANSPOSE_AFTER = 2                     # backward passes served by the scatter form before a kNN graph is transposed
+# The scatter form accumulates dL/dp in float32 (one vector reduction per edge instead of three fp64 ones, 3x faster)
+# on maps of at least this many points: there the fp32 rounding of the per-point sums (random, 6e-8 relative per
+# addition) averages out over the points the chain stage adds up in fp64 (measured: gradients agree with the fp64
+# gather form to ~1e-7 on the bench map, tests/test_gpu_parity.py::test_scatter_f32_agrees_with_gather_form).
+# DC_SCATTER_F32=0 / 1 forces the choice; DC_BACKWARD=gather forces the deterministic fp64 gather form (bitwise
+# reproducible gradients), DC_BACKWARD=scatter the scatter form.
+SCATTER_F32_MIN_POINTS = 1 << 20
 CHAIN_CHUNK = 2048                      # rows per block of the chain stage (256 threads x 8)
 CHAIN_REC = 12 + 2 * L.MAX_TERMS        # doubles per partial record (dc_step.cu)
 
@@ -95,7 +103,8 @@ class StepState(object):
         self.P = torch.empty((n, 4), dtype=torch.float64, device=dev)
         self.stash = torch.empty((n, 8), dtype=torch.float64, device=dev)
         self.loss_pp = torch.empty(n, dtype=torch.float64, device=dev)
-        self.g = torch.empty((n, 3), dtype=torch.float64, device=dev)       # dL/dp per point, original order
+        self.g = torch.empty((n, 3), dtype=torch.float64, device=dev)       # dL/dp per point (fp64 forms)
+        self._g32 = None                                                    # float32 [n,4] accumulator of the fp32 scatter form
         self.n_blocks = ((n + 31) // 32 * 32 + 127) // 128
         self.partials = torch.zeros(2 * self.n_blocks + 2, dtype=torch.float64, device=dev)
         # block table of the chain stage: blocks are aligned to scans (CHAIN_CHUNK rows each)
@@ -192,9 +201,15 @@ class _FusedStep(torch.autograd.Function):
         # graph use the scatter form and the transpose is built once the graph is evidently being reused.
         graph = ctx.graph
         graph._bwd_calls = getattr(graph, '_bwd_calls', 0) + 1
-        if graph.symmetric:
+        force = os.environ.get('DC_SCATTER_F32')
+        scatter_f32 = (state.n >= SCATTER_F32_MIN_POINTS) if force is None else force == '1'
+        form = os.environ.get('DC_BACKWARD', 'auto')           # auto | gather | scatter
+        if form == 'scatter' or (form == 'auto' and scatter_f32 and not graph.symmetric):
+            gt = None                    # large kNN maps: the fp32 scatter form beats the gather form outright (1.4 vs 2.0 ms
+                                         # on the bench map) and needs no reverse lists
+        elif graph.symmetric:
             gt = graph
-        elif graph._transposed is not None or graph._bwd_calls > TRANSPOSE_AFTER:
+        elif form == 'gather' or graph._transposed is not None or graph._bwd_calls > TRANSPOSE_AFTER:
             gt = graph.transposed()
         else:
             gt = None
@@ -205,17 +220,22 @@ class _FusedStep(torch.autograd.Function):
         if raw:
             upstream = grads[0].to(torch.float64).contiguous()
         g_index = None
+        g_buf, g_code = state.g, L.DC_F64
         if gt is not None:
             # gather form over the transposed graph: atomic-free, deterministic
             L.call('dc_step_backward', L.ptr(state.P), state.n, L.ptr(gt.slice_ptr), L.ptr(gt.ell_idx), L.ptr(state.stash),
                    L.ptr(upstream), L.ptr(graph.map.order), L.ptr(state.g), st)
         else:
             # scatter form over the forward graph (L2 reductions): no transpose needed yet
-            state.g.zero_()
+            if scatter_f32:
+                if state._g32 is None:
+                    state._g32 = torch.empty((state.n, 4), dtype=torch.float32, device=dev)
+                g_buf, g_code = state._g32, L.DC_F32
+            g_buf.zero_()
             L.call('dc_step_backward_scatter', L.ptr(state.P), state.n, L.ptr(graph.slice_ptr), L.ptr(graph.ell_idx),
-                   L.ptr(state.stash), L.ptr(upstream), L.ptr(state.g), st)
+                   L.ptr(state.stash), L.ptr(upstream), L.ptr(g_buf), g_code, st)
             g_index = graph.map.inv_order
-        L.call('dc_step_chain', L.ptr(state.g), L.ptr(g_index), L.ptr(state.rec_dir_o), L.ptr(state.rec_vp_o), L.ptr(state.rec_meta_o),
+        L.call('dc_step_chain', L.ptr(g_buf), g_code, L.ptr(g_index), L.ptr(state.rec_dir_o), L.ptr(state.rec_vp_o), L.ptr(state.rec_meta_o),
                state.code, L.ptr(state.blk_scan), L.ptr(state.blk_start), L.ptr(state.blk_count), state.chain_blocks,
                L.ptr(state.scan_blk_first), L.ptr(poses12), S, model_kind, L.ptr(wv), L.ptr(ev), n_terms,
                L.ptr(state.chain_partials), L.ptr(dw), L.ptr(dexp), L.ptr(dposes), st)

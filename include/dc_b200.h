@@ -197,19 +197,21 @@ int dc_step_forward(const void* points, const uint32_t* rec_meta, int64_t n, con
 int dc_step_backward(const void* points, int64_t n, const int64_t* slice_ptr_t, const int32_t* ell_idx_t,
                      const double* stash, const double* upstream_pp, const int32_t* order, double* g_out, void* stream);
 
-/* pass C1, scatter form: row i adds u_i A_i (p_j - m_i) to g_sorted[j] (fp64 [n,3] in SORTED space, zeroed by the
- * caller) for every j of its own list with L2 reductions -- no transposed graph needed.  Used for the first
- * backward passes on a kNN graph, before building the transpose pays off. */
+/* pass C1, scatter form: row i adds u_i A_i (p_j - m_i) to g_sorted[j] (SORTED space, zeroed by the caller) for
+ * every j of its own list with L2 reductions -- no transposed graph needed.  Used for the first backward passes on
+ * a kNN graph, before building the transpose pays off.  g_dtype = DC_F64: g_sorted fp64 [n,3], three reductions per
+ * edge; DC_F32: g_sorted float32 [n,4] (16-byte aligned), ONE vector reduction per edge (3x the edge rate, fp32
+ * accumulation -- meant for large maps, where the rounding averages out in the chain stage). */
 int dc_step_backward_scatter(const void* points, int64_t n, const int64_t* slice_ptr, const int32_t* ell_idx,
-                             const double* stash, const double* upstream_pp, double* g_sorted, void* stream);
+                             const double* stash, const double* upstream_pp, void* g_sorted, int g_dtype, void* stream);
 
-/* pass C2 + C3: chain g (row of original point i: g[g_index[i]], or g[i] when g_index == NULL) through p = R_s (vp + d' dir) + t_s to dw[n_terms],
+/* pass C2 + C3: chain g (fp64 [n,3] or, g_dtype = DC_F32, float32 [n,4]; row of original point i: g[g_index[i]], or g[i] when g_index == NULL) through p = R_s (vp + d' dir) + t_s to dw[n_terms],
  * dexponent[n_terms] (NULL to skip) and dposes[S,12]; outputs are ACCUMULATED (caller zeroes).
  * Records are the dc_pack_records layout packed with inv_order == NULL (original order).  The block table
  * aligns blocks to scans: block b covers rows [block_start[b], block_start[b] + block_count[b]) of scan
  * block_scan[b]; blocks of scan s are [scan_block_first[s], scan_block_first[s+1]).  partials: scratch of
  * n_blocks * (12 + 2*DC_MAX_TERMS) doubles.  Block reductions + fixed-order final sums: deterministic. */
-int dc_step_chain(const double* g, const int32_t* g_index, const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta, int dtype,
+int dc_step_chain(const void* g, int g_dtype, const int32_t* g_index, const void* rec_dir, const void* rec_vp, const uint32_t* rec_meta, int dtype,
                   const int32_t* block_scan, const int64_t* block_start, const int32_t* block_count, int n_blocks,
                   const int32_t* scan_block_first, const double* poses, int n_scans, int model_kind, const double* w,
                   const double* exponent, int n_terms, double* partials, double* dw, double* dexponent, double* dposes,
