@@ -44,20 +44,43 @@ def model_kind_of(model):
     raise NotImplementedError('fused step supports Polynomial / ScaledPolynomial models, got %s' % name)
 
 
+_scan_table_cache = {}      # key -> (tbl, first, keep); two entries (the search and the step of one iteration use the same scans)
+
+
+def _plain(t, dt, shape_tail):
+    """The tensor itself when it already is a contiguous `dt` array of the expected shape (no torch op at all)."""
+    return t.dtype == dt and t.is_contiguous() and tuple(t.shape[1:]) == shape_tail
+
+
 def scan_table(clouds, dt):
     """Device table of per-scan tensor addresses for the batched kernels: (tbl int64 [S,5] = {vps, dirs, depth,
-    inc_angles, model mask} (0 = absent), first int64 [S+1], keep-alive list of the tensors the table points to)."""
+    inc_angles, model mask} (0 = absent), first int64 [S+1], keep-alive list of the tensors the table points to).
+    Host cost matters here (it sits in front of the search): tensors that are already in kernel layout are used as
+    they are, and the table of an unchanged list of scans is reused."""
+    key = (dt,) + tuple((id(c), c.depth.data_ptr(), c.dirs.data_ptr(), c.vps.data_ptr(),
+                         0 if c.inc_angles is None else c.inc_angles.data_ptr(),
+                         0 if c.mask is None else (c.mask.data_ptr(), c.mask._version)) for c in clouds)
+    hit = _scan_table_cache.get(key)
+    if hit is not None:
+        return hit
     rows, keep, first = [], [], [0]
     dev = clouds[0].depth.device
     for c in clouds:
         cnt = len(c)
         assert c.depth.dtype == dt and c.dirs.is_cuda
-        dirs = c.dirs.detach().reshape(-1, 3).contiguous()
-        vps = c.vps.detach()
-        vps = vps.to(dt).contiguous() if vps.shape[0] == cnt else vps.to(dt).expand(cnt, 3).contiguous()
-        depth = c.depth.detach().reshape(-1).contiguous()
-        inc = None if c.inc_angles is None else c.inc_angles.detach().reshape(-1).to(dt).contiguous()
-        mm = None if c.mask is None else c.mask.detach().to(torch.uint8).contiguous()
+        dirs = c.dirs if _plain(c.dirs, dt, (3,)) else c.dirs.detach().reshape(-1, 3).contiguous()
+        vps = c.vps
+        if not (_plain(vps, dt, (3,)) and vps.shape[0] == cnt):
+            vps = vps.detach()
+            vps = vps.to(dt).contiguous() if vps.shape[0] == cnt else vps.to(dt).expand(cnt, 3).contiguous()
+        depth = c.depth if _plain(c.depth, dt, (1,)) or _plain(c.depth, dt, ()) else c.depth.detach().reshape(-1).contiguous()
+        inc = c.inc_angles
+        if inc is not None and not (_plain(inc, dt, (1,)) or _plain(inc, dt, ())):
+            inc = inc.detach().reshape(-1).to(dt).contiguous()
+        mm = c.mask
+        if mm is not None:
+            # bool storage is one 0/1 byte per element: reinterpret instead of converting
+            mm = mm.view(torch.uint8) if (mm.dtype == torch.bool and mm.is_contiguous()) else mm.detach().to(torch.uint8).contiguous()
         keep += [dirs, vps, depth, inc, mm]
         rows.append([vps.data_ptr(), dirs.data_ptr(), depth.data_ptr(), 0 if inc is None else inc.data_ptr(),
                      0 if mm is None else mm.data_ptr()])
@@ -65,6 +88,9 @@ def scan_table(clouds, dt):
     both = L.upload(rows + [[f, 0, 0, 0, 0] for f in first], torch.int64, dev)      # one copy for both tables
     tbl = both[:len(rows)]
     first_t = both[len(rows):, 0].contiguous()
+    if len(_scan_table_cache) >= 2:
+        _scan_table_cache.pop(next(iter(_scan_table_cache)))
+    _scan_table_cache[key] = (tbl, first_t, keep)
     return tbl, first_t, keep
 
 
