@@ -1,5 +1,5 @@
 """Summarise an .ncu-rep (captured with `ncu --set full --import-source on`) into a small markdown file under
-profiles/.  Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_step_kernels.md "title"
+profiles/.  Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_step_kernels.md "title" [traffic.json n_points]
 """
 import csv
 import io
@@ -79,6 +79,24 @@ def main():
             pass
     open(dst, 'w').write('\n'.join(lines))
     print('wrote', dst)
+    if len(sys.argv) > 5:
+        # per-launch DRAM traffic by C-ABI entry point -> profiles/traffic.json (bench.py fills roofline.traffic from it)
+        import json
+        entry = {'knn_thread_kernel': 'dc_knn', 'step_points_kernel': 'dc_step_points', 'step_forward_kernel': 'dc_step_forward',
+                 'step_backward_gather_kernel': 'dc_step_backward', 'step_backward_scatter_kernel': 'dc_step_backward_scatter',
+                 'step_chain_kernel': 'dc_step_chain'}
+        rd, wr, du = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('gpu__time_duration.sum')
+        scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        tscale = {'ns': 1e-9, 'us': 1e-6, 'ms': 1e-3, 's': 1.0}
+        out = {'source': '%s (ncu --set full, timed NVTX region of bench.py)' % rep.split('/')[-1], 'n_points': int(sys.argv[5]), 'kernels': {}}
+        for r in data:
+            base = r[name_i].split('(')[0].replace('void ', '').split('<')[0].strip()
+            if base in entry and entry[base] not in out['kernels']:
+                out['kernels'][entry[base]] = {'kernel': r[name_i].split('(')[0], 'dram_read_bytes': float(r[rd]) * scale[units[rd]],
+                                               'dram_write_bytes': float(r[wr]) * scale[units[wr]],
+                                               'duration_s_under_ncu': float(r[du]) * tscale[units[du]]}
+        json.dump(out, open(sys.argv[4], 'w'), indent=1)
+        print('wrote', sys.argv[4])
 
 
 if __name__ == '__main__':
