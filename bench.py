@@ -200,7 +200,9 @@ def run_ours(args):
         """spatial slabs + halo exchange over NCCL (one-time setup of a training run; part of e2e only)"""
         if world == 1:
             return cl, None
-        wp = [c.transform(poses[s]).to_points() for c, s in zip(cl, my_scans)]
+        # points of all local scans in the initial map frame: one batched kernel (dc_world_points_batched)
+        from depth_correction_b200.preproc import _initial_map_points
+        wp = _initial_map_points(dc.global_cloud(clouds=cl, poses=poses[my_scans]))
         part = dc.SlabPartitioner()
         axis, bounds = part.plan(wp)
         loc = part.exchange(cl, my_scans, wp, axis, bounds, halo=NN_R)
@@ -328,11 +330,20 @@ def run_ours(args):
     e2e_step()
     sync()
     n_e2e = max(2, min(args.steps, 3))
+    eprof = None
+    if os.environ.get('DC_BENCH_E2E_CPROFILE') and rank == 0:
+        import cProfile
+        eprof = cProfile.Profile()
+        eprof.enable()
     w0 = time.perf_counter()
     for _ in range(n_e2e):
         out = e2e_step()
     sync()
     e2e_s = (time.perf_counter() - w0) / n_e2e
+    if eprof is not None:
+        import pstats
+        eprof.disable()
+        pstats.Stats(eprof, stream=sys.stderr).sort_stats('cumulative').print_stats(35)
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

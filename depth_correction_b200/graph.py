@@ -16,7 +16,7 @@ from . import _lib as L
 
 __all__ = ['SortedMap', 'Graph', 'search']
 
-DENSE_TABLE_MAX_CELLS = 1 << 27
+DENSE_TABLE_MAX_CELLS = 1 << 30      # 4 GB of int32 cell starts at most (a 100 M point, 760 m corridor needs 3e8 cells)
 
 
 def _as_points(x):

@@ -24,7 +24,7 @@ import torch.distributed as dist
 
 from .depth_cloud import DepthCloud
 
-__all__ = ['LocalMap', 'SlabPartitioner', 'reduce_step']
+__all__ = ['LocalMap', 'SlabPartitioner', 'distributed_quantile', 'reduce_step', 'sharded_inlier_sum_count']
 
 N_HIST_BINS = 1 << 14
 
@@ -66,11 +66,15 @@ class SlabPartitioner(object):
 
     # ---- 2. slab boundaries -----------------------------------------------------------------------
     def plan(self, world_points):
-        """world_points: list of [n,3] tensors (this rank's scans in the initial map frame).
-        Returns (axis, boundaries float64 [G+1]) with boundaries[0] = -inf, boundaries[G] = +inf."""
-        dev = world_points[0].device if world_points else torch.device('cpu')
-        pts = torch.cat([p.detach().reshape(-1, 3) for p in world_points]).double() if world_points else \
-            torch.zeros((0, 3), dtype=torch.float64, device=dev)
+        """world_points: list of [n,3] tensors (this rank's scans in the initial map frame) or one concatenated
+        [N,3] tensor.  Returns (axis, boundaries float64 [G+1]) with boundaries[0] = -inf, boundaries[G] = +inf."""
+        if isinstance(world_points, torch.Tensor):
+            dev = world_points.device
+            pts = world_points.detach().reshape(-1, 3).double()
+        else:
+            dev = world_points[0].device if world_points else torch.device('cpu')
+            pts = torch.cat([p.detach().reshape(-1, 3) for p in world_points]).double() if world_points else \
+                torch.zeros((0, 3), dtype=torch.float64, device=dev)
         big = 1e300
         lo = pts.min(dim=0).values if len(pts) else torch.full((3,), big, dtype=torch.float64, device=dev)
         hi = pts.max(dim=0).values if len(pts) else torch.full((3,), -big, dtype=torch.float64, device=dev)
@@ -95,24 +99,40 @@ class SlabPartitioner(object):
         """Route point records to slab owners (+ halo copies).
 
         clouds: this rank's per-scan DepthClouds (vps, dirs, depth, inc_angles, mask); scan_ids: their global
-        ids; world_points: their points in the initial map frame.  Returns a LocalMap.
+        ids; world_points: their points in the initial map frame (list per scan, or one concatenated [N,3] tensor).
+        Returns a LocalMap.
         """
-        assert len(clouds) == len(scan_ids) == len(world_points)
+        assert len(clouds) == len(scan_ids)
         G = self.world
         dev = clouds[0].depth.device if clouds else torch.device('cpu')
         dt = clouds[0].depth.dtype if clouds else torch.float32
-        frecs, irecs, coords = [], [], []
-        for c, sid, wp in zip(clouds, scan_ids, world_points):
-            n = len(c)
-            inc = c.inc_angles if c.inc_angles is not None else torch.zeros((n, 1), dtype=dt, device=dev)
-            mask = c.mask if c.mask is not None else torch.ones(n, dtype=torch.bool, device=dev)
-            frecs.append(torch.cat([c.vps.expand(n, 3), c.dirs, c.depth, inc.to(dt)], dim=1))
-            irecs.append(torch.stack([torch.full((n,), int(sid), dtype=torch.int64, device=dev),
-                                      torch.arange(n, dtype=torch.int64, device=dev), mask.long()], dim=1))
-            coords.append(wp.detach().reshape(-1, 3)[:, axis].double())
-        frec = torch.cat(frecs) if frecs else torch.zeros((0, 8), dtype=dt, device=dev)
-        irec = torch.cat(irecs) if irecs else torch.zeros((0, 3), dtype=torch.int64, device=dev)
-        x = torch.cat(coords) if coords else torch.zeros(0, dtype=torch.float64, device=dev)
+        sizes = [len(c) for c in clouds]
+        n = sum(sizes)
+        # one batched op per field (a training run calls this once, but with hundreds of scans per rank a loop of
+        # small per-scan ops costs tens of milliseconds of launches)
+        if clouds:
+            vps = torch.cat([c.vps.expand(m, 3) for c, m in zip(clouds, sizes)])
+            dirs = torch.cat([c.dirs for c in clouds])
+            depth = torch.cat([c.depth.reshape(-1, 1) for c in clouds])
+            inc = torch.cat([c.inc_angles.reshape(-1, 1).to(dt) if c.inc_angles is not None
+                             else torch.zeros((m, 1), dtype=dt, device=dev) for c, m in zip(clouds, sizes)])
+            frec = torch.cat([vps.to(dt), dirs, depth, inc], dim=1)
+            mask = torch.cat([c.mask if c.mask is not None else torch.ones(m, dtype=torch.bool, device=dev)
+                              for c, m in zip(clouds, sizes)])
+            sz = torch.as_tensor(sizes, dtype=torch.int64, device=dev)
+            first = torch.cumsum(sz, 0) - sz
+            sid = torch.repeat_interleave(torch.as_tensor([int(s) for s in scan_ids], dtype=torch.int64, device=dev), sz)
+            row = torch.arange(n, dtype=torch.int64, device=dev) - torch.repeat_interleave(first, sz)
+            irec = torch.stack([sid, row, mask.long()], dim=1)
+            if isinstance(world_points, torch.Tensor):
+                x = world_points.detach().reshape(-1, 3)[:, axis].double()
+            else:
+                x = torch.cat([wp.detach().reshape(-1, 3)[:, axis] for wp in world_points]).double()
+            assert x.numel() == n
+        else:
+            frec = torch.zeros((0, 8), dtype=dt, device=dev)
+            irec = torch.zeros((0, 3), dtype=torch.int64, device=dev)
+            x = torch.zeros(0, dtype=torch.float64, device=dev)
         owner = torch.bucketize(x, boundaries[1:-1].to(dev), right=True)          # slab g: b[g] <= x < b[g+1]
         send_f, send_i, send_counts = [], [], []
         for g in range(G):
@@ -135,13 +155,16 @@ class SlabPartitioner(object):
         key = ri[:, 0] * (int(ri[:, 1].max().item()) + 1 if len(ri) else 1) + ri[:, 1]
         order = torch.argsort(key, stable=True)
         rf, ri = rf[order], ri[order]
-        sids, sizes = torch.unique_consecutive(ri[:, 0], return_counts=True)
+        sids, sizes_l = torch.unique_consecutive(ri[:, 0], return_counts=True)
+        # split the record matrix into per-field arrays once; the per-scan clouds are contiguous row slices of them
+        f_vps, f_dirs = rf[:, 0:3].contiguous(), rf[:, 3:6].contiguous()
+        f_depth, f_inc = rf[:, 6:7].contiguous(), rf[:, 7:8].contiguous()
+        f_mask = ri[:, 2].bool()
         local_clouds, first = [], 0
-        for n in sizes.tolist():
-            f = rf[first:first + n]
-            local_clouds.append(DepthCloud(vps=f[:, 0:3].contiguous(), dirs=f[:, 3:6].contiguous(), depth=f[:, 6:7].contiguous(),
-                                           inc_angles=f[:, 7:8].contiguous(), mask=ri[first:first + n, 2].bool()))
-            first += n
+        for m in sizes_l.tolist():
+            local_clouds.append(DepthCloud(vps=f_vps[first:first + m], dirs=f_dirs[first:first + m], depth=f_depth[first:first + m],
+                                           inc_angles=f_inc[first:first + m], mask=f_mask[first:first + m]))
+            first += m
         return LocalMap(local_clouds, sids, ri[:, 3].bool(), ri[:, :2].contiguous(), axis,
                         (float(boundaries[self.rank]), float(boundaries[self.rank + 1])))
 
@@ -164,3 +187,91 @@ def reduce_step(sum_count, params, group=None):
         p.grad = (buf[off:off + n] / count).reshape(g.shape).to(g.dtype)
         off += n
     return buf[0] / count
+
+
+def distributed_quantile(x, q, group=None, max_gather=4096):
+    """torch.quantile(cat_over_ranks(x), q) (linear interpolation, 1-D, NaN-free) without gathering the data:
+    every rank holds a shard `x`; two all-reduced 2^16-bin histogram rounds narrow the two order statistics the
+    result interpolates between down to a few candidates, which are then gathered and sorted.  Works on any
+    device / backend (the CPU tests run it over gloo).  This is the global inlier threshold of
+    min_eigval_loss / trace_loss (`inlier_ratio < 1`, loss.py:256-267) for a map sharded over GPUs."""
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    x = x.detach().reshape(-1).double()
+    dev = x.device
+
+    def allsum(t):
+        if multi:
+            dist.all_reduce(t, group=group)
+        return t
+
+    n = int(allsum(torch.tensor([x.numel()], dtype=torch.float64, device=dev)).item())
+    assert n > 0, 'quantile of an empty set'
+    rank = q * (n - 1)
+    k_lo = int(rank)
+    k_hi = min(k_lo + 1, n - 1) if rank > k_lo else k_lo
+    big = torch.tensor([float('inf')], dtype=torch.float64, device=dev)
+    lo = torch.min(x) if x.numel() else big[0]
+    hi = torch.max(x) if x.numel() else -big[0]
+    mm = torch.stack([-lo, hi])
+    if multi:
+        dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
+    lo, hi = -mm[0], mm[1]
+
+    def order_statistic(k):
+        """k-th smallest (0-based) of the union."""
+        a, b, below = lo.clone(), hi.clone(), 0           # the statistic lies in [a, b]; `below` values are < a
+        cur = x
+        for _ in range(6):
+            cnt = int(allsum(torch.tensor([cur.numel()], dtype=torch.float64, device=dev)).item())
+            if cnt <= max_gather or not (b > a):
+                break
+            nb = 1 << 16
+            width = (b - a) / nb
+            bins = ((cur - a) / width).long().clamp_(0, nb - 1)
+            hist = allsum(torch.bincount(bins, minlength=nb).double())
+            cum = torch.cumsum(hist, 0)
+            bsel = int(torch.searchsorted(cum, torch.tensor([float(k - below) + 0.5], dtype=torch.float64, device=dev)).item())
+            below += int(cum[bsel - 1].item()) if bsel > 0 else 0
+            cur = cur[bins == bsel]
+            a, b = a + bsel * width, a + (bsel + 1) * width
+        # gather the remaining candidates (equal sizes via padding with +inf)
+        m = torch.tensor([cur.numel()], dtype=torch.int64, device=dev)
+        if multi:
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+        m = int(m.item())
+        pad = torch.full((m,), float('inf'), dtype=torch.float64, device=dev)
+        pad[:cur.numel()] = cur
+        if multi:
+            parts = [torch.empty_like(pad) for _ in range(dist.get_world_size(group))]
+            dist.all_gather(parts, pad, group=group)
+            pad = torch.cat(parts)
+        return torch.sort(pad).values[k - below]
+
+    v_lo = order_statistic(k_lo)
+    v_hi = order_statistic(k_hi) if k_hi != k_lo else v_lo
+    return torch.lerp(v_lo, v_hi, rank - k_lo)
+
+
+def sharded_inlier_sum_count(cloud, owned, inlier_ratio=1.0, inlier_loss_mult=1.0, inlier_max_loss=None,
+                             loss='min_eigval_loss', sqrt=False, normalization=False, group=None):
+    """Multi-GPU form of the inlier-selecting losses (loss.py:256-293 / 332-369): the quantile of the raw per-point
+    loss is taken over the OWNED points of all ranks (distributed_quantile), points above the threshold are dropped,
+    and the local (sum, count) of the survivors is returned with autograd history for `reduce_step`."""
+    from . import _lib as L
+    from .fused import fused_loss
+    from .loss import _kind_flags, min_eigval_loss, trace_loss
+    loss_fun = trace_loss if loss in ('trace_loss', trace_loss) else min_eigval_loss
+    kind, flags = _kind_flags(loss_fun, dict(sqrt=False, normalization=normalization))
+    raw = fused_loss(cloud.step_state(), cloud._model, cloud.poses_tensor(), kind, flags | L.FLAG_RAW, mask=None)[owned]
+    thr = None
+    if inlier_ratio < 1.0:
+        thr = inlier_loss_mult * distributed_quantile(raw, inlier_ratio, group=group)
+    if inlier_max_loss is not None:
+        cap = torch.as_tensor(inlier_max_loss, dtype=raw.dtype, device=raw.device)
+        thr = cap if thr is None else torch.min(cap, thr)
+    if thr is not None:
+        raw = raw[raw.detach() <= thr]
+    val = torch.relu(raw)
+    if sqrt:
+        val = torch.sqrt(val)
+    return torch.stack([val.sum(), torch.as_tensor(float(val.numel()), dtype=val.dtype, device=val.device)])

@@ -30,7 +30,7 @@ def main():
         poses = torch.as_tensor(poses_np, device=dev)
         d0 = torch.as_tensor(np.random.default_rng(0).normal(0, 0.005, (S, 6)), device=dev)
 
-        def run(local_clouds, local):
+        def run(local_clouds, local, inlier_ratio=1.0):
             model = dc.ScaledPolynomial(w=[0.003, -0.002], exponent=[2, 4], device=dev)
             deltas = d0.clone().requires_grad_(True)
             sel = None if local is None else local.scan_ids
@@ -40,8 +40,12 @@ def main():
                 cloud=dc.global_cloud(clouds=local_clouds, model=model, poses=pc if sel is None else pc[sel]),
                 neighborhoods=ns, cfg=cfg)
             if local is None:
-                loss, _ = dc.trace_loss(feats, sqrt=True)
+                loss, _ = dc.trace_loss(feats, sqrt=True, inlier_ratio=inlier_ratio)
                 loss.backward()
+            elif inlier_ratio < 1.0:
+                # global inlier threshold over the owned points of all ranks (distributed quantile)
+                sc = dc.sharded_inlier_sum_count(feats, local.owned, inlier_ratio=inlier_ratio, loss='trace_loss', sqrt=True)
+                loss = dc.reduce_step(sc, [model.w, deltas])
             else:
                 sc = dc.fused_sum_count(feats, mask=local.owned, loss='trace_loss', sqrt=True)
                 loss = dc.reduce_step(sc, [model.w, deltas])
@@ -58,6 +62,12 @@ def main():
             err = (a - b).abs().max().item() / b.abs().max().item()
             results['%s k=%d' % (name, k)] = err
             assert err < 1e-9, (name, k, err)
+        ref_in = run(clouds, None, inlier_ratio=0.7)
+        got_in = run(local.clouds, local, inlier_ratio=0.7)
+        for a, b, name in zip(got_in, ref_in, ('loss', 'w_grad', 'pose_grad')):
+            err = (a - b).abs().max().item() / b.abs().max().item()
+            results['inlier %s k=%d' % (name, k)] = err
+            assert err < 1e-9, ('inlier', name, k, err)
     if rank == 0:
         print('MULTIGPU_OK', results)
     dist.destroy_process_group()

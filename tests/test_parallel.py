@@ -150,3 +150,47 @@ def test_single_process_partition_is_identity():
     local = part.exchange(clouds, list(range(len(clouds))), world_pts, axis, bounds, halo=R)
     assert local.owned.all() and len(local) == sum(len(c) for c in clouds)
     assert all(torch.equal(a.depth, b.depth) for a, b in zip(local.clouds, clouds))
+
+
+def _quantile_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import depth_correction_b200 as dc
+        rng = np.random.default_rng(5)
+        cases = {
+            'lognormal': rng.lognormal(-9.0, 2.0, 300001),                 # loss-like: spans many decades
+            'ties': np.round(rng.random(50000), 2),                        # 101 distinct values
+            'tiny': rng.random(7),
+            'constant': np.full(1000, 0.25),
+            'outlier': np.concatenate([rng.random(20000) * 1e-6, [1e9]]),  # one value stretches the range
+        }
+        for name, full in cases.items():
+            shard = torch.as_tensor(full[rank::world] if name != 'tiny' else (full if rank == 0 else full[:0]))
+            for q in (0.0, 0.3, 0.5, 0.9, 0.999, 1.0):
+                ours = dc.distributed_quantile(shard, q, max_gather=64).item()
+                ref = torch.quantile(torch.as_tensor(full), q).item()
+                assert ours == ref, (name, q, ours, ref)
+        out.put((rank, 'ok'))
+    except Exception as ex:
+        import traceback
+        out.put((rank, 'fail', traceback.format_exc(), repr(ex)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_quantile_equals_torch_quantile_world2():
+    """The global inlier threshold of a sharded map (inlier_ratio < 1, loss.py:256-267): bit-equal to
+    torch.quantile of the concatenated shards, without gathering them."""
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_quantile_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for r in results:
+        assert r[1] == 'ok', r[2]
