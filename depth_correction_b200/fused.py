@@ -44,7 +44,11 @@ def model_kind_of(model):
     raise NotImplementedError('fused step supports Polynomial / ScaledPolynomial models, got %s' % name)
 
 
-_scan_table_cache = {}      # key -> (tbl, first, keep); two entries (the search and the step of one iteration use the same scans)
+# key -> (tbl, first): two entries (the search and the step of one iteration use the same scans).  Only tables that
+# point straight at the caller's tensors are cached, and the cache holds NO reference to them: the key is made of the
+# very addresses and lengths the table contains, so a hit is valid whatever happened to the objects in between
+# (a cache that kept the tensors alive made every new set of scans allocate fresh device memory: 16 -> 60 ms e2e).
+_scan_table_cache = {}
 
 
 def _plain(t, dt, shape_tail):
@@ -57,30 +61,39 @@ def scan_table(clouds, dt):
     inc_angles, model mask} (0 = absent), first int64 [S+1], keep-alive list of the tensors the table points to).
     Host cost matters here (it sits in front of the search): tensors that are already in kernel layout are used as
     they are, and the table of an unchanged list of scans is reused."""
-    key = (dt,) + tuple((id(c), c.depth.data_ptr(), c.dirs.data_ptr(), c.vps.data_ptr(),
+    key = (dt,) + tuple((len(c), c.depth.data_ptr(), c.dirs.data_ptr(), c.vps.data_ptr(), tuple(c.vps.shape),
                          0 if c.inc_angles is None else c.inc_angles.data_ptr(),
-                         0 if c.mask is None else (c.mask.data_ptr(), c.mask._version)) for c in clouds)
+                         0 if c.mask is None else c.mask.data_ptr()) for c in clouds)
     hit = _scan_table_cache.get(key)
     if hit is not None:
-        return hit
+        return hit[0], hit[1], []
     rows, keep, first = [], [], [0]
+    all_plain = True
     dev = clouds[0].depth.device
     for c in clouds:
         cnt = len(c)
         assert c.depth.dtype == dt and c.dirs.is_cuda
-        dirs = c.dirs if _plain(c.dirs, dt, (3,)) else c.dirs.detach().reshape(-1, 3).contiguous()
+        dirs = c.dirs
+        if not _plain(dirs, dt, (3,)):
+            dirs, all_plain = dirs.detach().reshape(-1, 3).contiguous(), False
         vps = c.vps
         if not (_plain(vps, dt, (3,)) and vps.shape[0] == cnt):
             vps = vps.detach()
             vps = vps.to(dt).contiguous() if vps.shape[0] == cnt else vps.to(dt).expand(cnt, 3).contiguous()
-        depth = c.depth if _plain(c.depth, dt, (1,)) or _plain(c.depth, dt, ()) else c.depth.detach().reshape(-1).contiguous()
+            all_plain = False
+        depth = c.depth
+        if not (_plain(depth, dt, (1,)) or _plain(depth, dt, ())):
+            depth, all_plain = depth.detach().reshape(-1).contiguous(), False
         inc = c.inc_angles
         if inc is not None and not (_plain(inc, dt, (1,)) or _plain(inc, dt, ())):
-            inc = inc.detach().reshape(-1).to(dt).contiguous()
+            inc, all_plain = inc.detach().reshape(-1).to(dt).contiguous(), False
         mm = c.mask
         if mm is not None:
             # bool storage is one 0/1 byte per element: reinterpret instead of converting
-            mm = mm.view(torch.uint8) if (mm.dtype == torch.bool and mm.is_contiguous()) else mm.detach().to(torch.uint8).contiguous()
+            if mm.dtype == torch.bool and mm.is_contiguous():
+                mm = mm.view(torch.uint8)
+            else:
+                mm, all_plain = mm.detach().to(torch.uint8).contiguous(), False
         keep += [dirs, vps, depth, inc, mm]
         rows.append([vps.data_ptr(), dirs.data_ptr(), depth.data_ptr(), 0 if inc is None else inc.data_ptr(),
                      0 if mm is None else mm.data_ptr()])
@@ -88,9 +101,10 @@ def scan_table(clouds, dt):
     both = L.upload(rows + [[f, 0, 0, 0, 0] for f in first], torch.int64, dev)      # one copy for both tables
     tbl = both[:len(rows)]
     first_t = both[len(rows):, 0].contiguous()
-    if len(_scan_table_cache) >= 2:
-        _scan_table_cache.pop(next(iter(_scan_table_cache)))
-    _scan_table_cache[key] = (tbl, first_t, keep)
+    if all_plain:
+        if len(_scan_table_cache) >= 2:
+            _scan_table_cache.pop(next(iter(_scan_table_cache)))
+        _scan_table_cache[key] = (tbl, first_t)
     return tbl, first_t, keep
 
 
