@@ -716,3 +716,37 @@ def test_scatter_f32_agrees_with_gather_form(dc, dev, monkeypatch):
     assert rel_err_norm(gw64, gwg) < 1e-11 and rel_err_norm(gd64, gdg) < 1e-11
     assert rel_err_norm(gw32, gwg) < 1e-6, rel_err_norm(gw32, gwg)
     assert rel_err_norm(gd32, gdg) < 1e-6, rel_err_norm(gd32, gdg)
+
+
+def test_knn_two_million_points_sampled_vs_ckdtree(dc, dev):
+    """Bench-shaped map at 2 M points (16 full-resolution scans): a random sample of 20 000 rows of the kNN graph
+    against cKDTree built on the whole map, plus size-independent properties of the full graph: every row holds k
+    distinct indices or is padded, the search is idempotent, and a radius graph is symmetric."""
+    from oracle import oracle
+    from depth_correction_b200.graph import search
+    from depth_correction_b200.synthetic import make_sequence
+    scans, poses, _ = make_sequence('corridor', n_scans=16, pattern='os0-128', seed=0)
+    pts = np.concatenate([s['points'].astype(np.float64) @ T[:3, :3].T + T[:3, 3] for s, T in zip(scans, poses)])
+    p = torch.as_tensor(pts, device=dev)
+    g = search(p, None, k=32, r=0.4)
+    nb = g.neighbors()
+    dist = g.distances()
+    rows = torch.as_tensor(np.random.default_rng(1).choice(len(pts), 20000, replace=False), device=dev)
+    d_ref, i_ref = oracle.nearest_neighbors(torch.as_tensor(pts), torch.as_tensor(pts[rows.cpu().numpy()]), k=32, r=0.4)
+    assert torch.equal(nb[rows].cpu(), i_ref)
+    assert torch.equal(dist[rows].cpu(), d_ref)
+    # properties of the whole graph
+    srt = nb.sort(dim=1).values
+    assert ((srt[:, 1:] != srt[:, :-1]) | (srt[:, 1:] < 0)).all()                   # no index twice in a row
+    assert (nb[:, 0] == torch.arange(len(pts), device=dev)).all()                    # nearest neighbour of a point is itself
+    assert (dist[:, 1:] >= dist[:, :-1]).all()                                       # rows sorted by distance
+    assert torch.equal(search(p, None, k=32, r=0.4).neighbors(), nb)                 # idempotent
+    sub = p[:400000]
+    gr = search(sub, None, r=0.03)
+    a = gr.neighbors()
+    i = torch.arange(len(sub), device=dev)[:, None].expand_as(a)[a >= 0]
+    j = a[a >= 0]
+    fwd = torch.stack([i, j], 1)
+    bwd = torch.stack([j, i], 1)
+    key = lambda e: (e[:, 0] * len(sub) + e[:, 1]).sort().values
+    assert torch.equal(key(fwd), key(bwd))                                           # j in N(i)  <=>  i in N(j)
