@@ -125,7 +125,7 @@ class SlabPartitioner(object):
             row = torch.arange(n, dtype=torch.int64, device=dev) - torch.repeat_interleave(first, sz)
             irec = torch.stack([sid, row, mask.long()], dim=1)
             if isinstance(world_points, torch.Tensor):
-                x = world_points.detach().reshape(-1, 3)[:, axis].double()
+                x = world_points.detach().reshape(-1, 3)[:, axis].double().contiguous()
             else:
                 x = torch.cat([wp.detach().reshape(-1, 3)[:, axis] for wp in world_points]).double()
             assert x.numel() == n
@@ -133,7 +133,7 @@ class SlabPartitioner(object):
             frec = torch.zeros((0, 8), dtype=dt, device=dev)
             irec = torch.zeros((0, 3), dtype=torch.int64, device=dev)
             x = torch.zeros(0, dtype=torch.float64, device=dev)
-        owner = torch.bucketize(x, boundaries[1:-1].to(dev), right=True)          # slab g: b[g] <= x < b[g+1]
+        owner = torch.bucketize(x, boundaries[1:-1].to(dev).contiguous(), right=True)          # slab g: b[g] <= x < b[g+1]
         send_f, send_i, send_counts = [], [], []
         for g in range(G):
             lo, hi = float(boundaries[g]), float(boundaries[g + 1])
