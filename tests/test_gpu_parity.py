@@ -750,3 +750,64 @@ def test_knn_two_million_points_sampled_vs_ckdtree(dc, dev):
     bwd = torch.stack([j, i], 1)
     key = lambda e: (e[:, 0] * len(sub) + e[:, 1]).sort().values
     assert torch.equal(key(fwd), key(bwd))                                           # j in N(i)  <=>  i in N(j)
+
+
+def _edge_scene(n_per_scan, seed):
+    """Two tiny scans of a noisy plane 3 m in front of the sensor (float32 values)."""
+    rng = np.random.default_rng(seed)
+    scans = []
+    for s in range(2):
+        y, z = rng.uniform(-0.5, 0.5, n_per_scan), rng.uniform(-0.5, 0.5, n_per_scan)
+        x = 3.0 + 0.3 * y + 0.01 * rng.standard_normal(n_per_scan)
+        scans.append(np.stack([x, y, z], 1).astype(np.float32))
+    poses = np.stack([np.eye(4), np.eye(4)])
+    poses[1, :3, 3] = [0.02, -0.01, 0.03]
+    return scans, poses
+
+
+@pytest.mark.parametrize('case', ['k1', 'tiny', 'mask_all_false', 'isolated'])
+def test_fused_step_edge_cases_vs_oracle(dc, dev, case):
+    """Edge cases of the fused step against the oracle: k = 1 (every neighbourhood is the point itself: zero
+    covariance through the Bessel clamp), a cloud smaller than one slice, a loss mask that keeps nothing (mean over
+    an empty set is NaN in the reference too), and points without any neighbour inside r."""
+    from oracle import oracle
+    n_per = 5 if case == 'tiny' else 300
+    scans_np, poses = _edge_scene(n_per, 3)
+    if case == 'isolated':
+        scans_np[1][:40] += np.float32(50.0) * (1 + np.arange(40, dtype=np.float32))[:, None]     # far from everything
+    kw = dict(k=1, r=None) if case == 'k1' else dict(k=None, r=0.25)
+    cfg = dc.Config(nn_k=kw['k'] or 0, nn_r=kw['r'], pose_correction=dc.PoseCorrection.pose)
+    rng = np.random.default_rng(8)
+    inc = [rng.uniform(0.1, 1.2, (len(s), 1)) for s in scans_np]
+    clouds, oscans = [], []
+    for s, a in zip(scans_np, inc):
+        c = dc.DepthCloud.from_points(torch.as_tensor(s.astype(np.float64), device=dev))
+        c.inc_angles = torch.as_tensor(a, device=dev)
+        clouds.append(c)
+        vps, dirs, depth = oracle.from_points(torch.as_tensor(s.astype(np.float64)))
+        oscans.append({'vps': vps, 'dirs': dirs, 'depth': depth, 'inc_angles': torch.as_tensor(a), 'mask': torch.ones(len(s), dtype=torch.bool)})
+    n = sum(len(s) for s in scans_np)
+    poses_t = torch.as_tensor(poses, device=dev)
+    deltas = torch.as_tensor(rng.normal(0, 1e-3, (2, 6)), device=dev).requires_grad_(True)
+    model = dc.ScaledPolynomial(w=[0.004, -0.003], exponent=[2, 4], device=dev)
+    ns = dc.establish_neighborhoods(clouds=clouds, poses=poses_t, cfg=cfg)
+    pc = torch.stack(dc.create_corrected_poses(poses_t, deltas, cfg))
+    feats = dc.compute_neighborhood_features(cloud=dc.global_cloud(clouds=clouds, model=model, poses=pc), neighborhoods=ns, cfg=cfg)
+    mask = torch.zeros(n, dtype=torch.bool, device=dev) if case == 'mask_all_false' else None
+    loss, _ = dc.min_eigval_loss(feats, mask=mask, normalization=True)
+    loss.backward()
+    pts0, _ = oracle.global_points(oscans, torch.as_tensor(poses))
+    _, nb = oracle.nearest_neighbors(pts0, k=kw['k'], r=kw['r'])
+    assert torch.equal(ns[0].cpu(), nb)
+    ref = oracle.map_consistency_step(oscans, torch.as_tensor(poses), nb, model.w.detach().cpu(), model.exponent.cpu(),
+                                      pose_deltas=deltas.detach().cpu(), loss_mask=None if mask is None else mask.cpu(),
+                                      loss='min_eigval_loss', normalization=True)
+    if case == 'mask_all_false':
+        assert torch.isnan(loss) and torch.isnan(ref['loss'])
+        return
+    assert abs(loss.item() - ref['loss'].item()) <= 1e-9 * abs(ref['loss'].item()) + 1e-18
+    if case == 'k1':
+        assert loss.item() == 0.0 and model.w.grad.abs().max() == 0 and deltas.grad.abs().max() == 0
+        return
+    assert rel_err_norm(model.w.grad.cpu().numpy(), ref['w_grad'].numpy()) < 1e-8
+    assert rel_err_norm(deltas.grad.cpu().numpy(), ref['pose_deltas_grad'].numpy()) < 1e-8
