@@ -811,3 +811,47 @@ def test_fused_step_edge_cases_vs_oracle(dc, dev, case):
         return
     assert rel_err_norm(model.w.grad.cpu().numpy(), ref['w_grad'].numpy()) < 1e-8
     assert rel_err_norm(deltas.grad.cpu().numpy(), ref['pose_deltas_grad'].numpy()) < 1e-8
+
+
+def test_fused_step_one_million_points_vs_oracle(dc, dev, monkeypatch):
+    """The fused step at map scale (9 full-resolution scans, 1.18 M points, float32 records) against the CPU oracle
+    (cKDTree + torch fp64 autograd on the same values): loss, dL/dw and dL/dpose for the deterministic fp64 gather form
+    and for the default form of large maps (float32 vector-reduction scatter)."""
+    from oracle import oracle
+    from depth_correction_b200.synthetic import make_sequence
+    scans_np, _, poses = make_sequence('corridor', n_scans=9, pattern='os0-128', seed=12)
+    rng = np.random.default_rng(2)
+    cfg = dc.Config(nn_k=16, nn_r=0.4, pose_correction=dc.PoseCorrection.pose)
+    clouds, oscans = [], []
+    for s in scans_np:
+        inc = rng.uniform(0.05, 1.3, (len(s['points']), 1)).astype(np.float32)
+        msk = rng.random(len(s['points'])) < 0.9
+        c = dc.DepthCloud.from_points(torch.as_tensor(s['points'], device=dev))
+        c.inc_angles = torch.as_tensor(inc, device=dev)
+        c.mask = torch.as_tensor(msk, device=dev)
+        clouds.append(c)
+        # the oracle consumes the float32 records the kernels see (dirs / depth as computed in float32), up-cast
+        oscans.append({'vps': c.vps.double().cpu(), 'dirs': c.dirs.double().cpu(), 'depth': c.depth.double().cpu(),
+                       'inc_angles': torch.as_tensor(inc.astype(np.float64)), 'mask': torch.as_tensor(msk)})
+    n = sum(len(c) for c in clouds)
+    assert n >= (1 << 20)
+    poses_t = torch.as_tensor(poses, device=dev)
+    d0 = torch.as_tensor(rng.normal(0, 2e-3, (len(clouds), 6)), device=dev)
+    ns = dc.establish_neighborhoods(clouds=clouds, poses=poses_t, cfg=cfg)
+    pts0, _ = oracle.global_points(oscans, torch.as_tensor(poses))
+    _, nb = oracle.nearest_neighbors(pts0, k=16, r=0.4)
+    assert torch.equal(ns[0].cpu(), nb)
+    ref = oracle.map_consistency_step(oscans, torch.as_tensor(poses), nb, torch.tensor([[0.004, -0.003]], dtype=torch.float64),
+                                      torch.tensor([[2.0, 4.0]], dtype=torch.float64), pose_deltas=d0.cpu(),
+                                      loss='min_eigval_loss', normalization=True)
+    for form, tol in (('gather', 1e-9), ('auto', 1e-6)):
+        monkeypatch.setenv('DC_BACKWARD', form)
+        model = dc.ScaledPolynomial(w=[0.004, -0.003], exponent=[2, 4], device=dev)
+        deltas = d0.clone().requires_grad_(True)
+        pc = torch.stack(dc.create_corrected_poses(poses_t, deltas, cfg))
+        feats = dc.compute_neighborhood_features(cloud=dc.global_cloud(clouds=clouds, model=model, poses=pc), neighborhoods=ns, cfg=cfg)
+        loss, _ = dc.min_eigval_loss(feats, normalization=True)
+        loss.backward()
+        assert abs(loss.item() - ref['loss'].item()) <= 1e-10 * abs(ref['loss'].item()), form
+        assert rel_err_norm(model.w.grad.cpu().numpy(), ref['w_grad'].numpy()) < tol, (form, rel_err_norm(model.w.grad.cpu().numpy(), ref['w_grad'].numpy()))
+        assert rel_err_norm(deltas.grad.cpu().numpy(), ref['pose_deltas_grad'].numpy()) < tol, form
