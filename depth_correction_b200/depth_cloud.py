@@ -14,7 +14,7 @@ graph, so a training loop that never reads them never pays for the padded int64 
 ROS / open3d / matplotlib helpers of the reference (visualisation, meshes, messages) are out of scope.
 """
 import numpy as np
-from numpy.lib.recfunctions import merge_arrays, structured_to_unstructured, unstructured_to_structured
+from numpy.lib.recfunctions import structured_to_unstructured
 import torch
 
 from .nearest_neighbors import ball_angle_to_distance, nearest_neighbors
@@ -370,21 +370,32 @@ class DepthCloud(object):
 
     # ---- I/O ----------------------------------------------------------------------------------
     def to_structured_array(self, colors=None):
-        def part(x, names, dtype=np.float32):
-            return unstructured_to_structured(np.asarray(x.detach().cpu().numpy(), dtype=dtype), names=names)
-        parts = [part(self.get_points(), ['x', 'y', 'z']),
-                 part(self.vps.expand(self.size(), 3), ['vp_%s' % f for f in 'xyz'])]
+        """depth_cloud.py:508-533: x, y, z, vp_*[, normal_*, inc_angle, loss, mask, r, g, b] (float32; mask uint8).
+        Built column by column (numpy.lib.recfunctions.merge_arrays, which the reference uses, cannot merge an
+        unsigned field in numpy >= 2: its default fill value -1 overflows uint8)."""
+        cols = []
+
+        def add(x, names, dtype=np.float32):
+            a = np.asarray(x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x, dtype=dtype).reshape(self.size(), -1)
+            assert a.shape[1] == len(names)
+            cols.extend((name, dtype, a[:, i]) for i, name in enumerate(names))
+
+        add(self.get_points(), ['x', 'y', 'z'])
+        add(self.vps.expand(self.size(), 3), ['vp_%s' % f for f in 'xyz'])
         if self.normals is not None:
-            parts.append(part(self.normals, ['normal_%s' % f for f in 'xyz']))
+            add(self.normals, ['normal_%s' % f for f in 'xyz'])
         if self.inc_angles is not None:
-            parts.append(part(self.inc_angles, ['inc_angle']))
+            add(self.inc_angles, ['inc_angle'])
         if self.loss is not None:
-            parts.append(part(self.loss.reshape(-1, 1), ['loss']))
+            add(self.loss, ['loss'])
         if self.mask is not None:
-            parts.append(part(self.mask.reshape(-1, 1), ['mask'], np.uint8))
+            add(self.mask, ['mask'], np.uint8)
         if colors is not None:
-            parts.append(unstructured_to_structured(np.asarray(colors, dtype=np.float32), names=['r', 'g', 'b']))
-        return merge_arrays(parts, flatten=True)
+            add(colors, ['r', 'g', 'b'])
+        out = np.empty(self.size(), dtype=[(name, dtype) for name, dtype, _ in cols])
+        for name, _, values in cols:
+            out[name] = values
+        return out
 
     @staticmethod
     def concatenate(clouds, fields=None, dependent=False):

@@ -118,3 +118,38 @@ def test_hot_path_refuses_cpu_tensors():
     c.update_points()
     with pytest.raises(RuntimeError):
         c.update_neighbors(r=0.5)
+
+
+def test_structured_array_round_trip_matches_reference():
+    """DepthCloud <-> structured array (x, y, z, vp_*, normal_*, inc_angle, loss, mask; depth_cloud.py:508-533,
+    577-590): field names, dtypes and values; live against the reference when its tree is present."""
+    import depth_correction_b200 as dc
+    from numpy.lib.recfunctions import unstructured_to_structured
+    from oracle import ref_shim
+    rng = np.random.default_rng(3)
+    n = 50
+    cols = np.concatenate([rng.normal(0, 5, (n, 3)), rng.normal(0, 0.1, (n, 3)), rng.normal(0, 1, (n, 3))], 1).astype(np.float32)
+    cols[:, 6:9] /= np.linalg.norm(cols[:, 6:9], axis=1, keepdims=True)
+    arr = unstructured_to_structured(cols, names=['x', 'y', 'z', 'vp_x', 'vp_y', 'vp_z', 'normal_x', 'normal_y', 'normal_z'])
+    cloud = dc.DepthCloud.from_structured_array(arr)
+    assert torch.allclose(cloud.to_points(), torch.as_tensor(cols[:, :3]), atol=1e-5)
+    assert torch.equal(cloud.vps, torch.as_tensor(cols[:, 3:6])) and torch.equal(cloud.normals, torch.as_tensor(cols[:, 6:9]))
+    cloud.inc_angles = torch.as_tensor(rng.uniform(0, 1.5, (n, 1)).astype(np.float32))
+    cloud.loss = torch.as_tensor(rng.random(n).astype(np.float32))
+    cloud.mask = torch.as_tensor(rng.random(n) < 0.5)
+    out = cloud.to_structured_array()
+    assert out.dtype.names == ('x', 'y', 'z', 'vp_x', 'vp_y', 'vp_z', 'normal_x', 'normal_y', 'normal_z', 'inc_angle', 'loss', 'mask')
+    assert out['mask'].dtype == np.uint8 and out['x'].dtype == np.float32
+    assert np.allclose(np.stack([out[f] for f in ('x', 'y', 'z')], 1), cols[:, :3], atol=1e-5)
+    assert np.array_equal(out['inc_angle'], cloud.inc_angles.numpy()[:, 0]) and np.array_equal(out['mask'], cloud.mask.numpy().astype(np.uint8))
+    if ref_shim.available():
+        ref = ref_shim.load()
+        rc = ref.DepthCloud.from_structured_array(arr)
+        assert torch.allclose(rc.depth, cloud.depth) and torch.allclose(rc.dirs, cloud.dirs) and torch.equal(rc.vps, cloud.vps)
+        rc.inc_angles = cloud.inc_angles
+        rc.loss = cloud.loss[:, None]
+        # (the reference's merge_arrays cannot take the uint8 mask field under numpy >= 2: compared without it)
+        ro = rc.to_structured_array()
+        assert ro.dtype.names == tuple(f for f in out.dtype.names if f != 'mask')
+        for f in ro.dtype.names:
+            assert ro[f].dtype == out[f].dtype and np.allclose(ro[f], out[f], atol=1e-6), f
