@@ -855,3 +855,42 @@ def test_fused_step_one_million_points_vs_oracle(dc, dev, monkeypatch):
         assert abs(loss.item() - ref['loss'].item()) <= 1e-10 * abs(ref['loss'].item()), form
         assert rel_err_norm(model.w.grad.cpu().numpy(), ref['w_grad'].numpy()) < tol, (form, rel_err_norm(model.w.grad.cpu().numpy(), ref['w_grad'].numpy()))
         assert rel_err_norm(deltas.grad.cpu().numpy(), ref['pose_deltas_grad'].numpy()) < tol, form
+
+
+def test_container_and_pipeline_helpers(dc, dev):
+    """Smaller pieces of the reference API that the loops above do not touch directly: pose parametrisation round
+    trip, filtered_cloud (depth + seeded voxel filter, preproc.py:25-32) against the oracle, slicing / concatenation
+    with neighbour index shifting, neighbour collection."""
+    from oracle import oracle
+    from depth_correction_b200.synthetic import make_sequence
+    rng = np.random.default_rng(4)
+    xyzaa = torch.as_tensor(np.concatenate([rng.normal(0, 1, (12, 3)), rng.normal(0, 0.7, (12, 3))], 1), device=dev)
+    back = dc.matrix_to_xyz_axis_angle(dc.xyz_axis_angle_to_matrix(xyzaa))
+    assert torch.allclose(back, xyzaa, atol=1e-12)
+    # filtered_cloud == filter_depth then filter_grid(keep='random', rng = default_rng(cfg.random_seed))
+    scans, _, _ = make_sequence('corridor', n_scans=1, pattern='os0-32', seed=13)
+    pts = scans[0]['points']
+    cfg = dc.Config(min_depth=2.0, max_depth=10.0, grid_res=0.3, random_seed=99)
+    out = dc.filtered_cloud(dc.DepthCloud.from_points(torch.as_tensor(pts, device=dev)), cfg)
+    depth = np.linalg.norm(pts.astype(np.float32), axis=1)
+    kept = np.nonzero((depth >= np.float32(2.0)) & (depth <= np.float32(10.0)))[0]
+    # the voxel filter sees the points rebuilt from (vps, dirs, depth) in float32, like the reference
+    c_ref = dc.DepthCloud.from_points(torch.as_tensor(pts[kept], device=dev))
+    ind = oracle.filter_grid(c_ref.to_points().cpu().numpy(), np.float32(0.3), keep='random', rng=np.random.default_rng(99))
+    assert len(out) == len(ind)
+    assert torch.equal(out.to_points().cpu(), c_ref.to_points().cpu()[torch.as_tensor(ind)])
+    # slicing, concatenation, neighbour collection
+    a = dc.DepthCloud.from_points(torch.as_tensor(pts[:500], device=dev))
+    b = dc.DepthCloud.from_points(torch.as_tensor(pts[500:900], device=dev))
+    a.update_all(r=0.5)
+    b.update_all(r=0.5)
+    both = a + b
+    assert len(both) == 900 and both.neighbors.shape[0] == 900
+    nb_b = both.neighbors[500:]
+    assert torch.equal(nb_b[nb_b >= 0] - 500, b.neighbors[b.neighbors >= 0]) and (both.neighbors[:500][:, :a.neighbors.shape[1]] == a.neighbors).all()
+    sel = torch.arange(10, 20, device=dev)
+    idx = a.collect_neighbors(sel)
+    expect = torch.unique(a.neighbors[sel][a.neighbors[sel] >= 0])
+    assert torch.equal(idx, expect) and len(a.filter_with_neighbors(sel)) == len(expect)
+    sub = a[torch.arange(0, 500, 7, device=dev)]
+    assert len(sub) == 72 and sub.neighbors is None and sub.eigvals.shape == (72, 3)
