@@ -17,33 +17,33 @@ def timing(f):
 
 
 def covs(x, obs_axis=-2, var_axis=-1, center=True, correction=True, weights=None):
-    """Covariance matrices from samples along `obs_axis` (generic utility, utils.py:109-149).
-
-    Neighbourhood covariances of a DepthCloud do not go through this dense [.., K, 3, 3] form;
-    they use the gather kernel (ops.neighborhood_mean_cov)."""
+    """Covariance matrices of samples laid out along `obs_axis` with variables along `var_axis` (generic utility with
+    the semantics of utils.py:109-149: optional per-sample weights, Bessel correction on the weight sum, a floor of
+    1e-6 on a floating-point normaliser).  Neighbourhood covariances of a DepthCloud do not go through this dense
+    [.., K, 3, 3] form; they use the gather kernel (ops.neighborhood_mean_cov)."""
     assert isinstance(x, torch.Tensor)
     assert obs_axis != var_axis
     assert weights is None or isinstance(weights, torch.Tensor)
-    w = weights.sum(dim=obs_axis, keepdim=True) if weights is not None else x.shape[obs_axis]
-    if center:
-        xm = (weights * x).sum(dim=obs_axis, keepdim=True) / w if weights is not None else x.mean(dim=obs_axis, keepdim=True)
-        xc = x - xm
+    # bring the data to [..., observations, variables]
+    xs = x.movedim((obs_axis, var_axis), (-2, -1))
+    if weights is None:
+        norm = xs.shape[-2]
+        mean = xs.mean(dim=-2, keepdim=True)
     else:
-        xc = x
-    var_axis_2 = var_axis + 1 if var_axis >= 0 else var_axis - 1
-    xx = xc.unsqueeze(var_axis) * xc.unsqueeze(var_axis_2)
-    if weights is not None:
-        xx = weights.unsqueeze(var_axis) * xx
-    if obs_axis < var_axis and obs_axis < 0:
-        obs_axis -= 1
-    elif obs_axis > var_axis and obs_axis > 0:
-        obs_axis += 1
-    xx = xx.sum(dim=obs_axis)
+        ws = weights.movedim((obs_axis, var_axis), (-2, -1)) if weights.dim() == x.dim() else weights
+        norm = ws.sum(dim=-2, keepdim=True)
+        mean = (ws * xs).sum(dim=-2, keepdim=True) / norm
+        norm = norm.squeeze(-2).unsqueeze(-1) if norm.dim() >= 2 else norm
+    d = xs - mean if center else xs
+    if weights is None:
+        scatter = torch.einsum('...ki,...kj->...ij', d, d)
+    else:
+        scatter = torch.einsum('...ki,...kj->...ij', ws * d, d)
     if correction:
-        w = w - 1
-    if isinstance(w, torch.Tensor) and w.dtype.is_floating_point:
-        w = w.clamp(1e-6, None)
-    return xx / w
+        norm = norm - 1
+    if isinstance(norm, torch.Tensor) and norm.dtype.is_floating_point:
+        norm = norm.clamp(1e-6, None)
+    return scatter / norm
 
 
 def trace(x, dim1=-2, dim2=-1):
