@@ -119,11 +119,11 @@ class SlabPartitioner(object):
             frec = torch.cat([vps.to(dt), dirs, depth, inc], dim=1)
             mask = torch.cat([c.mask if c.mask is not None else torch.ones(m, dtype=torch.bool, device=dev)
                               for c, m in zip(clouds, sizes)])
-            sz = torch.as_tensor(sizes, dtype=torch.int64, device=dev)
+            sz = torch.as_tensor(sizes, dtype=torch.int64, device=dev)        # (record columns below are int32: half the traffic)
             first = torch.cumsum(sz, 0) - sz
             sid = torch.repeat_interleave(torch.as_tensor([int(s) for s in scan_ids], dtype=torch.int64, device=dev), sz)
             row = torch.arange(n, dtype=torch.int64, device=dev) - torch.repeat_interleave(first, sz)
-            irec = torch.stack([sid, row, mask.long()], dim=1)
+            irec = torch.stack([sid.int(), row.int(), mask.int()], dim=1)
             if isinstance(world_points, torch.Tensor):
                 x = world_points.detach().reshape(-1, 3)[:, axis].double().contiguous()
             else:
@@ -131,28 +131,34 @@ class SlabPartitioner(object):
             assert x.numel() == n
         else:
             frec = torch.zeros((0, 8), dtype=dt, device=dev)
-            irec = torch.zeros((0, 3), dtype=torch.int64, device=dev)
+            irec = torch.zeros((0, 3), dtype=torch.int32, device=dev)
             x = torch.zeros(0, dtype=torch.float64, device=dev)
-        owner = torch.bucketize(x, boundaries[1:-1].to(dev).contiguous(), right=True)          # slab g: b[g] <= x < b[g+1]
-        send_f, send_i, send_counts = [], [], []
-        for g in range(G):
-            lo, hi = float(boundaries[g]), float(boundaries[g + 1])
-            member = (x >= lo - halo) & (x < hi + halo)
-            sel = member.nonzero().squeeze(1)
-            send_f.append(frec[sel])
-            send_i.append(torch.cat([irec[sel], (owner[sel] == g).long()[:, None]], dim=1))
-            send_counts.append(int(sel.numel()))
-        counts = torch.tensor(send_counts, dtype=torch.int64, device=dev)
-        recv = torch.empty_like(counts)
+        inner = boundaries[1:-1].to(dev).contiguous()
+        owner = torch.bucketize(x, inner, right=True)                               # slab g: b[g] <= x < b[g+1]
+        # a point is sent to every slab within `halo` of it: g_min .. g_max (usually just its owner), i.e. the slabs
+        # with b[g] - halo <= x < b[g+1] + halo.  One stable sort by destination replaces a pass per destination.
+        g_max = torch.bucketize(x + halo, inner, right=True)
+        g_min = torch.bucketize(x - halo, inner, right=True)
+        copies = g_max - g_min + 1
+        src = torch.repeat_interleave(torch.arange(n, dtype=torch.int64, device=dev), copies)
+        start = torch.cumsum(copies, 0) - copies
+        dest = g_min[src] + (torch.arange(src.numel(), dtype=torch.int64, device=dev) - start[src])
+        by_dest = torch.argsort(dest, stable=True)                                  # keeps (scan, row) order inside a destination
+        src, dest = src[by_dest], dest[by_dest]
+        send_counts = torch.bincount(dest, minlength=G)
+        send_f = frec[src]
+        send_i = torch.cat([irec[src], (owner[src] == dest).to(irec.dtype)[:, None]], dim=1)
+        recv = torch.empty_like(send_counts)
         if G > 1:
-            dist.all_to_all_single(recv, counts, group=self.group)
+            dist.all_to_all_single(recv, send_counts, group=self.group)
         else:
-            recv.copy_(counts)
-        recv_counts = recv.tolist()
-        rf = self._all_to_all(torch.cat(send_f), send_counts, recv_counts)
-        ri = self._all_to_all(torch.cat(send_i), send_counts, recv_counts)
+            recv.copy_(send_counts)
+        both = torch.stack([send_counts, recv]).tolist()                            # the one host read-back before the exchange
+        send_counts, recv_counts = both[0], both[1]
+        rf = self._all_to_all(send_f, send_counts, recv_counts)
+        ri = self._all_to_all(send_i, send_counts, recv_counts)
         # group by (scan id, row): scans become contiguous and keep their original point order
-        key = ri[:, 0] * (int(ri[:, 1].max().item()) + 1 if len(ri) else 1) + ri[:, 1]
+        key = ri[:, 0].long() * (int(ri[:, 1].max().item()) + 1 if len(ri) else 1) + ri[:, 1].long()
         order = torch.argsort(key, stable=True)
         rf, ri = rf[order], ri[order]
         sids, sizes_l = torch.unique_consecutive(ri[:, 0], return_counts=True)
@@ -165,7 +171,7 @@ class SlabPartitioner(object):
             local_clouds.append(DepthCloud(vps=f_vps[first:first + m], dirs=f_dirs[first:first + m], depth=f_depth[first:first + m],
                                            inc_angles=f_inc[first:first + m], mask=f_mask[first:first + m]))
             first += m
-        return LocalMap(local_clouds, sids, ri[:, 3].bool(), ri[:, :2].contiguous(), axis,
+        return LocalMap(local_clouds, sids.long(), ri[:, 3].bool(), ri[:, :2].long().contiguous(), axis,
                         (float(boundaries[self.rank]), float(boundaries[self.rank + 1])))
 
 
