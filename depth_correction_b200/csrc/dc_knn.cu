@@ -36,20 +36,19 @@ __device__ __forceinline__ void knn_scan(const dc_grid& g, const uint64_t* __res
       int lo, hi;
       dc_row_range(g, pkeys, n, cell_start, c0 - rho, c0 + rho, c1 + e1, c2 + e2, lo, hi);
       // four independent candidate loads in flight per thread (the loop is latency bound otherwise; a software
-      // pipeline with eight in flight cost registers / occupancy and was 30 % slower)
-      int j = lo;
-      for (; j + 4 <= hi; j += 4) {
-        const dc_point p0 = dc_ld_point(P + j), p1 = dc_ld_point(P + j + 1);
-        const dc_point p2 = dc_ld_point(P + j + 2), p3 = dc_ld_point(P + j + 3);
+      // pipeline with eight in flight cost registers / occupancy and was 30 % slower).  The tail of a row goes
+      // through the same four-wide body with clamped addresses: a one-at-a-time tail loop exposed a full load
+      // latency per candidate on up to three candidates of every row.
+      for (int j = lo; j < hi; j += 4) {
+        const int last = hi - 1;
+        const int j1 = j + 1 < last ? j + 1 : last, j2 = j + 2 < last ? j + 2 : last, j3 = j + 3 < last ? j + 3 : last;
+        const dc_point p0 = dc_ld_point(P + j), p1 = dc_ld_point(P + j1);
+        const dc_point p2 = dc_ld_point(P + j2), p3 = dc_ld_point(P + j3);
         const double d0 = dc_dist2(p0, pq), d1 = dc_dist2(p1, pq), d2 = dc_dist2(p2, pq), d3 = dc_dist2(p3, pq);
         f(j, d0);
-        f(j + 1, d1);
-        f(j + 2, d2);
-        f(j + 3, d3);
-      }
-      for (; j < hi; ++j) {
-        const dc_point pj = dc_ld_point(P + j);
-        f(j, dc_dist2(pj, pq));
+        if (j + 1 < hi) f(j + 1, d1);
+        if (j + 2 < hi) f(j + 2, d2);
+        if (j + 3 < hi) f(j + 3, d3);
       }
     }
   }

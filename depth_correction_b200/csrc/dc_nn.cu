@@ -36,12 +36,19 @@ radius_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys
       for (int e1 = -rings; e1 <= rings; ++e1) {
         int lo, hi;
         dc_row_range(g, pkeys, n, cell_start, c0 - rings, c0 + rings, c1 + e1, c2 + e2, lo, hi);
-        for (int j = lo; j < hi; ++j) {
-          const dc_point pj = dc_ld_point(P + j);
-          if (dc_dist2(pj, pq) <= r2) {
-            if (FILL) ell_idx[base + (int64_t)cnt * DC_SLICE + lane] = j;
-            ++cnt;
-          }
+        // four candidate loads in flight (the scan is latency bound); the tail of a row reuses the body with
+        // clamped addresses
+        for (int j = lo; j < hi; j += 4) {
+          const int last = hi - 1;
+          const int j1 = j + 1 < last ? j + 1 : last, j2 = j + 2 < last ? j + 2 : last, j3 = j + 3 < last ? j + 3 : last;
+          const dc_point p0 = dc_ld_point(P + j), p1 = dc_ld_point(P + j1);
+          const dc_point p2 = dc_ld_point(P + j2), p3 = dc_ld_point(P + j3);
+          const bool in0 = dc_dist2(p0, pq) <= r2, in1 = j + 1 < hi && dc_dist2(p1, pq) <= r2;
+          const bool in2 = j + 2 < hi && dc_dist2(p2, pq) <= r2, in3 = j + 3 < hi && dc_dist2(p3, pq) <= r2;
+          if (in0) { if (FILL) ell_idx[base + (int64_t)cnt * DC_SLICE + lane] = j; ++cnt; }
+          if (in1) { if (FILL) ell_idx[base + (int64_t)cnt * DC_SLICE + lane] = j + 1; ++cnt; }
+          if (in2) { if (FILL) ell_idx[base + (int64_t)cnt * DC_SLICE + lane] = j + 2; ++cnt; }
+          if (in3) { if (FILL) ell_idx[base + (int64_t)cnt * DC_SLICE + lane] = j + 3; ++cnt; }
         }
       }
     }
