@@ -303,6 +303,30 @@ int dc_icp_backward(const void* points1, const void* points2, int dtype, const v
 int dc_f64_sort_keys(const double* x, int64_t n, uint64_t* keys, int32_t* n_nan, void* stream);
 int dc_f64_from_sort_keys(const uint64_t* keys, int64_t n, double* x, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU slab exchange (no counterpart in the single-process reference).  Slab g of
+ * n_ranks owns b[g] <= x < b[g+1] along the split axis (inner_boundaries = b[1] .. b[n_ranks-1], a HOST array);
+ * a point is sent to every slab with b[g] - halo <= x < b[g+1] + halo.
+ *   dc_route_count : gmin / gmax (uint8 [n]) = first / last destination of every point of world_points (fp64 [n,3]),
+ *                    counts int32 [n_ranks] = records per destination
+ *   dc_route_pack  : send_f [M,8] (cloud dtype: vp.xyz, dir.xyz, depth, inc_angle) and send_i int32 [M,4] (scan id,
+ *                    row, model mask, owned) contiguous per destination (dest_offset int64 [n_ranks] = exclusive sum of
+ *                    counts; cursor int32 [n_ranks] scratch), read through the scan pointer table of
+ *                    dc_pack_records_batched; order inside a destination is arbitrary
+ *   dc_route_keys  : keys[t] = scan id << 32 | row, ids[t] = t of received index records (for dc_sort_pairs)
+ *   dc_route_unpack: received records gathered in `order` into vps / dirs [m,3], depth / inc [m], mask / owned
+ *                    uint8 [m], gid int64 [m,2] = (scan id, row)
+ * ------------------------------------------------------------------------------------------- */
+int dc_route_count(const double* world_points, int axis, int64_t n, const double* inner_boundaries, int n_ranks, double halo,
+                   uint8_t* gmin, uint8_t* gmax, int32_t* counts, void* stream);
+int dc_route_pack(const void* scan_ptr_table, const int64_t* first, const int32_t* scan_ids, int n_scans, int64_t n, int dtype,
+                  const double* world_points, int axis, const double* inner_boundaries, int n_ranks, double halo,
+                  const uint8_t* gmin, const uint8_t* gmax, const int64_t* dest_offset, int32_t* cursor, void* send_f,
+                  int32_t* send_i, void* stream);
+int dc_route_keys(const int32_t* recv_i, int64_t m, uint64_t* keys, int32_t* ids, void* stream);
+int dc_route_unpack(const void* recv_f, const int32_t* recv_i, const int32_t* order, int64_t m, int dtype, void* vps, void* dirs,
+                    void* depth, void* inc, uint8_t* mask, uint8_t* owned, int64_t* gid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
