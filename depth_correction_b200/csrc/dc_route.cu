@@ -174,3 +174,24 @@ extern "C" int dc_route_unpack(const void* recv_f, const int32_t* recv_i, const 
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
+
+// histogram of the coordinate along `axis` (slab boundaries with equal point counts are read off its prefix sum)
+__global__ void axis_hist_kernel(const double* __restrict__ wp, int axis, int64_t n, double a0, double scale, int n_bins,
+                                 int32_t* __restrict__ hist) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long b = (long long)((wp[3 * i + axis] - a0) * scale);      // truncation like torch's .long()
+  b = b < 0 ? 0 : (b > n_bins - 1 ? n_bins - 1 : b);
+  atomicAdd(hist + b, 1);
+}
+
+extern "C" int dc_axis_histogram(const double* world_points, int axis, int64_t n, double a0, double scale, int n_bins,
+                                 int32_t* hist, void* stream) {
+  if (axis < 0 || axis > 2 || n_bins < 1) return dc_set_error(DC_ERR_ARG, "dc_axis_histogram: bad axis / bin count");
+  cudaStream_t st = (cudaStream_t)stream;
+  DC_CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(int32_t) * n_bins, st));
+  if (n <= 0) return DC_OK;
+  axis_hist_kernel<<<dc_blocks(n, 256), 256, 0, st>>>(world_points, axis, n, a0, scale, n_bins, hist);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}

@@ -76,15 +76,32 @@ class SlabPartitioner(object):
             pts = torch.cat([p.detach().reshape(-1, 3) for p in world_points]).double() if world_points else \
                 torch.zeros((0, 3), dtype=torch.float64, device=dev)
         big = 1e300
-        lo = pts.min(dim=0).values if len(pts) else torch.full((3,), big, dtype=torch.float64, device=dev)
-        hi = pts.max(dim=0).values if len(pts) else torch.full((3,), -big, dtype=torch.float64, device=dev)
+        on_gpu = pts.is_cuda and len(pts) > 0
+        if on_gpu:
+            # bounding box and histogram by two kernels of the library (one pass each) instead of a dozen torch passes
+            from . import _lib as L
+            pts = pts.contiguous()
+            box = torch.empty(6, dtype=torch.float64, device=dev)
+            bad = torch.zeros(1, dtype=torch.int32, device=dev)
+            L.call('dc_bounds', L.ptr(pts), L.DC_F64, pts.shape[0], L.ptr(box), L.ptr(bad), L.stream())
+            lo, hi = box[:3], box[3:]
+        else:
+            lo = pts.min(dim=0).values if len(pts) else torch.full((3,), big, dtype=torch.float64, device=dev)
+            hi = pts.max(dim=0).values if len(pts) else torch.full((3,), -big, dtype=torch.float64, device=dev)
         lo = self._all_reduce(lo.clone(), dist.ReduceOp.MIN)
         hi = self._all_reduce(hi.clone(), dist.ReduceOp.MAX)
-        axis = int(torch.argmax(hi - lo).item())
-        a0, a1 = float(lo[axis]), float(hi[axis])
+        lohi = torch.cat([lo, hi]).tolist()
+        ext = [lohi[3 + a] - lohi[a] for a in range(3)]
+        axis = max(range(3), key=lambda a: (ext[a], -a))                # first axis of the largest extent, like argmax
+        a0, a1 = lohi[axis], lohi[3 + axis]
         width = max(a1 - a0, 1e-12)
-        bins = ((pts[:, axis] - a0) * (N_HIST_BINS / width)).long().clamp_(0, N_HIST_BINS - 1)
-        hist = torch.bincount(bins, minlength=N_HIST_BINS).double()
+        if on_gpu:
+            hist32 = torch.empty(N_HIST_BINS, dtype=torch.int32, device=dev)
+            L.call('dc_axis_histogram', L.ptr(pts), axis, pts.shape[0], a0, N_HIST_BINS / width, N_HIST_BINS, L.ptr(hist32), L.stream())
+            hist = hist32.double()
+        else:
+            bins = ((pts[:, axis] - a0) * (N_HIST_BINS / width)).long().clamp_(0, N_HIST_BINS - 1)
+            hist = torch.bincount(bins, minlength=N_HIST_BINS).double()
         hist = self._all_reduce(hist)
         cum = torch.cumsum(hist, dim=0)
         total = cum[-1]

@@ -324,6 +324,10 @@ int dc_route_pack(const void* scan_ptr_table, const int64_t* first, const int32_
                   const uint8_t* gmin, const uint8_t* gmax, const int64_t* dest_offset, int32_t* cursor, void* send_f,
                   int32_t* send_i, void* stream);
 int dc_route_keys(const int32_t* recv_i, int64_t m, uint64_t* keys, int32_t* ids, void* stream);
+/* hist[b] = number of points with floor-toward-zero((x_axis - a0) * scale) == b (clamped to 0 .. n_bins-1): the rank-local
+ * part of the histogram SlabPartitioner.plan all-reduces to cut slabs of equal point count */
+int dc_axis_histogram(const double* world_points, int axis, int64_t n, double a0, double scale, int n_bins, int32_t* hist,
+                      void* stream);
 int dc_route_unpack(const void* recv_f, const int32_t* recv_i, const int32_t* order, int64_t m, int dtype, void* vps, void* dirs,
                     void* depth, void* inc, uint8_t* mask, uint8_t* owned, int64_t* gid, void* stream);
 
