@@ -193,80 +193,76 @@ class SlabPartitioner(object):
         return LocalMap(local_clouds, sids.long(), ri[:, 3].bool(), ri[:, :2].long().contiguous(), axis,
                         (float(boundaries[self.rank]), float(boundaries[self.rank + 1])))
 
-
-def _exchange_cuda(self, clouds, scan_ids, world_points, axis, boundaries, halo):
-    """GPU form of SlabPartitioner.exchange: routing, packing and unpacking in four kernels (dc_route_*), two
-    all-to-alls, three small read-backs (send counts, receive counts, per-scan sizes).  Same result as the torch
-    form above (which the CPU / gloo tests exercise) up to the arbitrary order inside a destination, which the
-    (scan, row) sort on the receiving side removes."""
-    import ctypes
-    from . import _lib as L
-    from .fused import scan_table
-    G = self.world
-    dev = clouds[0].depth.device
-    dt = clouds[0].depth.dtype
-    code = L.dtype_code(dt)
-    st = L.stream()
-    n = sum(len(c) for c in clouds)
-    wp = world_points if isinstance(world_points, torch.Tensor) else torch.cat([w.detach().reshape(-1, 3) for w in world_points])
-    wp = wp.detach().reshape(-1, 3).to(torch.float64).contiguous()
-    assert wp.shape[0] == n
-    tbl, first, _keep = scan_table(clouds, dt)
-    sid_t = L.upload([int(s) for s in scan_ids], torch.int32, dev)
-    inner = [float(v) for v in boundaries[1:-1].tolist()]
-    inner_c = (ctypes.c_double * max(len(inner), 1))(*inner)
-    gmin = torch.empty(n, dtype=torch.uint8, device=dev)
-    gmax = torch.empty(n, dtype=torch.uint8, device=dev)
-    counts = torch.empty(G, dtype=torch.int32, device=dev)
-    L.call('dc_route_count', L.ptr(wp), int(axis), n, inner_c, G, float(halo), L.ptr(gmin), L.ptr(gmax), L.ptr(counts), st)
-    counts64 = counts.long()
-    recv = torch.empty_like(counts64)
-    if G > 1:
-        dist.all_to_all_single(recv, counts64, group=self.group)
-    else:
-        recv.copy_(counts64)
-    both = torch.stack([counts64, recv]).tolist()                 # read-back 1 + 2
-    send_counts, recv_counts = both[0], both[1]
-    offs = [0]
-    for c in send_counts[:-1]:
-        offs.append(offs[-1] + c)
-    m_send = sum(send_counts)
-    dest_offset = L.upload(offs, torch.int64, dev)
-    cursor = torch.empty(G, dtype=torch.int32, device=dev)
-    send_f = torch.empty((m_send, 8), dtype=dt, device=dev)
-    send_i = torch.empty((m_send, 4), dtype=torch.int32, device=dev)
-    L.call('dc_route_pack', L.ptr(tbl), L.ptr(first), L.ptr(sid_t), len(clouds), n, code, L.ptr(wp), int(axis), inner_c, G, float(halo),
-           L.ptr(gmin), L.ptr(gmax), L.ptr(dest_offset), L.ptr(cursor), L.ptr(send_f), L.ptr(send_i), st)
-    rf = self._all_to_all(send_f, send_counts, recv_counts)
-    ri = self._all_to_all(send_i, send_counts, recv_counts)
-    m = rf.shape[0]
-    keys = torch.empty(m, dtype=torch.int64, device=dev)
-    ids = torch.empty(m, dtype=torch.int32, device=dev)
-    skeys = torch.empty(m, dtype=torch.int64, device=dev)
-    order = torch.empty(m, dtype=torch.int32, device=dev)
-    f_vps = torch.empty((m, 3), dtype=dt, device=dev)
-    f_dirs = torch.empty((m, 3), dtype=dt, device=dev)
-    f_depth = torch.empty((m, 1), dtype=dt, device=dev)
-    f_inc = torch.empty((m, 1), dtype=dt, device=dev)
-    f_mask = torch.empty(m, dtype=torch.bool, device=dev)
-    f_owned = torch.empty(m, dtype=torch.bool, device=dev)
-    gid = torch.empty((m, 2), dtype=torch.int64, device=dev)
-    if m > 0:
-        L.call('dc_route_keys', L.ptr(ri), m, L.ptr(keys), L.ptr(ids), st)
-        L.call_with_temp('dc_sort_pairs', dev, L.ptr(keys), L.ptr(skeys), L.ptr(ids), L.ptr(order), m, 63, after=(st,))
-        L.call('dc_route_unpack', L.ptr(rf), L.ptr(ri), L.ptr(order), m, code, L.ptr(f_vps), L.ptr(f_dirs), L.ptr(f_depth), L.ptr(f_inc),
-               L.ptr(f_mask.view(torch.uint8)), L.ptr(f_owned.view(torch.uint8)), L.ptr(gid), st)
-    sids, sizes_l = torch.unique_consecutive(gid[:, 0], return_counts=True)          # read-back 3
-    local_clouds, first_row = [], 0
-    for sz in sizes_l.tolist():
-        local_clouds.append(DepthCloud(vps=f_vps[first_row:first_row + sz], dirs=f_dirs[first_row:first_row + sz],
-                                       depth=f_depth[first_row:first_row + sz], inc_angles=f_inc[first_row:first_row + sz],
-                                       mask=f_mask[first_row:first_row + sz]))
-        first_row += sz
-    return LocalMap(local_clouds, sids, f_owned, gid, axis, (float(boundaries[self.rank]), float(boundaries[self.rank + 1])))
-
-
-SlabPartitioner._exchange_cuda = _exchange_cuda
+    def _exchange_cuda(self, clouds, scan_ids, world_points, axis, boundaries, halo):
+        """GPU form of SlabPartitioner.exchange: routing, packing and unpacking in four kernels (dc_route_*), two
+        all-to-alls, three small read-backs (send counts, receive counts, per-scan sizes).  Same result as the torch
+        form above (which the CPU / gloo tests exercise) up to the arbitrary order inside a destination, which the
+        (scan, row) sort on the receiving side removes."""
+        import ctypes
+        from . import _lib as L
+        from .fused import scan_table
+        G = self.world
+        dev = clouds[0].depth.device
+        dt = clouds[0].depth.dtype
+        code = L.dtype_code(dt)
+        st = L.stream()
+        n = sum(len(c) for c in clouds)
+        wp = world_points if isinstance(world_points, torch.Tensor) else torch.cat([w.detach().reshape(-1, 3) for w in world_points])
+        wp = wp.detach().reshape(-1, 3).to(torch.float64).contiguous()
+        assert wp.shape[0] == n
+        tbl, first, _keep = scan_table(clouds, dt)
+        sid_t = L.upload([int(s) for s in scan_ids], torch.int32, dev)
+        inner = [float(v) for v in boundaries[1:-1].tolist()]
+        inner_c = (ctypes.c_double * max(len(inner), 1))(*inner)
+        gmin = torch.empty(n, dtype=torch.uint8, device=dev)
+        gmax = torch.empty(n, dtype=torch.uint8, device=dev)
+        counts = torch.empty(G, dtype=torch.int32, device=dev)
+        L.call('dc_route_count', L.ptr(wp), int(axis), n, inner_c, G, float(halo), L.ptr(gmin), L.ptr(gmax), L.ptr(counts), st)
+        counts64 = counts.long()
+        recv = torch.empty_like(counts64)
+        if G > 1:
+            dist.all_to_all_single(recv, counts64, group=self.group)
+        else:
+            recv.copy_(counts64)
+        both = torch.stack([counts64, recv]).tolist()                 # read-back 1 + 2
+        send_counts, recv_counts = both[0], both[1]
+        offs = [0]
+        for c in send_counts[:-1]:
+            offs.append(offs[-1] + c)
+        m_send = sum(send_counts)
+        dest_offset = L.upload(offs, torch.int64, dev)
+        cursor = torch.empty(G, dtype=torch.int32, device=dev)
+        send_f = torch.empty((m_send, 8), dtype=dt, device=dev)
+        send_i = torch.empty((m_send, 4), dtype=torch.int32, device=dev)
+        L.call('dc_route_pack', L.ptr(tbl), L.ptr(first), L.ptr(sid_t), len(clouds), n, code, L.ptr(wp), int(axis), inner_c, G, float(halo),
+               L.ptr(gmin), L.ptr(gmax), L.ptr(dest_offset), L.ptr(cursor), L.ptr(send_f), L.ptr(send_i), st)
+        rf = self._all_to_all(send_f, send_counts, recv_counts)
+        ri = self._all_to_all(send_i, send_counts, recv_counts)
+        m = rf.shape[0]
+        keys = torch.empty(m, dtype=torch.int64, device=dev)
+        ids = torch.empty(m, dtype=torch.int32, device=dev)
+        skeys = torch.empty(m, dtype=torch.int64, device=dev)
+        order = torch.empty(m, dtype=torch.int32, device=dev)
+        f_vps = torch.empty((m, 3), dtype=dt, device=dev)
+        f_dirs = torch.empty((m, 3), dtype=dt, device=dev)
+        f_depth = torch.empty((m, 1), dtype=dt, device=dev)
+        f_inc = torch.empty((m, 1), dtype=dt, device=dev)
+        f_mask = torch.empty(m, dtype=torch.bool, device=dev)
+        f_owned = torch.empty(m, dtype=torch.bool, device=dev)
+        gid = torch.empty((m, 2), dtype=torch.int64, device=dev)
+        if m > 0:
+            L.call('dc_route_keys', L.ptr(ri), m, L.ptr(keys), L.ptr(ids), st)
+            L.call_with_temp('dc_sort_pairs', dev, L.ptr(keys), L.ptr(skeys), L.ptr(ids), L.ptr(order), m, 63, after=(st,))
+            L.call('dc_route_unpack', L.ptr(rf), L.ptr(ri), L.ptr(order), m, code, L.ptr(f_vps), L.ptr(f_dirs), L.ptr(f_depth), L.ptr(f_inc),
+                   L.ptr(f_mask.view(torch.uint8)), L.ptr(f_owned.view(torch.uint8)), L.ptr(gid), st)
+        sids, sizes_l = torch.unique_consecutive(gid[:, 0], return_counts=True)          # read-back 3
+        local_clouds, first_row = [], 0
+        for sz in sizes_l.tolist():
+            local_clouds.append(DepthCloud(vps=f_vps[first_row:first_row + sz], dirs=f_dirs[first_row:first_row + sz],
+                                           depth=f_depth[first_row:first_row + sz], inc_angles=f_inc[first_row:first_row + sz],
+                                           mask=f_mask[first_row:first_row + sz]))
+            first_row += sz
+        return LocalMap(local_clouds, sids, f_owned, gid, axis, (float(boundaries[self.rank]), float(boundaries[self.rank + 1])))
 
 
 def reduce_step(sum_count, params, group=None):
