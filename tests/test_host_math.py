@@ -153,3 +153,18 @@ def test_structured_array_round_trip_matches_reference():
         assert ro.dtype.names == tuple(f for f in out.dtype.names if f != 'mask')
         for f in ro.dtype.names:
             assert ro[f].dtype == out[f].dtype and np.allclose(ro[f], out[f], atol=1e-6), f
+
+
+def test_config_yaml_round_trip(tmp_path):
+    """Config fields survive to_yaml / from_yaml (the training driver writes train.yaml / best.yaml with it)."""
+    import depth_correction_b200 as dc
+    cfg = dc.Config(nn_k=16, nn_r=0.3, eigenvalue_bounds=[[0, None, 0.01]], loss='trace_loss', lr=2e-3,
+                    pose_correction=dc.PoseCorrection.pose, model_kwargs={'w': [0.0, 0.0], 'exponent': [2.0, 4.0]})
+    path = str(tmp_path / 'cfg.yaml')
+    cfg.to_yaml(path)
+    back = dc.Config().from_yaml(path)
+    for k in ('nn_k', 'nn_r', 'eigenvalue_bounds', 'loss', 'lr', 'pose_correction', 'model_kwargs', 'grid_res', 'random_seed'):
+        assert getattr(back, k) == getattr(cfg, k), k
+    copy = cfg.copy()
+    copy.model_kwargs['w'][0] = 1.0                      # (one level deep, like the reference's Config.copy)
+    assert isinstance(copy, dc.Config) and copy.nn_k == 16
