@@ -14,7 +14,7 @@ from .model import BaseModel, Polynomial, ScaledPolynomial, load_model, model_by
 from .loss import Reduction, batch_loss, create_loss, fused_sum_count, loss_by_name, min_eigval_loss, reduce, trace_loss
 from .icp import icp_loss, point_to_plane_dist, point_to_point_dist
 from .parallel import LocalMap, SlabPartitioner, distributed_quantile, reduce_step, sharded_inlier_sum_count
-from .filters import (filter_depth, filter_eigenvalue, filter_eigenvalue_ratio, filter_eigenvalue_ratios,
+from .filters import (feature_mask, filter_depth, filter_eigenvalue, filter_eigenvalue_ratio, filter_eigenvalue_ratios,
                       filter_eigenvalues, filter_shadow_points, filter_valid_neighbors, within_bounds)
 from .filters_grid import filter_grid
 from .preproc import (GlobalCloud, Neighborhoods, compute_neighborhood_features, establish_neighborhoods,

@@ -56,7 +56,8 @@ SIGNATURES = {
     'dc_ell_offsets': [_P, _L, _P, _P, _SZP, _P],
     'dc_radius_fill': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _D, _P, _P, _P],
     'dc_knn': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _I, _D, _P, _P, _P],
-    'dc_knn_sort_rows': [_I, _P, _P, _L, _P],
+    'dc_knn_cells': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _I, _D, _P, _P, _SZP, _P],
+    'dc_knn_sort_rows': [_P, _L, _I, _P, _P, _L, _P],
     'dc_knn_distances': [_P, _P, _I, _P, _L, _P, _P],
     'dc_ell_to_padded': [_P, _P, _L, _P, _P, _I, _P, _P],
     'dc_ell_to_dist': [_I, _P, _P, _L, _P, _P, _P],
@@ -74,12 +75,14 @@ SIGNATURES = {
     'dc_set_loss_mask': [_P, _L, _P, _P, _P],
     'dc_step_points': [_P, _P, _P, _I, _L, _P, _I, _I, _P, _P, _I, _P, _P],
     'dc_step_forward': [_P, _P, _L, _P, _P, _I, _I, _P, _P, _P, _P, _P, _SZ, _P],
+    'dc_step_forward_scatter': [_P, _P, _L, _P, _P, _I, _I, _P, _P, _P, _P, _SZ, _P],
     'dc_step_backward': [_P, _L, _P, _P, _P, _P, _P, _P, _P],
     'dc_step_backward_scatter': [_P, _L, _P, _P, _P, _P, _P, _I, _P],
     'dc_step_chain': [_P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P],
     'dc_pose_compose': [_P, _P, _I, _I, _P, _P],
     'dc_pose_compose_backward': [_P, _P, _I, _I, _P, _P, _P],
     'dc_features': [_P, _I, _L, _P, _P, _I, _P, _P, _P],
+    'dc_feature_mask': [_P, _I, _L, _I, _P, _I, _P, _L, _I, _P, _P],
     'dc_features_backward': [_P, _I, _L, _P, _P, _I, _P, _P, _P, _P],
     'dc_eigh3': [_P, _I, _L, _P, _P, _P],
     'dc_eigh3_backward': [_P, _P, _I, _L, _P, _P, _P, _P],

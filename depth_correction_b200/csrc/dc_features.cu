@@ -3,6 +3,7 @@
 // (depth_cloud.py:291-424) when they are called one by one, plus their backward passes so the
 // staged API stays differentiable like the reference's autograd graph.  The training loop does not
 // use these; it runs the fused kernels in dc_step.cu.
+#include <string.h>
 #include "dc_common.cuh"
 #include "dc_math.cuh"
 
@@ -287,6 +288,75 @@ extern "C" int dc_from_points(const void* points, const void* vps, int dtype, in
   else
     from_points_kernel<double><<<dc_blocks(n, 256), 256, 0, st>>>((const double*)points, (const double*)vps, n, (double*)dirs,
                                                                   (double*)depth, (double*)vps_out);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Feature masks (filters.py:85-113, 184-254; composed at preproc.py:53-62 and :130-142): every bound of a
+// configuration in ONE launch instead of one compare + one AND per bound.  Comparisons are inclusive and done in the
+// tensor's own dtype like torch (`x >= min` with a python scalar compares in x.dtype; the ratio is a division in
+// x.dtype), NaN fails every bound.
+// ---------------------------------------------------------------------------------------------
+#define DC_MASK_MAX_BOUNDS 16
+struct dc_mask_bounds {
+  int n;
+  int kind[DC_MASK_MAX_BOUNDS];      // 0: lo <= v[a] <= hi ; 1: lo <= v[a] / v[b] <= hi
+  int a[DC_MASK_MAX_BOUNDS], b[DC_MASK_MAX_BOUNDS];
+  int use_lo[DC_MASK_MAX_BOUNDS], use_hi[DC_MASK_MAX_BOUNDS];
+  double lo[DC_MASK_MAX_BOUNDS], hi[DC_MASK_MAX_BOUNDS];
+};
+
+template <typename T>
+__global__ void feature_mask_kernel(const T* __restrict__ vals, int64_t n, int stride, dc_mask_bounds bd,
+                                    const int64_t* __restrict__ valid_counts, int64_t min_valid, int init,
+                                    uint8_t* __restrict__ mask) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool keep = init ? true : (mask[i] != 0);
+  if (valid_counts) keep = keep && valid_counts[i] >= min_valid;
+  T v0 = (T)0, v1 = (T)0, v2 = (T)0;
+  if (vals && bd.n > 0) {
+    v0 = vals[i * stride];
+    if (stride > 1) v1 = vals[i * stride + 1];
+    if (stride > 2) v2 = vals[i * stride + 2];
+  }
+#pragma unroll 1
+  for (int t = 0; t < bd.n; ++t) {
+    const T va = bd.a[t] == 0 ? v0 : (bd.a[t] == 1 ? v1 : v2), vb = bd.b[t] == 0 ? v0 : (bd.b[t] == 1 ? v1 : v2);
+    const T x = bd.kind[t] == 0 ? va : va / vb;
+    if (bd.use_lo[t]) keep = keep && (x >= (T)bd.lo[t]);
+    if (bd.use_hi[t]) keep = keep && (x <= (T)bd.hi[t]);
+  }
+  mask[i] = keep ? 1 : 0;
+}
+
+extern "C" int dc_feature_mask(const void* vals, int dtype, int64_t n, int stride, const double* bounds_host, int n_bounds,
+                               const int64_t* valid_counts, int64_t min_valid, int init, uint8_t* mask, void* stream) {
+  if (n <= 0) return DC_OK;
+  if (n_bounds < 0 || n_bounds > DC_MASK_MAX_BOUNDS) return dc_set_error(DC_ERR_ARG, "dc_feature_mask: at most 16 bounds per call");
+  if (stride < 1 || stride > 3) return dc_set_error(DC_ERR_ARG, "dc_feature_mask: stride must be 1..3");
+  if (n_bounds > 0 && !vals) return dc_set_error(DC_ERR_ARG, "dc_feature_mask: bounds without values");
+  dc_mask_bounds bd;
+  memset(&bd, 0, sizeof(bd));
+  bd.n = n_bounds;
+  for (int t = 0; t < n_bounds; ++t) {
+    const double* r = bounds_host + 5 * t;      // {kind, a, b, lo, hi}; lo = -inf / hi = +inf / NaN disable a side
+    bd.kind[t] = (int)r[0];
+    bd.a[t] = (int)r[1];
+    bd.b[t] = (int)r[2];
+    if (bd.kind[t] < 0 || bd.kind[t] > 1 || bd.a[t] < 0 || bd.a[t] >= stride || bd.b[t] < 0 || bd.b[t] >= stride)
+      return dc_set_error(DC_ERR_ARG, "dc_feature_mask: bad bound record");
+    bd.use_lo[t] = r[3] > -INFINITY;             // false for -inf and NaN (within_bounds: `min > -inf`)
+    bd.use_hi[t] = r[4] < INFINITY;
+    bd.lo[t] = r[3];
+    bd.hi[t] = r[4];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DC_F32)
+    feature_mask_kernel<float><<<dc_blocks(n, 256), 256, 0, st>>>((const float*)vals, n, stride, bd, valid_counts, min_valid, init, mask);
+  else
+    feature_mask_kernel<double><<<dc_blocks(n, 256), 256, 0, st>>>((const double*)vals, n, stride, bd, valid_counts, min_valid, init, mask);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

@@ -248,12 +248,18 @@ __device__ __forceinline__ void dc_store_stash(dc_stash* dst, const dc_stash& s)
   d4[1] = make_double4(s.vy, s.vz, s.alpha, s.beta);
 }
 
-template <int LOSS>
+// SCAT: the backward scatter (pass C1, float32 form) runs in the same kernel.  For the mean / sum reductions the
+// upstream gradient of every loss term is ONE scalar that the chain stage applies afterwards, so right after the
+// eigen epilogue the thread still holds everything the scatter needs (mean, v0, alpha, beta) in registers: it walks its
+// index column a second time (L1/L2-hot) and issues the vector reductions into g32.  No stash is written or re-read
+// and the index array and the neighbour records are not fetched from HBM a second time.
+template <int LOSS, bool SCAT>
 __global__ void __launch_bounds__(STEP_THREADS)
 step_forward_kernel(const dc_point* __restrict__ P, const uint32_t* __restrict__ rec_meta, int64_t n,
                     const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ ell_idx, int flags,
                     double* __restrict__ loss_pp, dc_stash* __restrict__ stash, double* __restrict__ eigvals,
-                    double* __restrict__ loss_sum, double* __restrict__ partials, unsigned int* __restrict__ done) {
+                    double* __restrict__ loss_sum, double* __restrict__ partials, unsigned int* __restrict__ done,
+                    float4* __restrict__ g32) {
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool live = row < n;
@@ -349,6 +355,33 @@ step_forward_kernel(const dc_point* __restrict__ P, const uint32_t* __restrict__
       s.alpha = f * alpha; s.beta = f * beta;
       dc_store_stash(stash + row, s);
     }
+    if (SCAT) {
+      const double f = 2.0 * icw * dfac;
+      const double ua = f * alpha, ub = f * beta;
+      if (ua != 0.0 || ub != 0.0) {        // masked-out / inactive loss term: nothing to scatter
+        const double mx = pi.x + sx * iw, my = pi.y + sy * iw, mz = pi.z + sz * iw;
+#define DC_SCAT(j_)                                                                  \
+  if ((j_) >= 0) {                                                                   \
+    const dc_point pj = dc_ld_point(P + (j_));                                       \
+    const double ex = pj.x - mx, ey = pj.y - my, ez = pj.z - mz;                     \
+    const double a = ua * (v0[0] * ex + v0[1] * ey + v0[2] * ez);                    \
+    const double vx = a * v0[0] + ub * ex, vy = a * v0[1] + ub * ey, vz = a * v0[2] + ub * ez; \
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g32 + (j_)), "f"((float)vx), \
+                 "f"((float)vy), "f"((float)vz), "f"(0.f) : "memory");               \
+  }
+        int c2 = 0;
+        for (; c2 + 4 <= width; c2 += 4) {
+          const int j0 = __ldg(col + (c2 + 0) * DC_SLICE), j1 = __ldg(col + (c2 + 1) * DC_SLICE);
+          const int j2 = __ldg(col + (c2 + 2) * DC_SLICE), j3 = __ldg(col + (c2 + 3) * DC_SLICE);
+          DC_SCAT(j0) DC_SCAT(j1) DC_SCAT(j2) DC_SCAT(j3)
+        }
+        for (; c2 < width; ++c2) {
+          const int j0 = __ldg(col + c2 * DC_SLICE);
+          DC_SCAT(j0)
+        }
+#undef DC_SCAT
+      }
+    }
   }
   if (!loss_sum) return;
   // deterministic two-level reduction: per-block partials, last block adds them in index order
@@ -396,13 +429,38 @@ extern "C" int dc_step_forward(const void* points, const uint32_t* rec_meta, int
   unsigned int* done = loss_sum ? (unsigned int*)((char*)partials + (size_t)blocks * 16) : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   if (loss_kind == DC_LOSS_TRACE)
-    step_forward_kernel<DC_LOSS_TRACE><<<blocks, STEP_THREADS, 0, st>>>((const dc_point*)points, rec_meta, n, slice_ptr, ell_idx, flags,
-                                                                         loss_pp, (dc_stash*)stash, eigvals, loss_sum, part, done);
+    step_forward_kernel<DC_LOSS_TRACE, false><<<blocks, STEP_THREADS, 0, st>>>((const dc_point*)points, rec_meta, n, slice_ptr, ell_idx, flags,
+                                                                                loss_pp, (dc_stash*)stash, eigvals, loss_sum, part, done, nullptr);
   else if (loss_kind == DC_LOSS_MIN_EIGVAL)
-    step_forward_kernel<DC_LOSS_MIN_EIGVAL><<<blocks, STEP_THREADS, 0, st>>>((const dc_point*)points, rec_meta, n, slice_ptr, ell_idx, flags,
-                                                                              loss_pp, (dc_stash*)stash, eigvals, loss_sum, part, done);
+    step_forward_kernel<DC_LOSS_MIN_EIGVAL, false><<<blocks, STEP_THREADS, 0, st>>>((const dc_point*)points, rec_meta, n, slice_ptr, ell_idx, flags,
+                                                                                     loss_pp, (dc_stash*)stash, eigvals, loss_sum, part, done, nullptr);
   else
     return dc_set_error(DC_ERR_ARG, "dc_step_forward: unknown loss kind");
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+extern "C" int dc_step_forward_scatter(const void* points, const uint32_t* rec_meta, int64_t n, const int64_t* slice_ptr,
+                                       const int32_t* ell_idx, int loss_kind, int flags, double* loss_pp, void* g_sorted32,
+                                       double* loss_sum, void* partials, size_t partials_bytes, void* stream) {
+  if (n <= 0) return DC_OK;
+  if (flags & DC_FLAG_RAW) return dc_set_error(DC_ERR_ARG, "dc_step_forward_scatter: per-point upstream gradients need the two-kernel form");
+  if (!g_sorted32 || !loss_sum) return dc_set_error(DC_ERR_ARG, "dc_step_forward_scatter: g_sorted32 and loss_sum are required");
+  const int blocks = dc_blocks(((n + 31) / 32) * 32, STEP_THREADS);
+  if (partials_bytes < (size_t)blocks * 16 + 16)
+    return dc_set_error(DC_ERR_ARG, "dc_step_forward_scatter: partials buffer too small (need 16*blocks+16 bytes)");
+  double* part = (double*)partials;
+  unsigned int* done = (unsigned int*)((char*)partials + (size_t)blocks * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  DC_CUDA_CHECK(cudaMemsetAsync(g_sorted32, 0, (size_t)n * 16, st));
+  if (loss_kind == DC_LOSS_TRACE)
+    step_forward_kernel<DC_LOSS_TRACE, true><<<blocks, STEP_THREADS, 0, st>>>((const dc_point*)points, rec_meta, n, slice_ptr, ell_idx, flags,
+                                                                               loss_pp, nullptr, nullptr, loss_sum, part, done, (float4*)g_sorted32);
+  else if (loss_kind == DC_LOSS_MIN_EIGVAL)
+    step_forward_kernel<DC_LOSS_MIN_EIGVAL, true><<<blocks, STEP_THREADS, 0, st>>>((const dc_point*)points, rec_meta, n, slice_ptr, ell_idx, flags,
+                                                                                    loss_pp, nullptr, nullptr, loss_sum, part, done, (float4*)g_sorted32);
+  else
+    return dc_set_error(DC_ERR_ARG, "dc_step_forward_scatter: unknown loss kind");
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

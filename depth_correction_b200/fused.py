@@ -27,6 +27,25 @@ TRANSPOSE_AFTER = 2                     # backward passes served by the scatter 
 # DC_SCATTER_F32=0 / 1 forces the choice; DC_BACKWARD=gather forces the deterministic fp64 gather form (bitwise
 # reproducible gradients), DC_BACKWARD=scatter the scatter form.
 SCATTER_F32_MIN_POINTS = 1 << 20
+# 'auto' (policy above) | 'gather' (fp64, atomic-free, bitwise reproducible gradients) | 'scatter'.  Set through
+# set_backward_form() / Config.backward_form; the environment variable DC_BACKWARD only provides the initial value.
+BACKWARD_FORM = os.environ.get('DC_BACKWARD', 'auto')
+_form_logged = set()
+
+
+def set_backward_form(form):
+    """Select how dL/dp is accumulated: 'auto', 'gather' (deterministic fp64) or 'scatter' (L2 reductions; float32 on
+    maps of >= 2^20 points).  The reference's autograd is deterministic: use 'gather' for bit-reproducible runs."""
+    global BACKWARD_FORM
+    assert form in ('auto', 'gather', 'scatter'), form
+    BACKWARD_FORM = form
+
+
+def _scatter_f32(n):
+    force = os.environ.get('DC_SCATTER_F32')
+    return (n >= SCATTER_F32_MIN_POINTS) if force is None else force == '1'
+
+
 CHAIN_CHUNK = 2048                      # rows per block of the chain stage (256 threads x 8)
 CHAIN_REC = 12 + 2 * L.MAX_TERMS        # doubles per partial record (dc_step.cu)
 
@@ -166,7 +185,8 @@ class StepState(object):
         self.blk_count = tab[2 * nbk:3 * nbk].to(torch.int32)
         self.scan_blk_first = tab[3 * nbk:].to(torch.int32)
         self.chain_partials = torch.empty(max(self.chain_blocks, 1) * CHAIN_REC, dtype=torch.float64, device=dev)
-        self._mask_key = None
+        self._mask_set, self._mask_ref, self._mask_ver = True, None, None      # packed with an all-true loss mask
+        self._keyed = []
         self.generation = 0
 
     @property
@@ -176,17 +196,17 @@ class StepState(object):
         return g
 
     def set_loss_mask(self, mask):
-        """mask: bool [N] in original (concatenated) order or None (= all points)."""
-        key = None if mask is None else (mask.data_ptr(), mask._version, tuple(mask.shape))
-        if key == self._mask_key:
+        """mask: bool [N] in original (concatenated) order or None (= all points).  The upload is skipped only for the
+        very same tensor object at the same version (a strong reference is kept, so its address cannot be recycled by
+        a different mask of the same shape)."""
+        if self._mask_set and mask is self._mask_ref and (mask is None or mask._version == self._mask_ver):
             return
         m8 = None
         if mask is not None:
             assert mask.numel() == self.n
             m8 = mask.detach().to(device=self.device).to(torch.uint8).contiguous()
         L.call('dc_set_loss_mask', L.ptr(m8), self.n, L.ptr(self.graph.map.order), L.ptr(self.rec_meta), L.stream())
-        self._mask_key = key
-        self._mask_keepalive = m8
+        self._mask_set, self._mask_ref, self._mask_ver = True, mask, None if mask is None else mask._version
 
 
 class _FusedStep(torch.autograd.Function):
@@ -212,9 +232,22 @@ class _FusedStep(torch.autograd.Function):
                L.ptr(poses12), S, model_kind, L.ptr(wv), L.ptr(ev), n_terms, L.ptr(state.P), st)
         raw = bool(flags & L.FLAG_RAW)
         loss_sum = None if raw else torch.empty(2, dtype=torch.float64, device=dev)
-        L.call('dc_step_forward', L.ptr(state.P), L.ptr(state.rec_meta), state.n, L.ptr(g.slice_ptr), L.ptr(g.ell_idx),
-               loss_kind, flags, L.ptr(state.loss_pp), L.ptr(state.stash), None, L.ptr(loss_sum),
-               L.ptr(state.partials), state.partials.numel() * 8, st)
+        # mean / sum reductions on large kNN maps: forward and the float32 backward scatter in ONE kernel (the upstream
+        # gradient is a scalar applied after the chain stage); nothing is stashed.  Only when a gradient is wanted.
+        form = BACKWARD_FORM
+        fused_bwd = (not raw and any(ctx.needs_input_grad[:3]) and not g.symmetric and _scatter_f32(state.n)
+                     and form in ('auto', 'scatter') and os.environ.get('DC_FUSE_BWD', '1') == '1')
+        if fused_bwd:
+            if state._g32 is None:
+                state._g32 = torch.empty((state.n, 4), dtype=torch.float32, device=dev)
+            L.call('dc_step_forward_scatter', L.ptr(state.P), L.ptr(state.rec_meta), state.n, L.ptr(g.slice_ptr),
+                   L.ptr(g.ell_idx), loss_kind, flags, L.ptr(state.loss_pp), L.ptr(state._g32), L.ptr(loss_sum),
+                   L.ptr(state.partials), state.partials.numel() * 8, st)
+        else:
+            L.call('dc_step_forward', L.ptr(state.P), L.ptr(state.rec_meta), state.n, L.ptr(g.slice_ptr), L.ptr(g.ell_idx),
+                   loss_kind, flags, L.ptr(state.loss_pp), L.ptr(state.stash), None, L.ptr(loss_sum),
+                   L.ptr(state.partials), state.partials.numel() * 8, st)
+        ctx.fused_bwd = fused_bwd
         state.generation += 1
         ctx.state, ctx.generation = state, state.generation
         ctx.graph = g                 # keeps the graph (and with it the state's buffers) alive until backward
@@ -241,10 +274,11 @@ class _FusedStep(torch.autograd.Function):
         # graph use the scatter form and the transpose is built once the graph is evidently being reused.
         graph = ctx.graph
         graph._bwd_calls = getattr(graph, '_bwd_calls', 0) + 1
-        force = os.environ.get('DC_SCATTER_F32')
-        scatter_f32 = (state.n >= SCATTER_F32_MIN_POINTS) if force is None else force == '1'
-        form = os.environ.get('DC_BACKWARD', 'auto')           # auto | gather | scatter
-        if form == 'scatter' or (form == 'auto' and scatter_f32 and not graph.symmetric):
+        scatter_f32 = _scatter_f32(state.n)
+        form = BACKWARD_FORM                                   # auto | gather | scatter
+        if ctx.fused_bwd:
+            gt = None                    # dL/dp already sits in state._g32 (dc_step_forward_scatter)
+        elif form == 'scatter' or (form == 'auto' and scatter_f32 and not graph.symmetric):
             gt = None                    # large kNN maps: the fp32 scatter form beats the gather form outright (1.4 vs 2.0 ms
                                          # on the bench map) and needs no reverse lists
         elif graph.symmetric:
@@ -261,7 +295,15 @@ class _FusedStep(torch.autograd.Function):
             upstream = grads[0].to(torch.float64).contiguous()
         g_index = None
         g_buf, g_code = state.g, L.DC_F64
-        if gt is not None:
+        chosen = 'fused float32 scatter' if ctx.fused_bwd else ('fp64 gather' if gt is not None else
+                                                                 ('float32 scatter' if scatter_f32 else 'fp64 scatter'))
+        if chosen not in _form_logged and os.environ.get('DC_VERBOSE'):
+            _form_logged.add(chosen)
+            print('depth_correction_b200: backward form "%s" (n = %d, fused.set_backward_form)' % (chosen, state.n))
+        if ctx.fused_bwd:
+            g_buf, g_code = state._g32, L.DC_F32
+            g_index = graph.map.inv_order
+        elif gt is not None:
             # gather form over the transposed graph: atomic-free, deterministic
             L.call('dc_step_backward', L.ptr(state.P), state.n, L.ptr(gt.slice_ptr), L.ptr(gt.ell_idx), L.ptr(state.stash),
                    L.ptr(upstream), L.ptr(graph.map.order), L.ptr(state.g), st)

@@ -16,6 +16,7 @@ from . import _lib as L
 
 __all__ = ['SortedMap', 'Graph', 'search']
 
+KNN_OCC_DEFAULT = '0.3'                # mean points per occupied cell / k the kNN cell size aims at
 DENSE_TABLE_MAX_CELLS = 1 << 30      # 4 GB of int32 cell starts at most (a 100 M point, 760 m corridor needs 3e8 cells)
 
 
@@ -198,7 +199,7 @@ class Graph(object):
                 Q = self.map.P if self._Q is None else self._Q
                 L.call('dc_knn_distances', L.ptr(self.map.P), L.ptr(Q), self.width, L.ptr(self.ell_idx), self.n_rows,
                        L.ptr(self.ell_d2), L.stream())
-            L.call('dc_knn_sort_rows', self.width, L.ptr(self.ell_idx), L.ptr(self.ell_d2), self.n_rows, L.stream())
+            L.call('dc_knn_sort_rows', L.ptr(self.map.P), self.map.n, self.width, L.ptr(self.ell_idx), L.ptr(self.ell_d2), self.n_rows, L.stream())
         self._rows_sorted = True
 
     def neighbors(self):
@@ -297,33 +298,43 @@ class Graph(object):
 _cell_hint = {}
 
 
-def _knn_cell_size(points, k, r, bounds):
-    """Cell edge for kNN search: aim at ~0.3 k points per occupied cell, estimated from key-only sorts."""
+def _knn_cell_size(points, k, r, bounds, use_hint=True):
+    """Cell edge for kNN search: aim at ~DC_KNN_OCC * k points per occupied cell, estimated from key-only sorts.
+
+    The estimate of the previous search is reused (no sort at all) only for a map of the same size (+-5 %) AND the
+    same extent (+-10 % per axis): an unrelated map of similar size but different scale gets its own estimate."""
     lo, hi = bounds
+    occ_env = os.environ.get('DC_KNN_OCC', KNN_OCC_DEFAULT)
     hint_key = (int(k), float(r) if r else None, points.dtype, str(points.device))
-    hint = _cell_hint.get(hint_key)
-    if hint is not None and 0.8 * hint[0] <= points.shape[0] <= 1.25 * hint[0] \
-            and hint[2] == os.environ.get('DC_KNN_OCC', '0.3'):
+    hint = _cell_hint.get(hint_key) if use_hint else None
+    ext = [max(h - l, 1e-12) for l, h in zip(lo, hi)]
+    same_extent = hint is not None and all(0.9 * a <= b <= 1.1 * a for a, b in zip(hint[3], ext))
+    if hint is not None and same_extent and 0.8 * hint[0] <= points.shape[0] <= 1.25 * hint[0] and hint[2] == occ_env:
         c0 = hint[1]
         if 0.95 * hint[0] <= points.shape[0] <= 1.05 * hint[0]:
-            return c0           # same map size: the cell size only steers speed, never the result
+            return c0           # same map: the cell size only steers speed, never the result
     elif r:
-        c0 = float(r)
+        c0 = float(r) * (1.0 + 1e-6)
     else:
-        c0 = max(max(h - l for l, h in zip(lo, hi)) / 256.0, 1e-9)
+        c0 = max(max(ext) / 256.0, 1e-9)
     # a disc of radius c on a surface with `occ` points per c^2 holds pi * occ points; the mean occupancy is dominated
-    # by sparse cells (a typical QUERY sits in a cell 2x as full), measured optimum on lidar maps: occ ~ 0.3 k
-    target = max(float(os.environ.get('DC_KNN_OCC', 0.3)) * k, 2.0)
+    # by sparse cells (a typical QUERY sits in a cell 2x as full)
+    target = max(float(occ_env) * k, 2.0)
     for _ in range(4):
         occ = SortedMap.occupancy_of(points, lo, hi, c0)
         if 0.8 * target <= occ <= 1.25 * target:
             break
         c0 = c0 * min(max(math.sqrt(target / occ), 1.0 / 8.0), 8.0)
         if r and c0 > r:
-            c0 = float(r)
+            c0 = float(r) * (1.0 + 1e-6)      # a hair above r: one ring always covers r
             break
-    _cell_hint[hint_key] = (points.shape[0], c0, os.environ.get('DC_KNN_OCC', '0.3'))
+    _cell_hint[hint_key] = (points.shape[0], c0, occ_env, ext)
     return c0
+
+
+def clear_cell_hints():
+    """Forget the cell sizes remembered from earlier searches (the next search estimates its own: "cold" search)."""
+    _cell_hint.clear()
 
 
 def search(points, query=None, k=None, r=None, cell=None):
@@ -353,8 +364,13 @@ def search(points, query=None, k=None, r=None, cell=None):
         k = int(k)
         sp = torch.arange(ns + 1, dtype=torch.int64, device=dev) * (L.SLICE * k)
         idx = torch.empty(max(ns * L.SLICE * k, 1), dtype=torch.int32, device=dev)
-        L.call('dc_knn', L.ptr(smap.P), L.ptr(smap.keys), n, L.ptr(Q), L.ptr(qkeys), nq, spec, L.ptr(smap.cell_start),
-               k, float(r) if r else 0.0, L.ptr(idx), None, st)
+        if k <= 128 and os.environ.get('DC_KNN', 'cells') != 'thread':
+            # one warp per occupied cell; the few queries it cannot decide in fp32 go through the thread kernel inside
+            L.call_with_temp('dc_knn_cells', dev, L.ptr(smap.P), L.ptr(smap.keys), n, L.ptr(Q), L.ptr(qkeys), nq, spec,
+                             L.ptr(smap.cell_start), k, float(r) if r else 0.0, L.ptr(idx), after=(st,))
+        else:
+            L.call('dc_knn', L.ptr(smap.P), L.ptr(smap.keys), n, L.ptr(Q), L.ptr(qkeys), nq, spec, L.ptr(smap.cell_start),
+                   k, float(r) if r else 0.0, L.ptr(idx), None, st)
         g = Graph(smap, sp, idx, nq, k, q_order=qorder, ell_d2=None, mode='knn', symmetric=False, k=k, r=r)
         g._Q = None if self_query else Q
         return g

@@ -14,7 +14,7 @@ import torch
 from . import _lib as _L
 from .config import NeighborhoodType
 from .depth_cloud import DepthCloud
-from .filters import (filter_depth, filter_eigenvalue_ratios, filter_eigenvalues, filter_shadow_points,
+from .filters import (feature_mask, filter_depth, filter_eigenvalue_ratios, filter_eigenvalues, filter_shadow_points,
                       filter_valid_neighbors, within_bounds)
 from .fused import StepState, model_kind_of, scan_table
 from .graph import Graph, SortedMap, search
@@ -149,14 +149,21 @@ class GlobalCloud(DepthCloud):
         return not any(f in self.__dict__ for f in ('vps', 'dirs', 'depth'))
 
     def step_state(self):
-        key = tuple((id(c), c.depth.data_ptr(), c.dirs.data_ptr(),
-                     None if c.inc_angles is None else c.inc_angles.data_ptr(),
-                     None if c.mask is None else (c.mask.data_ptr(), c.mask._version)) for c in self._scans)
+        """The packed scan records are a snapshot of the scans' tensors: the cache entry is valid only for the very
+        same tensor objects at the same version (in-place edits bump `_version`), and it keeps strong references to
+        them so that neither `id()` nor device addresses can be recycled while it lives."""
+        tensors = []
+        for c in self._scans:
+            tensors += [c.depth, c.dirs, c.vps, c.inc_angles, c.mask]
+        key = tuple(None if t is None else (t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
         cache = self._graph._step_cache
-        if key not in cache:
+        st = cache.get(key)
+        if st is None or len(st._keyed) != len(tensors) or any(a is not b for a, b in zip(st._keyed, tensors)):
             cache.clear()
-            cache[key] = StepState(self._graph, self._scans)
-        return cache[key]
+            st = StepState(self._graph, self._scans)
+            st._keyed = tensors
+            cache[key] = st
+        return st
 
 
 def filtered_cloud(cloud, cfg):
@@ -183,15 +190,13 @@ def local_feature_cloud(cloud, cfg):
         cloud.update_dir_neighbors(angle=cfg.shadow_neighborhood_angle)
         cloud = filter_shadow_points(cloud, list(cfg.shadow_angle_bounds), log=cfg.log_filters)
     cloud.update_all(k=cfg.nn_k, r=cfg.nn_r)
-    if cfg.eigenvalue_bounds:
-        if cloud.mask is None:
-            cloud.mask = torch.ones((len(cloud),), dtype=torch.bool, device=cloud.device())
-        cloud.mask = cloud.mask & filter_eigenvalues(cloud, cfg.eigenvalue_bounds, only_mask=True, log=cfg.log_filters)
-    if cfg.eigenvalue_ratio_bounds:
-        if cloud.mask is None:
-            cloud.mask = torch.ones((len(cloud),), dtype=torch.bool, device=cloud.device())
-        cloud.mask = cloud.mask & filter_eigenvalue_ratios(cloud, cfg.eigenvalue_ratio_bounds, only_mask=True,
-                                                           log=cfg.log_filters)
+    if cfg.eigenvalue_bounds or cfg.eigenvalue_ratio_bounds:
+        # every bound of the configuration in one launch (the reference: one compare + one AND per bound, :53-62)
+        cloud.mask = feature_mask(cloud, eigenvalue_bounds=cfg.eigenvalue_bounds,
+                                  eigenvalue_ratio_bounds=cfg.eigenvalue_ratio_bounds, mask=cloud.mask)
+        if cfg.log_filters:
+            filter_eigenvalues(cloud, cfg.eigenvalue_bounds, only_mask=True, log=True)
+            filter_eigenvalue_ratios(cloud, cfg.eigenvalue_ratio_bounds, only_mask=True, log=True)
     return cloud
 
 
@@ -221,14 +226,15 @@ def global_cloud(clouds=None, model=None, poses=None, pose_corrections=None, dat
 
 def global_cloud_mask(cloud, mask, cfg):
     """Mask of points used by the loss (preproc.py:122-164)."""
-    if mask is None:
-        mask = torch.ones((len(cloud),), dtype=torch.bool, device=cloud.device())
-    if cfg.min_valid_neighbors:
-        mask = mask & filter_valid_neighbors(cloud, min=cfg.min_valid_neighbors, only_mask=True, log=cfg.log_filters)
-    if cfg.eigenvalue_bounds:
-        mask = mask & filter_eigenvalues(cloud, bounds=cfg.eigenvalue_bounds, only_mask=True, log=cfg.log_filters)
-    if cfg.eigenvalue_ratio_bounds:
-        mask = mask & filter_eigenvalue_ratios(cloud, bounds=cfg.eigenvalue_ratio_bounds, only_mask=True, log=cfg.log_filters)
+    # neighbour count, eigenvalue and eigenvalue-ratio bounds: one launch (the reference: :130-142, a compare and an
+    # AND per bound)
+    mask = feature_mask(cloud, eigenvalue_bounds=cfg.eigenvalue_bounds, eigenvalue_ratio_bounds=cfg.eigenvalue_ratio_bounds,
+                        min_valid_neighbors=cfg.min_valid_neighbors, mask=mask)
+    if cfg.log_filters:
+        if cfg.min_valid_neighbors:
+            filter_valid_neighbors(cloud, min=cfg.min_valid_neighbors, only_mask=True, log=True)
+        filter_eigenvalues(cloud, bounds=cfg.eigenvalue_bounds, only_mask=True, log=True)
+        filter_eigenvalue_ratios(cloud, bounds=cfg.eigenvalue_ratio_bounds, only_mask=True, log=True)
     if cfg.dir_dispersion_bounds:
         mask = mask & within_bounds(cloud.dir_dispersion(), bounds=cfg.dir_dispersion_bounds)
     if cfg.vp_dispersion_bounds:

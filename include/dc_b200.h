@@ -103,13 +103,23 @@ int dc_radius_fill(const void* P, const uint64_t* pkeys, int64_t n, const void* 
 /* kNN (r <= 0) or kNN within r (strict <, like cKDTree's distance_upper_bound): fixed-width ELL
  * (slice_ptr[t] = 32*k*t) holding the k nearest of every query in NO particular order (the step kernels
  * only need the set); ell_d2 (optional) receives the squared distances.  Exact ties at the k-th distance
- * are broken by the smaller sorted-space index. */
+ * are broken by the smaller ORIGINAL index (the tag of the map record), so the result does not depend on
+ * the cell size.  One query per thread: the general path (any k, any density); dc_knn_cells is the fast one. */
 int dc_knn(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
            const dc_grid_spec* spec_host, const int32_t* cell_start, int k, double r, int32_t* ell_idx, double* ell_d2,
            void* stream);
-/* order every kNN row by (d^2, index) in place: cKDTree.query returns distance-sorted rows
- * (nearest_neighbors.py:48); needed only when the reference layout is exported */
-int dc_knn_sort_rows(int k, int32_t* ell_idx, double* ell_d2, int64_t nq, void* stream);
+/* The same search, one WARP per occupied query cell (the fast path for k <= 128): the candidate block of a cell is
+ * staged once in registers as fp32 offsets from the cell centre, the cell's queries are streamed through it with a
+ * shared-memory histogram select, and every query whose fp32 classification is not provably the fp64 one (plus cells
+ * whose block exceeds the register slots or needs more than four rings) is finished by the fp64 one-thread-per-query
+ * kernel of dc_knn.  Same result as dc_knn bit for bit.  Replaces cKDTree.query (nearest_neighbors.py:48-49).
+ * temp: 64 + 12 nq bytes + select scratch (two-phase size query). */
+int dc_knn_cells(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
+                 const dc_grid_spec* spec_host, const int32_t* cell_start, int k, double r, int32_t* ell_idx, void* temp,
+                 size_t* temp_bytes, void* stream);
+/* order every kNN row by (d^2, original index = tag of the map record) in place: cKDTree.query returns
+ * distance-sorted rows (nearest_neighbors.py:48); needed only when the reference layout is exported */
+int dc_knn_sort_rows(const void* P, int64_t n, int k, int32_t* ell_idx, double* ell_d2, int64_t nq, void* stream);
 /* squared distances of a kNN graph recomputed from the records (bit-identical to the ones the selection
  * compared); the training path calls dc_knn with ell_d2 == NULL and never needs them */
 int dc_knn_distances(const void* P, const void* Q, int k, const int32_t* ell_idx, int64_t nq, double* ell_d2,
@@ -191,6 +201,16 @@ int dc_step_forward(const void* points, const uint32_t* rec_meta, int64_t n, con
                     const int32_t* ell_idx, int loss_kind, int flags, double* loss_pp, double* stash, double* eigvals,
                     double* loss_sum, void* partials, size_t partials_bytes, void* stream);
 
+/* passes B + C1 in ONE kernel, for the mean / sum reductions (no DC_FLAG_RAW): the upstream gradient of every loss
+ * term is then a single scalar that dc_step_chain's caller applies afterwards, so the thread that has just finished the
+ * eigen epilogue walks its index column again and adds A_i (p_j - m_i) to g_sorted32[j] (float32 [n,4], SORTED space,
+ * zeroed inside this call) with one 16-byte vector reduction per edge.  No stash, no second read of the index array
+ * from HBM.  Replaces update_mean/cov/eig + loss (depth_cloud.py:291-399, loss.py:216-370) AND the neighbour part of
+ * loss.backward() (train.py:306-312).  loss_pp may be NULL. */
+int dc_step_forward_scatter(const void* points, const uint32_t* rec_meta, int64_t n, const int64_t* slice_ptr,
+                            const int32_t* ell_idx, int loss_kind, int flags, double* loss_pp, void* g_sorted32,
+                            double* loss_sum, void* partials, size_t partials_bytes, void* stream);
+
 /* pass C1: g_j = sum_{i : j in N(i)} u_i A_i (p_j - m_i), a gather over the TRANSPOSED graph (sorted space),
  * written to the point's ORIGINAL row: g_out fp64 [n,3].  upstream_pp: optional per-point upstream gradient
  * in sorted space (NULL = 1 for every row).  No atomics. */
@@ -231,6 +251,15 @@ int dc_pose_compose_backward(const double* poses, const double* deltas, int n_sc
  * ------------------------------------------------------------------------------------------- */
 int dc_features(const void* points, int dtype, int64_t n, const int64_t* neighbors, const float* weights, int K,
                 void* mean, void* cov, void* stream);
+/* Feature masks in one launch: filter_valid_neighbors / filter_eigenvalue(s) / filter_eigenvalue_ratio(s) /
+ * within_bounds (filters.py:85-113, 184-254), as composed by local_feature_cloud (preproc.py:53-62) and
+ * global_cloud_mask (preproc.py:130-142).  vals: [n, stride] values of `dtype` (eigvals: stride 3; a scalar field such
+ * as a dispersion: stride 1), bounds_host: n_bounds (<= 16) records {kind, a, b, lo, hi} of doubles on the HOST with
+ * kind 0: lo <= vals[i,a] <= hi, kind 1: lo <= vals[i,a] / vals[i,b] <= hi; bounds are inclusive, compared in `dtype`
+ * like torch does, -inf / +inf / NaN disable a side; valid_counts (int64 [n], may be NULL) >= min_valid.
+ * init != 0: mask = result; init == 0: mask &= result.  mask: uint8 / bool [n]. */
+int dc_feature_mask(const void* vals, int dtype, int64_t n, int stride, const double* bounds_host, int n_bounds,
+                    const int64_t* valid_counts, int64_t min_valid, int init, uint8_t* mask, void* stream);
 int dc_features_backward(const void* points, int dtype, int64_t n, const int64_t* neighbors, const float* weights, int K,
                          const void* gmean, const void* gcov, void* gpoints, void* stream);
 int dc_eigh3(const void* cov, int dtype, int64_t n, void* eigvals, void* eigvecs, void* stream);
