@@ -299,9 +299,10 @@ def run_ours(args):
     # ---- full-size parity property: the gradients of the timed path (fp32 vector-reduction scatter on large maps)
     # against the deterministic fp64 gather form on the same graph and inputs
     gw_fast, gd_fast = model.w.grad.detach().clone(), deltas.grad.detach().clone()
-    os.environ['DC_BACKWARD'] = 'gather'
+    from depth_correction_b200 import fused as _fused
+    _fused.set_backward_form('gather')
     one_step(dc, clouds, poses, deltas, model, cfg, ns=ns, local=local)
-    os.environ.pop('DC_BACKWARD')
+    _fused.set_backward_form('auto')
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
     grad_check = {'w_grad_rel_err_vs_fp64_gather': rel(gw_fast, model.w.grad), 'pose_grad_rel_err_vs_fp64_gather': rel(gd_fast, deltas.grad)}
     ns.graph._transposed = None          # (release the reverse lists again)

@@ -17,6 +17,7 @@ from .parallel import LocalMap, SlabPartitioner, distributed_quantile, reduce_st
 from .filters import (feature_mask, filter_depth, filter_eigenvalue, filter_eigenvalue_ratio, filter_eigenvalue_ratios,
                       filter_eigenvalues, filter_shadow_points, filter_valid_neighbors, within_bounds)
 from .filters_grid import filter_grid
+from .fused import set_backward_form
 from .preproc import (GlobalCloud, Neighborhoods, compute_neighborhood_features, establish_neighborhoods,
                       filtered_cloud, global_cloud, global_cloud_mask, local_feature_cloud, offset_cloud)
 from .eval import create_corrected_poses, eval_loss_clouds, initialize_pose_corrections

@@ -26,11 +26,14 @@
 // (d2, original index) lexicographic order.  The original index (dc_point.tag) -- not the position in the cell-sorted
 // map -- breaks exact ties, so the selected set does not depend on the cell size.  The tag is only loaded when two
 // squared distances are bit-equal; j >= n stands for "no candidate" and sorts last.
-__device__ __forceinline__ long long knn_tag(const dc_point* __restrict__ P, int64_t n, int j) {
-  return (j >= 0 && (int64_t)j < n) ? P[j].tag : (j < 0 ? -1LL : 0x7fffffffffffffffLL);
+__device__ __noinline__ bool knn_tie(const dc_point* __restrict__ P, int64_t n, int ja, int jb) {
+  // out of line: exact ties are rare, and inlined the 64-bit tag loads cost the scan loops eight registers
+  const long long ta = (ja >= 0 && (int64_t)ja < n) ? P[ja].tag : (ja < 0 ? -1LL : 0x7fffffffffffffffLL);
+  const long long tb = (jb >= 0 && (int64_t)jb < n) ? P[jb].tag : (jb < 0 ? -1LL : 0x7fffffffffffffffLL);
+  return ta < tb;
 }
 __device__ __forceinline__ bool knn_less(const dc_point* __restrict__ P, int64_t n, double a, int ja, double b, int jb) {
-  return a < b || (a == b && knn_tag(P, n, ja) < knn_tag(P, n, jb));
+  return a < b || (a == b && knn_tie(P, n, ja, jb));
 }
 
 __device__ __forceinline__ int knn_bin(double d2, double scale) {
@@ -237,7 +240,7 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
   }
 }
 
-__global__ void __launch_bounds__(KNN_THREADS)
+__global__ void __launch_bounds__(KNN_THREADS, 8)
 knn_thread_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
                   const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
                   const int32_t* __restrict__ cell_start, int k, double r2cap, int max_ring,
@@ -313,15 +316,20 @@ extern "C" int dc_knn(const void* P, const uint64_t* pkeys, int64_t n, const voi
 // list that the one-thread-per-query fp64 kernel above (knn_thread_query) finishes.  Both paths select by
 // (fp64 d2, original index), so the union is bit-identical to the thread path alone.
 // ---------------------------------------------------------------------------------------------
-#define KT_WARPS 4
+#define KT_WARPS 1                 // one warp per block: everything derived from blockIdx / shared memory at uniform
+                                   // addresses is warp-uniform FOR THE COMPILER, so the warp collectives need no
+                                   // convergence wrappers (BSSY / WARPSYNC / ENDCOLLECTIVE around every shuffle)
 #define KT_THREADS (KT_WARPS * 32)
 #define KT_NB 8                    // register slots per lane: blocks of up to 256 candidates
 #define KT_CMAX (KT_NB * 32)
-#define KT_MMAX 4
-#define KT_ROWCAP 96               // >= (2 KT_MMAX + 1)^2 rows
-#define KT_LIST 32
+#define KT_MMAX 16                 // rings the cell kernel grows to (r / cell in practice)
+#define KT_ROWCAP 96               // non-empty rows of a block (more: fp64 path)
+#define KT_TAIL 8                  // candidates of the boundary bin kept per query (more: fp64 path)
+#define KT_HSTRIDE 67              // words per histogram row: bins 0..62, dummy 63, "below" 64; odd: lanes = queries read conflict-free
+#define KT_MIN_BLOCKS 16           // resident warps per SM the register allocation is held to
 #define KT_GRAB 8                  // cells fetched per atomic
-#define KT_WARP_WORDS (KT_CMAX + KT_ROWCAP + 100 + 64 + KT_LIST + KT_LIST)
+#define KT_LIST_WORDS (3 * KT_NB * 32)   // lane-private emit lists (front idx, tail idx, tail z); aliases the staging table
+#define KT_WARP_FIXED (KT_LIST_WORDS + KT_ROWCAP + 100 + 128 + 32 * KT_TAIL + 8)
 
 struct kt_ring {
   float sc;    // bins per unit of d2: 63 / (usable bound)
@@ -332,16 +340,16 @@ struct kt_ring {
 };
 struct kt_params {
   kt_ring ring[KT_MMAX + 1];
-  int mmax, k, pop_min, tile_stride;
+  int mmax, k, pop_min, tile_stride, warp_words;
 };
 
 #define KT_FULL 0xffffffffu
 
 // Non-empty rows of the block of ring m around cell (c0, c1, c2): s_rlo[i] = first sorted position, s_rpre[i] =
-// candidates before row i; returns the candidate count, n_rows by reference.
+// candidates before row i; returns the candidate count.
 __device__ __forceinline__ int kt_rows(const dc_grid& g, const uint64_t* __restrict__ pkeys, int64_t n,
                                        const int32_t* __restrict__ cell_start, int c0, int c1, int c2, int m, int lane,
-                                       int* s_rlo, int* s_rpre, int& n_rows) {
+                                       int* s_rlo, int* s_rpre, int* s_ctl) {
   const int w = 2 * m + 1, R = w * w;
   const unsigned lt = (1u << lane) - 1u;
   int base_rows = 0, base_cnt = 0;
@@ -360,16 +368,17 @@ __device__ __forceinline__ int kt_rows(const dc_grid& g, const uint64_t* __restr
     const unsigned ne = __ballot_sync(KT_FULL, cnt > 0);
     if (cnt > 0) {
       const int pos = base_rows + __popc(ne & lt);
-      s_rlo[pos] = lo;
-      s_rpre[pos] = base_cnt + inc - cnt;
+      if (pos < KT_ROWCAP) {
+        s_rlo[pos] = lo;
+        s_rpre[pos] = base_cnt + inc - cnt;
+      }
     }
     base_rows += __popc(ne);
     base_cnt += __shfl_sync(KT_FULL, inc, 31);
   }
-  if (lane == 0) s_rpre[base_rows] = base_cnt;
+  if (lane == 0) { s_rpre[base_rows < KT_ROWCAP ? base_rows : KT_ROWCAP] = base_cnt; s_ctl[1] = base_cnt; s_ctl[2] = base_rows; }
   __syncwarp();
-  n_rows = base_rows;
-  return base_cnt;
+  return s_ctl[1];      // read back from a uniform shared address: a warp-uniform value as far as the compiler can tell
 }
 
 __device__ __forceinline__ float kt_warp_max(float v) {
@@ -385,35 +394,125 @@ __device__ __forceinline__ void kt_push(unsigned mask, int cs, int ring, int lan
   }
 }
 
-__global__ void __launch_bounds__(KT_THREADS)
+// ---- inner loops.  The block's candidates sit in register slots 0 .. nb-1 of every lane; the slot loops are Duff's
+// devices: ONE straight-line copy of the eight slot bodies, entered at slot nb-1 (a switch with fall-through on the
+// warp-uniform nb), so that short blocks do not pay for empty slots, the independent FFMA chains of the slots overlap,
+// and the hot code stays small (with separate unrolled variants per block size the kernel was instruction-cache bound:
+// 8.7 no-instruction stall cycles per issue against 0.4).
+
+// phase 1 slot: histogram of z = zsc * (|c|^2 - 2 q.c) + zoff.  Every lane issues its atomic (ptxas turns a predicated
+// shared atomic into a branch with convergence bookkeeping): out-of-range candidates count in the dummy word 63; in a
+// refine pass (second level inside one bin) candidates below the bin count in word 64.
+#define KT_HIST_SLOT(b)                                                                         \
+  {                                                                                             \
+    float s_ = fmaf(ax, cx[b], cw[b]);                                                          \
+    s_ = fmaf(ay, cy[b], s_);                                                                   \
+    s_ = fmaf(az, cz[b], s_);                                                                   \
+    const float z_ = fmaf(s_, zsc, zoff);                                                       \
+    unsigned bin_ = min(__float2uint_rz(z_), 63u);                                              \
+    if (REFINE) bin_ = z_ < 0.f ? 64u : bin_;                                                   \
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hbase + 4u * bin_), "r"(1u));             \
+  }
+
+template <bool REFINE>
+__device__ __forceinline__ void kt_hist(int nb, const float (&cx)[KT_NB], const float (&cy)[KT_NB], const float (&cz)[KT_NB],
+                                        const float (&cw)[KT_NB], float ax, float ay, float az, float zsc, float zoff,
+                                        unsigned hbase) {
+  // slot pairs: two independent chains per basic block (a case label ends the scheduler's window)
+  switch ((nb + 1) >> 1) {
+    case 4: KT_HIST_SLOT(7) KT_HIST_SLOT(6)
+    case 3: KT_HIST_SLOT(5) KT_HIST_SLOT(4)
+    case 2: KT_HIST_SLOT(3) KT_HIST_SLOT(2)
+    case 1: KT_HIST_SLOT(1) KT_HIST_SLOT(0)
+    default: break;
+  }
+}
+
+// phase 3 slot: z < thr -> the lane's private front list; thr <= z < thr_hi -> its private tail list (index and z).
+// No collectives and no atomics here; the lists are compacted into the query's row once per query.
+#define KT_EMIT_SLOT(b)                                                                         \
+  {                                                                                             \
+    float s_ = fmaf(ax, cx[b], cw[b]);                                                          \
+    s_ = fmaf(ay, cy[b], s_);                                                                   \
+    s_ = fmaf(az, cz[b], s_);                                                                   \
+    const float z_ = fmaf(s_, zsc, zoff);                                                       \
+    if (z_ < thr) {                                                                             \
+      *pf = cj[b];                                                                              \
+      pf += 32;                                                                                 \
+    } else if (z_ < thr_hi) {                                                                   \
+      pt[0] = cj[b];                                                                            \
+      pt[KT_NB * 32] = __float_as_int(z_);                                                      \
+      pt += 32;                                                                                 \
+    }                                                                                           \
+  }
+
+// phase 2 (lanes = queries x histogram segments): first bin b with base + sum(bins <= b) >= k for every query row that
+// `want` selects; results {n_in, b, count before b, count of b} -> s_res[4 qi ..].  base = word 63 of the row when
+// `refined` (candidates below the refined bin), else 0; bins 0 .. 62 are summed.
+__device__ __forceinline__ void kt_scan(const int* s_u, int* s_res, int Gc, int k, int lpq, int sub, int qi, int seg,
+                                        bool want, bool refined) {
+  int S = 0, base = 0;
+  const int* hrow = s_u + qi * KT_HSTRIDE + sub * seg;
+  const int nbin = sub * seg + seg > 63 ? 63 - sub * seg : seg;       // the last segment stops at bin 62
+  const bool act = want && qi < Gc;
+  if (act) {
+    for (int b = 0; b < nbin; ++b) S += hrow[b];
+    if (refined) base = s_u[qi * KT_HSTRIDE + 64];
+  }
+  int inc = S;
+  for (int d = 1; d < lpq; d <<= 1) {
+    const int t = __shfl_up_sync(KT_FULL, inc, d, lpq);
+    if (sub >= d) inc += t;
+  }
+  inc += base;
+  const int n_in = __shfl_sync(KT_FULL, inc, lpq - 1, lpq);
+  const int E = inc - S;
+  if (act) {
+    if (n_in < k) {
+      if (sub == 0) { s_res[4 * qi] = n_in; s_res[4 * qi + 1] = 63; s_res[4 * qi + 2] = n_in; s_res[4 * qi + 3] = 0; }
+    } else if (E < k && E + S >= k) {
+      int acc = E, b = 0, h = hrow[0];
+      while (acc + h < k) { acc += h; h = hrow[++b]; }
+      s_res[4 * qi] = n_in; s_res[4 * qi + 1] = sub * seg + b; s_res[4 * qi + 2] = acc; s_res[4 * qi + 3] = h;
+    } else if (E >= k && sub == 0) {
+      // (refined rows only) k candidates already lie below the refined bin: cannot happen, flagged for the fp64 path
+      s_res[4 * qi] = n_in; s_res[4 * qi + 1] = 0; s_res[4 * qi + 2] = 0; s_res[4 * qi + 3] = 1 << 20;
+    }
+  }
+}
+
+#define KT_FB_AMBIGUOUS 1     // gap between the last selected and the first rejected candidate below the fp32 uncertainty
+#define KT_FB_CROWDED 2       // more than KT_TAIL candidates share the (refined) boundary bin: exact ties / duplicates
+#define KT_FB_RING 3          // needs more rings than KT_MMAX, or the ring table entry is unusable
+
+__global__ void __launch_bounds__(KT_THREADS, KT_MIN_BLOCKS)
 knn_cell_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
                 const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
                 const int32_t* __restrict__ cell_start, kt_params prm, const int32_t* __restrict__ task_start,
                 const int32_t* __restrict__ n_tasks_p, int32_t* counters, int2* fb_list, int32_t* __restrict__ ell_idx) {
   extern __shared__ __align__(16) int kt_smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x;
   const int k = prm.k, ts = prm.tile_stride;
-  int* s_idx = kt_smem + wib * (KT_WARP_WORDS + 32 * ts);
-  int* s_rlo = s_idx + KT_CMAX;
+  int* s_list = kt_smem;                              // lane-private emit lists; during staging: sorted positions
+  int* s_rlo = s_list + KT_LIST_WORDS;                // row table of the block
   int* s_rpre = s_rlo + KT_ROWCAP;
-  unsigned* s_hist = (unsigned*)(s_rpre + 100);
-  float* s_lv = (float*)(s_hist + 64);
-  int* s_ls = (int*)(s_lv + KT_LIST);
-  int* s_tile = s_ls + KT_LIST;
+  int* s_res = s_rpre + 100;                          // scan results [32][4]; during emit: row counters [32][2]
+  float* s_sv = (float*)(s_res + 128);                // z of the boundary-bin candidates [32][KT_TAIL]
+  int* s_ctl = (int*)(s_sv + 32 * KT_TAIL);           // control words published by one lane, read by all
+  int* s_u = s_ctl + 8;                               // histograms [32][KT_HSTRIDE], later the output tile [32][ts]
   // ring table in shared memory: indexing the kernel parameter with a run-time ring would copy it to local memory
   __shared__ kt_ring s_ring[KT_MMAX + 1];
-#pragma unroll
-  for (int i = 0; i <= KT_MMAX; ++i)
-    if (threadIdx.x == i) s_ring[i] = prm.ring[i];
+  for (int i = lane; i <= KT_MMAX; i += 32) s_ring[i] = prm.ring[i < KT_MMAX ? i : KT_MMAX];
   __syncthreads();
   const int n_tasks = *n_tasks_p;
   const unsigned lt = (1u << lane) - 1u;
   int task_next = 0, task_end = 0;
   for (;;) {
     if (task_next >= task_end) {
-      int t0 = 0;
-      if (lane == 0) t0 = atomicAdd(&counters[0], KT_GRAB);
-      t0 = __shfl_sync(KT_FULL, t0, 0);
+      __syncwarp();
+      if (lane == 0) s_ctl[0] = atomicAdd(&counters[0], KT_GRAB);
+      __syncwarp();
+      const int t0 = s_ctl[0];
       if (t0 >= n_tasks) break;
       task_next = t0;
       task_end = t0 + KT_GRAB < n_tasks ? t0 + KT_GRAB : n_tasks;
@@ -421,8 +520,18 @@ knn_cell_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pke
     const int task = task_next++;
     const int s0 = task_start[task];
     const int s1 = task + 1 < n_tasks ? task_start[task + 1] : (int)nq;
+    // cell of the task from its first query (the very computation that produced the sort key, without the 64-bit
+    // divisions of decoding the key)
     int c0, c1, c2;
-    dc_key_coords(g, qkeys[s0], c0, c1, c2);
+    {
+      const dc_point p0 = dc_ld_point(Q + s0);
+      const double a0 = g.ax[0] == 0 ? p0.x : (g.ax[0] == 1 ? p0.y : p0.z), a1 = g.ax[1] == 0 ? p0.x : (g.ax[1] == 1 ? p0.y : p0.z),
+                   a2 = g.ax[2] == 0 ? p0.x : (g.ax[2] == 1 ? p0.y : p0.z);
+      // identical arithmetic to dc_cell_coords (which indexes p[ax[a]] and would put p in local memory here)
+      c0 = dc_clampi((int)floor((a0 - g.org[0]) * g.inv_cell), 0, g.d[0] - 1);
+      c1 = dc_clampi((int)floor((a1 - g.org[1]) * g.inv_cell), 0, g.d[1] - 1);
+      c2 = dc_clampi((int)floor((a2 - g.org[2]) * g.inv_cell), 0, g.d[2] - 1);
+    }
     // centre of the query cell = origin of the fp32 offsets (xyz order)
     const double o0 = g.org[0] + ((double)c0 + 0.5) * g.cell, o1 = g.org[1] + ((double)c1 + 0.5) * g.cell,
                  o2 = g.org[2] + ((double)c2 + 0.5) * g.cell;
@@ -431,11 +540,12 @@ knn_cell_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pke
     const double oz = g.ax[0] == 2 ? o0 : (g.ax[1] == 2 ? o1 : o2);
 
     float cx[KT_NB], cy[KT_NB], cz[KT_NB], cw[KT_NB];
-    int staged_m = 0, m_start = 0, C = 0, nb = 0;
+    int cj[KT_NB];
+    int rows_m = 0, staged_sb = -1, m_start = 0, C = 0;
+
     for (int cs = s0; cs < s1; cs += 32) {
       const int Gc = s1 - cs < 32 ? s1 - cs : 32;
       unsigned pend = Gc == 32 ? KT_FULL : ((1u << Gc) - 1u);
-      unsigned done = 0u;
       float qax = 0.f, qay = 0.f, qaz = 0.f, qk = 0.f;
       if (lane < Gc) {
         const dc_point pq = dc_ld_point(Q + cs + lane);
@@ -443,193 +553,240 @@ knn_cell_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pke
         qax = -2.f * x; qay = -2.f * y; qaz = -2.f * z;
         qk = fmaf(z, z, fmaf(y, y, x * x));
       }
+      // lanes <-> (query, segment of its histogram) for the scans: qw = pow2 >= Gc queries x lpq lanes each
+      const int qw = Gc <= 1 ? 1 : (1 << (32 - __clz(Gc - 1)));
+      const int lpq = 32 / qw, sub = lane & (lpq - 1), qi = lane / lpq, seg = 64 / lpq;
       int m = m_start ? m_start : 1;
       while (pend) {
-        if (staged_m != m) {
-          int n_rows;
-          C = kt_rows(g, pkeys, n, cell_start, c0, c1, c2, m, lane, s_rlo, s_rpre, n_rows);
+        if (rows_m != m) {
+          C = kt_rows(g, pkeys, n, cell_start, c0, c1, c2, m, lane, s_rlo, s_rpre, s_ctl);
           if (m_start == 0) {
             // first visit of this cell: skip rings whose block cannot hold k neighbours with some margin
             while (C < prm.pop_min && m < prm.mmax) {
               ++m;
-              C = kt_rows(g, pkeys, n, cell_start, c0, c1, c2, m, lane, s_rlo, s_rpre, n_rows);
+              C = kt_rows(g, pkeys, n, cell_start, c0, c1, c2, m, lane, s_rlo, s_rpre, s_ctl);
             }
             m_start = m;
           }
-          staged_m = m;
-          nb = (C + 31) >> 5;
-          if (C <= KT_CMAX) {
-            int rho = 0;
-#pragma unroll
-            for (int b = 0; b < KT_NB; ++b) {
-              cx[b] = 0.f; cy[b] = 0.f; cz[b] = 0.f; cw[b] = 3.0e38f;
-              const int i = 32 * b + lane;
-              if (i < C) {
-                while (s_rpre[rho + 1] <= i) ++rho;
-                const int j = s_rlo[rho] + (i - s_rpre[rho]);
-                const dc_point p = dc_ld_point(P + j);
-                const float x = (float)(p.x - ox), y = (float)(p.y - oy), z = (float)(p.z - oz);
-                cx[b] = x; cy[b] = y; cz[b] = z;
-                cw[b] = fmaf(z, z, fmaf(y, y, x * x));
-                s_idx[i] = j;
-              }
-            }
-            __syncwarp();
-          }
+          rows_m = m;
+          staged_sb = -1;
         }
         const kt_ring rg = s_ring[m];
-        if (C > KT_CMAX || !rg.usable) {       // block too large for the register slots: fp64 thread path
-          kt_push(pend, cs, m, lane, counters, fb_list);
-          pend = 0u;
+        const int n_rows = s_ctl[2];
+        if (!rg.usable || n_rows > KT_ROWCAP) {
+          kt_push(pend, cs, (m < 255 ? m : 255) | (KT_FB_RING << 8), lane, counters, fb_list);
           break;
         }
-        unsigned still = 0u;
-        for (unsigned rem = pend; rem; rem &= rem - 1u) {
-          const int gq = __ffs(rem) - 1;
-          const float ax = __shfl_sync(KT_FULL, qax, gq), ay = __shfl_sync(KT_FULL, qay, gq),
-                      az = __shfl_sync(KT_FULL, qaz, gq);
-          // + dv: every v >= 0 (the self pair evaluates to a few ulps around 0); conservative for the bound
-          const float off = fmaf(__shfl_sync(KT_FULL, qk, gq), rg.sc, rg.dv);
-          __syncwarp();
-          s_hist[lane] = 0u;
-          s_hist[lane + 32] = 0u;
-          __syncwarp();
-          float v[KT_NB];
-#pragma unroll
-          for (int b = 0; b < KT_NB; ++b) {
-            v[b] = 3.0e38f;
-            if (b < nb) {
-              float s = fmaf(ax, cx[b], cw[b]);
-              s = fmaf(ay, cy[b], s);
-              s = fmaf(az, cz[b], s);
-              v[b] = fmaf(s, rg.sc, off);
-              if (v[b] < 63.f) atomicAdd(&s_hist[(int)v[b]], 1u);
-            }
-          }
-          __syncwarp();
-          const uint2 hh = *(const uint2*)&s_hist[2 * lane];
-          const int hsum = (int)(hh.x + hh.y);
-          int inc = hsum;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(KT_FULL, inc, d);
-            if (lane >= d) inc += t;
-          }
-          const int n_in = __shfl_sync(KT_FULL, inc, 31);
-          float thr = 63.f;
-          int t_take = 0, cnt1 = 0;
-          const bool rl = n_in < k;
-          if (rl) {
-            if (!rg.rlim) {               // the block does not reach far enough: next ring
-              still |= 1u << gq;
-              continue;
-            }
-          } else {
-            const unsigned mk = __ballot_sync(KT_FULL, inc >= k);
-            const int L = __ffs(mk) - 1;
-            const int e = __shfl_sync(KT_FULL, inc - hsum, L), a = __shfl_sync(KT_FULL, (int)hh.x, L),
-                      bb = __shfl_sync(KT_FULL, (int)hh.y, L);
-            int b1, c_lo;
-            if (e + a >= k) { b1 = 2 * L; c_lo = e; cnt1 = a; } else { b1 = 2 * L + 1; c_lo = e + a; cnt1 = bb; }
-            t_take = k - c_lo;
-            thr = (float)(cnt1 == t_take ? b1 + 1 : b1);
-          }
-          const bool take_all = rl || cnt1 == t_take;
-          // ---- emit sweep: everything below thr is a neighbour
-          int* trow = s_tile + gq * ts;
-          int cnt = 0;
-          float vmax = -1.f;
-#pragma unroll
-          for (int b = 0; b < KT_NB; ++b) {
-            if (b < nb) {
-              const bool in = v[b] < thr;
-              const unsigned mm = __ballot_sync(KT_FULL, in);
-              if (in) {
-                trow[cnt + __popc(mm & lt)] = s_idx[32 * b + lane];
-                vmax = fmaxf(vmax, v[b]);
-              }
-              cnt += __popc(mm);
-            }
-          }
-          bool amb = false;
-          if (take_all) {
-            if (rl) {
-              bool band = false;
-#pragma unroll
-              for (int b = 0; b < KT_NB; ++b) band |= (v[b] >= 63.f && v[b] < 63.f + rg.dr);
-              amb = __any_sync(KT_FULL, band);
-            } else {
-              amb = thr - kt_warp_max(vmax) <= rg.dv;     // the nearest rejected candidate has v >= thr
-            }
-          } else if (cnt1 > KT_LIST) {
-            amb = true;
-          } else {
-            // ---- the cnt1 candidates of the boundary bin: rank them, take the t_take smallest
-            int pos = 0;
-#pragma unroll
-            for (int b = 0; b < KT_NB; ++b) {
-              if (b < nb) {
-                const bool mb = v[b] >= thr && v[b] < thr + 1.f;
-                const unsigned mm = __ballot_sync(KT_FULL, mb);
-                if (mb) {
-                  const int p = pos + __popc(mm & lt);
-                  if (p < KT_LIST) { s_lv[p] = v[b]; s_ls[p] = 32 * b + lane; }
-                }
-                pos += __popc(mm);
-              }
-            }
+        const int nsb = (C + KT_CMAX - 1) / KT_CMAX;
+        // per-lane state of query `lane`.  Transform: z = zsc * s + zoff (level 1: z = v = 63 d2 / bound; + dv keeps
+        // every v >= 0: the self pair evaluates to a few ulps around 0; conservative for the bound)
+        float q_zsc = rg.sc, q_zoff = fmaf(qk, rg.sc, rg.dv), q_dv = rg.dv;
+        float q_thr = 63.f, q_hi = 63.f;
+        int q_clo = 0, q_cnt1 = 0, q_t = 0;
+        bool q_rl = false;
+        int q_status = 4;            // 0 ready, 1 needs a larger ring, 2 fp64 path, 3 refine the boundary bin, 4 not in this round
+        unsigned active = pend;      // queries of the current pass
+        unsigned ready = 0u, crowded = 0u, still = 0u;
+        // pass 0: level-1 histograms + scan; pass 1: second histogram level for crowded boundary bins (usually
+        // skipped); pass 2: emit.  ONE staging site and one loop nest for all passes keeps the code small.
+        for (int pass = 0; pass < 3; ++pass) {
+          if (pass < 2) {
+            if (active == 0u) continue;
             __syncwarp();
-            const bool have = lane < cnt1;
-            const float lv = have ? s_lv[lane] : 3.0e38f;
-            const int ls = have ? s_ls[lane] : 0x7fffffff;
-            int rank = 0;
-            for (int j = 0; j < cnt1; ++j) {
-              const float vj = __shfl_sync(KT_FULL, lv, j);
-              const int sj = __shfl_sync(KT_FULL, ls, j);
-              rank += (vj < lv || (vj == lv && sj < ls)) ? 1 : 0;
+            for (int i = lane; i < Gc * KT_HSTRIDE; i += 32) s_u[i] = 0;
+          } else {
+            active = ready;
+            __syncwarp();
+            s_res[lane] = 0;             // row counters: [2 g] front entries, [2 g + 1] boundary-bin candidates
+            s_res[lane + 32] = 0;
+          }
+          __syncwarp();
+          for (int t = 0; t < nsb; ++t) {
+            const int sb = pass == 2 ? nsb - 1 - t : t;       // the emit pass starts with the block staged last
+            if (staged_sb != sb) {
+              // ---- stage candidates [256 sb, 256 sb + 256) of the block into the register slots
+              __syncwarp();
+              const int w0 = KT_CMAX * sb, w1 = C < w0 + KT_CMAX ? C : w0 + KT_CMAX;
+              for (int r = 0; r < n_rows; ++r) {
+                const int pre = s_rpre[r], nxt = s_rpre[r + 1];
+                if (nxt <= w0 || pre >= w1) continue;
+                const int a = pre > w0 ? pre : w0, e = nxt < w1 ? nxt : w1, lo = s_rlo[r];
+                for (int i = a + lane; i < e; i += 32) s_list[i - w0] = lo + (i - pre);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int b = 0; b < KT_NB; ++b) {
+                cx[b] = 0.f; cy[b] = 0.f; cz[b] = 0.f; cw[b] = 3.0e38f; cj[b] = -1;
+                if (w0 + 32 * b + lane < w1) {
+                  const int j = s_list[32 * b + lane];
+                  const dc_point p = dc_ld_point(P + j);
+                  const float x = (float)(p.x - ox), y = (float)(p.y - oy), z = (float)(p.z - oz);
+                  cx[b] = x; cy[b] = y; cz[b] = z;
+                  cw[b] = fmaf(z, z, fmaf(y, y, x * x));
+                  cj[b] = j;
+                }
+              }
+              __syncwarp();
+              staged_sb = sb;
             }
-            const unsigned mt = __ballot_sync(KT_FULL, have && rank == t_take - 1);
-            const unsigned mn = __ballot_sync(KT_FULL, have && rank == t_take);
-            if (pos != cnt1 || mt == 0u || mn == 0u) {
-              amb = true;       // cannot happen (the two sweeps classify identically); fp64 path if it ever does
-            } else {
-              const float v_t = __shfl_sync(KT_FULL, lv, __ffs(mt) - 1), v_n = __shfl_sync(KT_FULL, lv, __ffs(mn) - 1);
-              amb = v_n - v_t <= rg.dv;
-              const bool chosen = have && rank < t_take;
-              const unsigned mc = __ballot_sync(KT_FULL, chosen);
-              if (chosen) trow[cnt + __popc(mc & lt)] = s_idx[ls];
-              cnt += __popc(mc);
+            const int left = C - KT_CMAX * sb;
+            const int nb = left >= KT_CMAX ? KT_NB : (left + 31) >> 5;
+            for (unsigned rem = active; rem; rem &= rem - 1u) {
+              const int gq = __ffs(rem) - 1;
+              const float ax = __shfl_sync(KT_FULL, qax, gq), ay = __shfl_sync(KT_FULL, qay, gq),
+                          az = __shfl_sync(KT_FULL, qaz, gq), zsc = __shfl_sync(KT_FULL, q_zsc, gq),
+                          zoff = __shfl_sync(KT_FULL, q_zoff, gq);
+              if (pass == 0) {
+                kt_hist<false>(nb, cx, cy, cz, cw, ax, ay, az, zsc, zoff, (unsigned)__cvta_generic_to_shared(s_u + gq * KT_HSTRIDE));
+              } else if (pass == 1) {
+                kt_hist<true>(nb, cx, cy, cz, cw, ax, ay, az, zsc, zoff, (unsigned)__cvta_generic_to_shared(s_u + gq * KT_HSTRIDE));
+              } else {
+                const float thr = __shfl_sync(KT_FULL, q_thr, gq), thr_hi = __shfl_sync(KT_FULL, q_hi, gq);
+                const int clo = __shfl_sync(KT_FULL, q_clo, gq);
+                int* const pf0 = s_list + lane;
+                int* const pt0 = s_list + KT_NB * 32 + lane;
+                int* pf = pf0;
+                int* pt = pt0;
+                switch ((nb + 1) >> 1) {
+                  case 4: KT_EMIT_SLOT(7) KT_EMIT_SLOT(6)
+                  case 3: KT_EMIT_SLOT(5) KT_EMIT_SLOT(4)
+                  case 2: KT_EMIT_SLOT(3) KT_EMIT_SLOT(2)
+                  case 1: KT_EMIT_SLOT(1) KT_EMIT_SLOT(0)
+                  default: break;
+                }
+                // compact the private lists into the query's row: front entries by a warp scan of the counts,
+                // the (rare) boundary-bin candidates by a counter
+                const int cfl = (int)(pf - pf0) >> 5, ctl = (int)(pt - pt0) >> 5;
+                int inc = cfl;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                  const int u = __shfl_up_sync(KT_FULL, inc, d);
+                  if (lane >= d) inc += u;
+                }
+                const int total = __shfl_sync(KT_FULL, inc, 31);
+                int* trow = s_u + gq * ts;
+                const int base = s_res[2 * gq];
+                int* dst = trow + base + inc - cfl;
+                for (int i = 0; i < cfl; ++i) dst[i] = pf0[32 * i];
+                if (ctl > 0) {
+                  for (int i = 0; i < ctl; ++i) {
+                    const int p = atomicAdd(&s_res[2 * gq + 1], 1);
+                    if (p < KT_TAIL) { trow[clo + p] = pt0[32 * i]; s_sv[gq * KT_TAIL + p] = __int_as_float(pt0[32 * i + KT_NB * 32]); }
+                  }
+                }
+                __syncwarp();
+                if (lane == 0) s_res[2 * gq] = base + total;
+              }
             }
           }
-          if (amb) {
-            kt_push(1u << gq, cs, m, lane, counters, fb_list);
-          } else {
-            for (int c = cnt + lane; c < k; c += 32) trow[c] = -1;
-            done |= 1u << gq;
+          __syncwarp();
+          if (pass == 0) {
+            // ---- phase 2: bin of the k-th distance
+            kt_scan(s_u, s_res, Gc, k, lpq, sub, qi, seg, (pend >> qi) & 1u, false);
+            __syncwarp();
+            if (lane < Gc && ((pend >> lane) & 1u)) {
+              const int n_in = s_res[4 * lane], b1 = s_res[4 * lane + 1];
+              q_clo = s_res[4 * lane + 2];
+              q_cnt1 = s_res[4 * lane + 3];
+              if (n_in < k) {
+                q_rl = true;
+                q_status = rg.rlim ? 0 : 1;
+                q_thr = 63.f; q_hi = 63.f + rg.dr;           // tail = the band in which d2 < r^2 is undecidable in fp32
+              } else {
+                q_t = k - q_clo;
+                q_thr = (float)b1; q_hi = (float)(b1 + 1);   // tail = the boundary bin
+                q_status = 0;
+                if (q_cnt1 > KT_TAIL) {
+                  // crowded boundary bin (dense cells: d_k << reach): 63 sub-bins inside it, z = 63 (v - b1)
+                  q_status = 3;
+                  q_zsc = rg.sc * 63.f;
+                  q_zoff = fmaf(q_zoff, 63.f, -63.f * (float)b1);
+                  q_dv = fmaf(rg.dv, 63.f, 1e-3f);
+                }
+              }
+            }
+            active = __ballot_sync(KT_FULL, q_status == 3);
+          } else if (pass == 1) {
+            kt_scan(s_u, s_res, Gc, k, lpq, sub, qi, seg, (active >> qi) & 1u, true);
+            __syncwarp();
+            if (q_status == 3) {
+              const int n_in = s_res[4 * lane], b2 = s_res[4 * lane + 1];
+              q_clo = s_res[4 * lane + 2];
+              q_cnt1 = s_res[4 * lane + 3];
+              q_t = k - q_clo;
+              q_thr = (float)b2; q_hi = (float)(b2 + 1);
+              q_status = (n_in < k || q_cnt1 > KT_TAIL) ? 2 : 0;
+            }
+          }
+          if (pass < 2) {
+            ready = __ballot_sync(KT_FULL, q_status == 0);
+            crowded = __ballot_sync(KT_FULL, q_status == 2);
+            still = __ballot_sync(KT_FULL, q_status == 1);
           }
         }
+        __syncwarp();
+        // ---- phase 4 (lanes = queries): the t smallest of the boundary bin, ambiguity test, padding
+        bool amb = false;
+        if (q_status == 0) {
+          const int cf = s_res[2 * lane], ct = s_res[2 * lane + 1];
+          int* trow = s_u + lane * ts;
+          const float* sv = s_sv + lane * KT_TAIL;
+          int cnt_final = q_clo;
+          if (q_rl) {
+            amb = ct > 0 || cf != q_clo;
+          } else if (ct != q_cnt1 || cf != q_clo) {
+            amb = true;          // cannot happen (all sweeps classify identically); fp64 path if it ever does
+          } else if (q_cnt1 == q_t) {
+            float vm = -1.f;
+            for (int i = 0; i < ct; ++i) vm = fmaxf(vm, sv[i]);
+            amb = q_hi - vm <= q_dv;                    // the nearest rejected candidate has z >= the next bin edge
+            cnt_final = k;
+          } else {
+            // rank by (z, arrival); keep rank < t.  v_t / v_n: last kept / first rejected value
+            float v_t = -1.f, v_n = 3.0e38f;
+            unsigned keep = 0u;
+            for (int i = 0; i < ct; ++i) {
+              const float vi = sv[i];
+              int rank = 0;
+              for (int j = 0; j < ct; ++j) {
+                const float vj = sv[j];
+                rank += (vj < vi || (vj == vi && j < i)) ? 1 : 0;
+              }
+              if (rank < q_t) { keep |= 1u << i; v_t = fmaxf(v_t, vi); } else { v_n = fminf(v_n, vi); }
+            }
+            amb = v_n - v_t <= q_dv;
+            int w = q_clo;
+            for (int i = 0; i < ct; ++i)
+              if ((keep >> i) & 1u) trow[w++] = trow[q_clo + i];
+            cnt_final = k;
+          }
+          for (int c = cnt_final; c < k; ++c) trow[c] = -1;
+        }
+        const unsigned amb_m = __ballot_sync(KT_FULL, amb);
+        const unsigned done = ready & ~amb_m;
+        kt_push(amb_m, cs, (m < 255 ? m : 255) | (KT_FB_AMBIGUOUS << 8), lane, counters, fb_list);
+        kt_push(crowded, cs, (m < 255 ? m : 255) | (KT_FB_CROWDED << 8), lane, counters, fb_list);
+        __syncwarp();
+        // ---- write the finished rows: lanes = (query, column) so that short chunks still fill the warp
+        if (done) {
+          const int lq = lane & (qw - 1), cc = lane / qw, cstep = 32 / qw;
+          const int q = cs + lq;
+          if ((done >> lq) & 1u) {
+            int32_t* dst = ell_idx + (int64_t)(q >> 5) * k * DC_SLICE + (q & 31);
+            for (int c = cc; c < k; c += cstep) dst[(int64_t)c * DC_SLICE] = s_u[lq * ts + c];
+          }
+        }
+        __syncwarp();
         pend = still;
         if (pend) {
           if (m >= prm.mmax) {
-            kt_push(pend, cs, m + 1, lane, counters, fb_list);
+            kt_push(pend, cs, (m + 1 < 255 ? m + 1 : 255) | (KT_FB_RING << 8), lane, counters, fb_list);
             pend = 0u;
           } else {
-            ++m;
+            m = m < 4 ? m + 1 : (m + (m >> 1) < prm.mmax ? m + (m >> 1) : prm.mmax);
           }
         }
       }
-      // ---- write the finished rows of this chunk: lanes = (query, column) so that short chunks still fill the warp
-      __syncwarp();
-      if (done) {
-        const int qw = Gc <= 8 ? 8 : (Gc <= 16 ? 16 : 32);
-        const int lq = lane & (qw - 1), cc = lane / qw, cstep = 32 / qw;
-        const int q = cs + lq;
-        if ((done >> lq) & 1u) {
-          int32_t* dst = ell_idx + (int64_t)(q >> 5) * k * DC_SLICE + (q & 31);
-          for (int c = cc; c < k; c += cstep) dst[(int64_t)c * DC_SLICE] = s_tile[lq * ts + c];
-        }
-      }
-      __syncwarp();
     }
   }
 }
@@ -650,7 +807,8 @@ knn_thread_list_kernel(const dc_point* __restrict__ P, const uint64_t* __restric
     int c0, c1, c2;
     dc_key_coords(g, qkeys[q], c0, c1, c2);
     int cnt = 0;
-    const int first = e.y < 1 ? 1 : (e.y > max_ring ? max_ring : e.y);
+    const int ring = e.y & 0xff;        // (bits 8..: why the cell kernel gave up, for statistics)
+    const int first = ring < 1 ? 1 : (ring > max_ring ? max_ring : ring);
     knn_thread_query(P, pkeys, n, g, cell_start, pq, c0, c1, c2, k, r2cap, max_ring, first, &hist[0][threadIdx.x],
                      [&](int j, double d2) {
                        out_j[(int64_t)cnt * DC_SLICE] = j;
@@ -710,7 +868,9 @@ extern "C" int dc_knn_cells(const void* P, const uint64_t* pkeys, int64_t n, con
   kt_params prm;
   memset(&prm, 0, sizeof(prm));
   prm.k = k;
-  prm.tile_stride = k + 1;
+  prm.tile_stride = (k + KT_TAIL) | 1;                          // odd: row-per-lane accesses are conflict-free
+  const int union_words = 32 * prm.tile_stride > 32 * KT_HSTRIDE ? 32 * prm.tile_stride : 32 * KT_HSTRIDE;
+  prm.warp_words = KT_WARP_FIXED + union_words;
   prm.mmax = max_ring < KT_MMAX ? max_ring : KT_MMAX;
   const char* pop = getenv("DC_KNN_POP_X10");
   prm.pop_min = (int)((pop ? atof(pop) : 25.0) * 0.1 * k);
@@ -738,7 +898,7 @@ extern "C" int dc_knn_cells(const void* P, const uint64_t* pkeys, int64_t n, con
   knn_cells_init_kernel<<<1, 32, 0, st>>>(header, ell_idx, nq, k);
   DC_LAUNCH_CHECK();
   DC_CUDA_CHECK(cub::DeviceSelect::If(ws + off_cub, cub_bytes, iota, task_start, header, (int)nq, pred, st));
-  const size_t smem = (size_t)KT_WARPS * (KT_WARP_WORDS + 32 * prm.tile_stride) * sizeof(int);
+  const size_t smem = (size_t)KT_WARPS * prm.warp_words * sizeof(int);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     DC_CUDA_CHECK(cudaFuncSetAttribute(knn_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -90,6 +90,8 @@ def train(cfg, callbacks=None, train_datasets=None, val_datasets=None):
     if not train_datasets or val_datasets is None:
         raise NotImplementedError('pass train_datasets / val_datasets (iterables of (cloud, pose)); the dataset readers of '
                                   'the reference are outside the hot path')
+    from .fused import set_backward_form
+    set_backward_form(getattr(cfg, 'backward_form', 'auto'))
     if not cfg.log_dir:
         cfg.log_dir = tempfile.mkdtemp(prefix='depth_correction_b200_')
     os.makedirs(cfg.log_dir, exist_ok=True)

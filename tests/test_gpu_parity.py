@@ -699,8 +699,9 @@ def test_scatter_f32_agrees_with_gather_form(dc, dev, monkeypatch):
     ns = dc.establish_neighborhoods(clouds=clouds, poses=poses_t, cfg=cfg)
 
     def grads(mode):
-        monkeypatch.setenv('DC_BACKWARD', 'gather' if mode == 'gather' else 'scatter')
-        monkeypatch.setenv('DC_SCATTER_F32', '1' if mode == 'f32' else '0')
+        monkeypatch.setattr(fused, 'BACKWARD_FORM', 'gather' if mode == 'gather' else 'scatter')
+        monkeypatch.setenv('DC_SCATTER_F32', '1' if mode in ('f32', 'f32-two-kernels') else '0')
+        monkeypatch.setenv('DC_FUSE_BWD', '0' if mode == 'f32-two-kernels' else '1')
         model = dc.ScaledPolynomial(w=[0.003, -0.002], exponent=[2, 4], device=dev)
         deltas = torch.full((len(clouds), 6), 1e-3, dtype=torch.float64, device=dev, requires_grad=True)
         pc = torch.stack(dc.create_corrected_poses(poses_t, deltas, cfg))
@@ -711,11 +712,13 @@ def test_scatter_f32_agrees_with_gather_form(dc, dev, monkeypatch):
         return model.w.grad.cpu().numpy().ravel(), deltas.grad.cpu().numpy()
 
     gw64, gd64 = grads('f64')
-    gw32, gd32 = grads('f32')
+    gw32, gd32 = grads('f32')           # forward + scatter in ONE kernel (dc_step_forward_scatter)
+    gw2k, gd2k = grads('f32-two-kernels')
     gwg, gdg = grads('gather')          # last: builds the transposed graph
     assert rel_err_norm(gw64, gwg) < 1e-11 and rel_err_norm(gd64, gdg) < 1e-11
-    assert rel_err_norm(gw32, gwg) < 1e-6, rel_err_norm(gw32, gwg)
-    assert rel_err_norm(gd32, gdg) < 1e-6, rel_err_norm(gd32, gdg)
+    for gw, gd in ((gw32, gd32), (gw2k, gd2k)):
+        assert rel_err_norm(gw, gwg) < 1e-6, rel_err_norm(gw, gwg)
+        assert rel_err_norm(gd, gdg) < 1e-6, rel_err_norm(gd, gdg)
 
 
 def test_knn_two_million_points_sampled_vs_ckdtree(dc, dev):
@@ -844,8 +847,9 @@ def test_fused_step_one_million_points_vs_oracle(dc, dev, monkeypatch):
     ref = oracle.map_consistency_step(oscans, torch.as_tensor(poses), nb, torch.tensor([[0.004, -0.003]], dtype=torch.float64),
                                       torch.tensor([[2.0, 4.0]], dtype=torch.float64), pose_deltas=d0.cpu(),
                                       loss='min_eigval_loss', normalization=True)
+    from depth_correction_b200 import fused
     for form, tol in (('gather', 1e-9), ('auto', 1e-6)):
-        monkeypatch.setenv('DC_BACKWARD', form)
+        monkeypatch.setattr(fused, 'BACKWARD_FORM', form)
         model = dc.ScaledPolynomial(w=[0.004, -0.003], exponent=[2, 4], device=dev)
         deltas = d0.clone().requires_grad_(True)
         pc = torch.stack(dc.create_corrected_poses(poses_t, deltas, cfg))

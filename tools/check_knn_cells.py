@@ -42,7 +42,12 @@ def timed_search(pts, query, k, r, path, cell=None, reps=3):
     if path == 'cells':
         ws = L._workspace.get(('temp:dc_knn_cells', str(pts.device)))
         hdr = ws[:64].view(torch.int32).cpu()
-        fb = (int(hdr[0]), int(hdr[5]))
+        nq = g.n_rows
+        off = 64 + ((max(nq, 1) * 4 + 15) // 16) * 16
+        nfb = int(hdr[5])
+        reasons = ws[off:off + 8 * nfb].view(torch.int32).view(-1, 2)[:, 1] >> 8
+        rc = torch.bincount(reasons.long(), minlength=4).tolist() if nfb else [0, 0, 0, 0]
+        fb = (int(hdr[0]), nfb, rc[1:4])
     return g, best, fb
 
 
@@ -56,8 +61,8 @@ def compare(name, pts, query, k, r, cell=None):
     nq = gc.n_rows
     same = torch.equal(a, b)
     nbad = int((a != b).any(dim=1).sum().item()) if not same else 0
-    print('%-28s n=%8d nq=%8d k=%3d r=%s cell=%.4f occ=%5.1f | thread %8.3f ms  cells %8.3f ms (x%.2f) | cells %d fallback %d (%.2f%%) | %s'
-          % (name, pts.shape[0], nq, k, r, cellsz, occ, mt, mc, mt / mc, fb[0], fb[1], 100.0 * fb[1] / max(nq, 1),
+    print('%-28s n=%8d nq=%8d k=%3d r=%s cell=%.4f occ=%5.1f | thread %8.3f ms  cells %8.3f ms (x%.2f) | cells %d fp64 path %d (%.2f%%: ambiguous / crowded / ring %s) | %s'
+          % (name, pts.shape[0], nq, k, r, cellsz, occ, mt, mc, mt / mc, fb[0], fb[1], 100.0 * fb[1] / max(nq, 1), fb[2],
              'IDENTICAL' if same else 'MISMATCH in %d rows' % nbad), flush=True)
     if not same:
         bad = torch.nonzero((a != b).any(dim=1))[:3, 0].tolist()
