@@ -1,16 +1,27 @@
 #!/usr/bin/env python
 """Benchmark of the map-consistency hot path (BASELINE.json metric: points/s for
-neighbors + cov + eig map-consistency loss fwd+bwd).
+neighbors + cov + eig map-consistency loss fwd+bwd at 1/2/4/8 B200).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scans S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one neighbour search over the global cloud (kNN k=32 within r=0.4 m, incl. the transposed
-graph the backward needs and the packing of the scan records) + one fused forward + backward of
-min_eigval_loss(normalization=True) through ScaledPolynomial(w=[0,0], exponent=[2,4]) and per-scan SE(3)
-pose corrections, on a synthetic corridor of full-resolution OS0-128 scans (BASELINE.json configs[1]).
+One "step" = one neighbour search over the global cloud (kNN k=32 within r=0.4 m, incl. the packing of the scan records
+in sorted order) + one fused forward + backward of min_eigval_loss(normalization=True) through
+ScaledPolynomial(w=[0,0], exponent=[2,4]) and per-scan SE(3) pose corrections.
+
+  N = 1   workload = BASELINE.json configs[1]: synthetic corridor, 64 full-resolution OS0-128 scans (8.4 M points).
+          Extra keys: the fixed-graph steady state, a cold search, parity of the GPU path against the CPU baseline on the
+          CPU sample, and `strong_scaling` = the 600-scan HDL-64 street map (60 M points, configs[2]) on this one GPU --
+          the anchor of the N > 1 lines.
+  N > 1   `value` = STRONG scaling on that fixed 60 M point street map (north_star: ">= 6x from 1 to 8 GPUs on a 60 M
+          point map"): scans ingested in blocks of consecutive scans, equal-count spatial slabs + halo exchange (setup,
+          timed separately as `setup_ms`), search + fused step on every rank, one all-reduce per step.  `weak` = the
+          round-1 weak-scaling line (64 corridor scans per GPU) as a second key; `multi_gpu_parity` = sharded loss /
+          gradients against the single-GPU result on a small common map, checked inside the run.
+
 Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the byte accounting.
 """
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -25,10 +36,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from depth_correction_b200.synthetic import make_sequence   # noqa: E402  (numpy only)
+
+def _load_synthetic():
+    """depth_correction_b200/synthetic.py (numpy only) WITHOUT importing the package: the reference arm must not map
+    libdcb200.so."""
+    spec = importlib.util.spec_from_file_location('dc_b200_synthetic', os.path.join(ROOT, 'depth_correction_b200', 'synthetic.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+synthetic = _load_synthetic()
+make_sequence, make_poses = synthetic.make_sequence, synthetic.make_poses
 
 NN_K, NN_R = 32, 0.4
 METRIC = 'points/s (neighbour search + fused map-consistency loss fwd+bwd)'
+WORKLOADS = {
+    # name: (scene, pattern, depth clip)
+    'corridor': ('corridor', 'os0-128', (1.0, 25.0)),
+    'street': ('street', 'hdl-64', (5.0, 80.0)),
+}
+# SURVEY.md section 8(d): algorithmic bytes per point of the headline metric (search 60 + 4K, fixed-graph step 206 + 8K)
+HEADLINE_BYTES_PER_POINT = 266 + 12 * NN_K
+SURVEY_STEP_BYTES_PER_POINT = 206 + 8 * NN_K
 
 
 def parse_args():
@@ -37,12 +67,13 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--scans', type=int, default=64, help='scans per GPU (weak scaling)')
-    ap.add_argument('--pattern', default='os0-128')
-    ap.add_argument('--scene', default='corridor', choices=['corridor', 'street'],
-                    help='street + --pattern hdl-64 = the KITTI-360-shaped workload of BASELINE.json configs[2]')
+    ap.add_argument('--scans', type=int, default=64, help='corridor scans per GPU (N = 1 workload; weak-scaling key at N > 1)')
+    ap.add_argument('--scans-total', type=int, default=600, help='HDL-64 street scans of the strong-scaling map (60 M points)')
+    ap.add_argument('--scaling', default='auto', choices=['auto', 'weak', 'strong'],
+                    help='what `value` reports: auto = configs[1] at N = 1, strong (street map) at N > 1')
     ap.add_argument('--cpu-scans', type=int, default=6, help='scans in the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-strong-anchor', action='store_true', help='N = 1: skip the 60 M point street map')
     ap.add_argument('--profile', action='store_true', help='small fixed workload for ncu (no baseline, no e2e)')
     return ap.parse_args()
 
@@ -55,7 +86,7 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region (NVML in-process; nvidia-smi as fallback)."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
@@ -110,13 +141,19 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------
-SCENE = 'corridor'
-
-
-def host_scans(n_scans, pattern, first_scan=0):
-    clip = (1.0, 25.0) if SCENE == 'corridor' else (5.0, 80.0)
-    scans, _, poses = make_sequence(SCENE, n_scans=n_scans, pattern=pattern, seed=0, first_scan=first_scan, depth_clip=clip)
-    return [s['points'] for s in scans], poses
+def host_scans(n_scans, pattern='os0-128', first_scan=0, scene='corridor', scan_ids=None):
+    """float32 sensor-frame points of `n_scans` consecutive scans (or of the given scan ids) + the poses of exactly
+    those scans."""
+    clip = WORKLOADS[scene][2] if scene in WORKLOADS else (1.0, 25.0)
+    if scan_ids is None:
+        scans, _, poses = make_sequence(scene, n_scans=n_scans, pattern=pattern, seed=0, first_scan=first_scan, depth_clip=clip)
+        return [s['points'] for s in scans], poses
+    pts, poses = [], []
+    for sid in scan_ids:
+        scans, _, p = make_sequence(scene, n_scans=1, pattern=pattern, seed=0, first_scan=int(sid), depth_clip=clip)
+        pts.append(scans[0]['points'])
+        poses.append(p[0])
+    return pts, np.stack(poses) if poses else np.zeros((0, 4, 4))
 
 
 def local_features(dc, pts_dev, cfg):
@@ -144,8 +181,6 @@ def one_step(dc, clouds, poses, deltas, model, cfg, ns=None, timers=None, local=
         cloud = dc.global_cloud(clouds=clouds, model=model, poses=p0)
         feats = dc.compute_neighborhood_features(cloud=cloud, neighborhoods=ns, cfg=cfg)
         feats.step_state()                       # pack the scan records in sorted order
-        # (the backward runs in the scatter form: one float32 vector reduction per edge on maps of >= 2^20 points,
-        #  fp64 reductions below; DC_BACKWARD=gather selects the deterministic fp64 gather form, fused.py)
     e1.record()
     model.zero_grad(set_to_none=True)
     deltas.grad = None
@@ -166,6 +201,274 @@ def one_step(dc, clouds, poses, deltas, model, cfg, ns=None, timers=None, local=
     return loss, ns
 
 
+class Job(object):
+    """One workload on this process' GPU: ingestion (host scans -> device -> per-scan features), optional slab
+    partition over the ranks, and the timed loops."""
+
+    def __init__(self, dc, dev, world, rank, scene, scan_ids, n_scans_total):
+        self.dc, self.dev, self.world, self.rank = dc, dev, world, rank
+        self.scene, self.pattern = WORKLOADS[scene][0], WORKLOADS[scene][1]
+        self.scan_ids = list(scan_ids)
+        self.n_scans_total = n_scans_total
+        self.cfg = dc.Config(nn_k=NN_K, nn_r=NN_R, pose_correction=dc.PoseCorrection.pose)
+        pts_host, _ = host_scans(len(self.scan_ids), self.pattern, scene=self.scene, scan_ids=self.scan_ids)
+        self.poses_np = make_poses(self.scene, n_scans_total)
+        self.pts_pinned = [torch.from_numpy(p).pin_memory() for p in pts_host]
+        pts_dev = [p.to(dev, non_blocking=True) for p in self.pts_pinned]
+        self.ingested = local_features(dc, pts_dev, self.cfg)
+        self.poses = torch.as_tensor(self.poses_np, device=dev)
+        self.deltas = torch.zeros((n_scans_total, 6), dtype=torch.float64, device=dev, requires_grad=True)
+        self.model = dc.ScaledPolynomial(w=[0.0, 0.0], exponent=[2, 4], device=dev)
+        self.setup_ms = 0.0
+        self.clouds, self.local = self.repartition(self.ingested, timed=True)
+        self.n_local = sum(len(c) for c in self.clouds) if self.local is None else int(self.local.owned.sum().item())
+        self.n_resident = sum(len(c) for c in self.clouds)
+
+    def repartition(self, cl, timed=False):
+        """spatial slabs + halo exchange over NCCL (one-time setup of a training run; part of e2e only)"""
+        if self.world == 1:
+            return cl, None
+        dc = self.dc
+        from depth_correction_b200.preproc import _initial_map_points
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        # points of all local scans in the initial map frame: one batched kernel (dc_world_points_batched)
+        wp = _initial_map_points(dc.global_cloud(clouds=cl, poses=self.poses[self.scan_ids]))
+        part = dc.SlabPartitioner()
+        axis, bounds = part.plan(wp)
+        loc = part.exchange(cl, self.scan_ids, wp, axis, bounds, halo=NN_R)
+        e1.record()
+        if timed:
+            torch.cuda.synchronize()
+            self.setup_ms = self.allmax([e0.elapsed_time(e1)])[0]
+        return loc.clouds, loc
+
+    def sync(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def step(self, ns=None, timers=None, clouds=None, local=None, poses=None):
+        own = clouds is None
+        return one_step(self.dc, self.clouds if own else clouds, self.poses if poses is None else poses,
+                        self.deltas, self.model, self.cfg, ns=ns, timers=timers, local=self.local if own else local)
+
+    def allmax(self, vals):
+        if self.world == 1:
+            return list(vals)
+        import torch.distributed as dist
+        t = torch.tensor(list(vals), device=self.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def allsum(self, vals):
+        if self.world == 1:
+            return list(vals)
+        import torch.distributed as dist
+        t = torch.tensor(list(vals), device=self.dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        return t.tolist()
+
+    def timed(self, L, steps, warmup, profile_kernels=True, sampler=None, nvtx=False):
+        """`warmup` untimed + `steps` timed steps (search + step every time) -> dict of max-over-ranks device times."""
+        for _ in range(warmup):
+            loss, ns = self.step()
+        self.sync()
+        timers = []
+        launches0 = L.launch_count
+        L.profile = {} if profile_kernels else None
+        if sampler is not None:
+            sampler.start()
+        self.sync()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        if nvtx:
+            # `ncu --profile-from-start off` profiles exactly the timed steps (cudaProfilerStart/Stop cover every thread,
+            # the autograd thread that launches the backward kernels included)
+            torch.cuda.profiler.start()
+            torch.cuda.nvtx.range_push('timed_steps')
+        for _ in range(steps):
+            loss, ns = self.step(timers=timers)
+            gl = loss.detach()
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
+            torch.cuda.profiler.stop()
+        t1.record()
+        self.sync()
+        kernel_ms = L.collect_profile()
+        L.profile = None
+        total_ms = t0.elapsed_time(t1)
+        search_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in timers]))
+        step_ms = float(np.mean([b.elapsed_time(c) for _, b, c in timers]))
+        total_ms, search_ms, step_ms = self.allmax([total_ms, search_ms, step_ms])
+        n_total = int(round(self.allsum([float(self.n_local)])[0]))
+        return {'ms_per_step': total_ms / steps, 'search_ms': search_ms, 'step_ms': step_ms, 'n_total': n_total,
+                'value': n_total / (total_ms / steps * 1e-3), 'kernel_ms': kernel_ms, 'launches': L.launch_count - launches0,
+                'loss': float(gl.item()), 'ns': ns}
+
+    def fixed_graph(self, L, ns, steps):
+        """Steady state of a training run: the graph of the last search is REUSED (the reference searches once per run,
+        preproc.py:168-191 / train.py:172-175)."""
+        for _ in range(4):
+            self.step(ns=ns)
+        self.sync()
+        L.profile = {}
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_fixed = max(steps, 5)
+        f0.record()
+        for _ in range(n_fixed):
+            self.step(ns=ns)
+        f1.record()
+        self.sync()
+        kernel_ms = L.collect_profile()
+        L.profile = None
+        return self.allmax([f0.elapsed_time(f1) / n_fixed])[0], kernel_ms
+
+    def e2e(self, steps):
+        """The same metric end to end through the public API from pinned HOST buffers: H2D of every input, DepthCloud
+        construction, [slab partition + halo exchange,] search, step, D2H of loss and gradients -- all inside the timed
+        region, every step."""
+        dc, dev = self.dc, self.dev
+        inc_host = [c.inc_angles.cpu().pin_memory() for c in self.ingested]
+        mask_host = [c.mask.cpu().pin_memory() for c in self.ingested]
+        poses_host = torch.as_tensor(self.poses_np).pin_memory()
+        h2d = sum(p.numel() * 4 for p in self.pts_pinned) + sum(x.numel() * 4 for x in inc_host) \
+            + sum(x.numel() for x in mask_host) + poses_host.numel() * 8
+
+        def run():
+            cl = []
+            for p, a, m in zip(self.pts_pinned, inc_host, mask_host):
+                c = dc.DepthCloud.from_points(p.to(dev, non_blocking=True))
+                c.inc_angles = a.to(dev, non_blocking=True)
+                c.mask = m.to(dev, non_blocking=True)
+                cl.append(c)
+            ps = poses_host.to(dev, non_blocking=True)
+            cl, loc = self.repartition(cl)
+            loss, _ = self.step(clouds=cl, local=loc, poses=ps)
+            return torch.cat([loss.detach().reshape(1), self.model.w.grad.reshape(-1), self.deltas.grad.reshape(-1)]).cpu()
+
+        run()
+        self.sync()
+        n_e2e = max(2, min(steps, 3))
+        w0 = time.perf_counter()
+        for _ in range(n_e2e):
+            out = run()
+        self.sync()
+        e2e_s = self.allmax([(time.perf_counter() - w0) / n_e2e])[0]
+        h2d_all = int(round(self.allsum([float(h2d)])[0]))
+        return e2e_s, h2d_all, out.numel() * 8 * self.world
+
+
+def kernel_table(kernel_ms, alg, peak):
+    out = {}
+    for kname, v in kernel_ms.items():
+        if kname in alg and v['calls']:
+            ms = v['ms_total'] / v['calls']
+            gbs = alg[kname] / (ms * 1e-3) / 1e9
+            out[kname] = {'ms': round(ms, 4), 'algorithmic_bytes': alg[kname], 'GBps': round(gbs, 1), 'frac': round(gbs / peak, 4)}
+    return out
+
+
+def algorithmic_bytes(job, ns):
+    """every array once per pass, gathers assumed L2-served."""
+    g = ns.graph
+    idx_fwd = g.ell_idx.numel() * 4
+    idx_bwd = g._transposed.ell_idx.numel() * 4 if g._transposed is not None else idx_fwd
+    n_cells = g.map.n_cells if g.map.cell_start is not None else 0
+    nr = job.n_resident
+    big = nr >= (1 << 20)
+    return {
+        'dc_knn': nr * (32 + 8) + idx_fwd + 4 * n_cells,                    # records + keys + cell table in, lists out
+        'dc_cell_keys': nr * (24 + 8 + 4),
+        'dc_gather_points': nr * (24 + 4 + 32 + 4),
+        'dc_cell_table': nr * 8 + 4 * n_cells,
+        'dc_pack_records_batched': nr * (37 + 4 + 2 * 36),
+        'dc_world_points_batched': nr * (28 + 24),
+        'dc_step_points': nr * (36 + 32),
+        'dc_step_forward': idx_fwd + nr * (32 + 4 + 8 + 64),
+        # forward + float32 scatter in one kernel: index + point + meta in, loss out, g zeroed and reduced; no stash
+        'dc_step_forward_scatter': idx_fwd + nr * (32 + 4 + 8 + 32),
+        'dc_step_backward': idx_bwd + nr * (32 + 4 + 24),                   # gather form (transposed graph)
+        'dc_step_backward_scatter': idx_fwd + nr * (64 + (32 if big else 48)),
+        'dc_step_chain': nr * ((16 if big else 24) + 36 + 4),
+    }, idx_fwd, idx_bwd
+
+
+STEP_KERNELS = ('dc_step_points', 'dc_step_forward', 'dc_step_forward_scatter', 'dc_step_backward', 'dc_step_backward_scatter',
+                'dc_step_chain')
+
+
+def multi_gpu_parity(dc, dev, world, rank):
+    """Sharded loss / gradients against the single-GPU result on a small common map (4 reduced scans per rank), inside
+    the run: every rank computes the whole map alone, then its slab; errors are maxed over the ranks."""
+    import torch.distributed as dist
+    S = 4 * world
+    scans_np, _, poses_np = make_sequence('corridor', n_scans=S, pattern='os0-128', seed=3, rings=32, azimuths=256, step=1.5)
+    cfg = dc.Config(nn_k=12, nn_r=NN_R, pose_correction=dc.PoseCorrection.pose)
+    clouds = local_features(dc, [torch.as_tensor(s['points'], device=dev) for s in scans_np], cfg)
+    poses = torch.as_tensor(poses_np, device=dev)
+    d0 = torch.as_tensor(np.random.default_rng(0).normal(0, 0.005, (S, 6)), device=dev)
+
+    def run(local_clouds, local):
+        model = dc.ScaledPolynomial(w=[0.003, -0.002], exponent=[2, 4], device=dev)
+        deltas = d0.clone().requires_grad_(True)
+        sel = None if local is None else local.scan_ids
+        ns = dc.establish_neighborhoods(clouds=local_clouds, poses=poses if sel is None else poses[sel], cfg=cfg)
+        pc = torch.stack(dc.create_corrected_poses(poses, deltas, cfg))
+        feats = dc.compute_neighborhood_features(cloud=dc.global_cloud(clouds=local_clouds, model=model, poses=pc if sel is None else pc[sel]),
+                                                 neighborhoods=ns, cfg=cfg)
+        if local is None:
+            loss, _ = dc.min_eigval_loss(feats, normalization=True)
+            loss.backward()
+        else:
+            sc = dc.fused_sum_count(feats, mask=local.owned, loss='min_eigval_loss', normalization=True)
+            loss = dc.reduce_step(sc, [model.w, deltas])
+        return loss.detach(), model.w.grad.clone(), deltas.grad.clone()
+
+    ref = run(clouds, None)
+    mine = list(range(rank, S, world))                        # interleaved ingestion: forces a real exchange
+    wp = [clouds[i].transform(poses[i]).to_points() for i in mine]
+    part = dc.SlabPartitioner()
+    axis, bounds = part.plan(wp)
+    local = part.exchange([clouds[i] for i in mine], mine, wp, axis, bounds, halo=NN_R)
+    got = run(local.clouds, local)
+    errs = torch.stack([(a - b).abs().max() / b.abs().max() for a, b in zip(got, ref)])
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    out = {'loss': float(errs[0]), 'w': float(errs[1]), 'pose': float(errs[2]), 'n_points': int(sum(len(c) for c in clouds)),
+           'tolerance': 1e-9, 'ok': bool((errs < 1e-9).all())}
+    assert out['ok'], 'multi-GPU parity gate failed: %s' % out
+    return out
+
+
+def parity_vs_cpu(dc, dev, cpu):
+    """BASELINE.md section 3 gate: the GPU path on the very records of the CPU sample (float64 clouds built from the
+    oracle's per-scan records) against the CPU result: neighbour indices identical, loss / gradients within 1e-5."""
+    scans, poses = cpu['scans'], cpu['poses']
+    clouds = [dc.DepthCloud(vps=s['vps'].to(dev), dirs=s['dirs'].to(dev), depth=s['depth'].to(dev),
+                            inc_angles=s['inc_angles'].to(dev), mask=s['mask'].to(dev)) for s in scans]
+    cfg = dc.Config(nn_k=NN_K, nn_r=NN_R, pose_correction=dc.PoseCorrection.pose, float_type='float64')
+    poses_t = poses.to(dev)
+    model = dc.ScaledPolynomial(w=[0.0, 0.0], exponent=[2, 4], device=dev)
+    deltas = torch.zeros((len(clouds), 6), dtype=torch.float64, device=dev, requires_grad=True)
+    ns = dc.establish_neighborhoods(clouds=clouds, poses=poses_t, cfg=cfg)
+    pc = torch.stack(dc.create_corrected_poses(poses_t, deltas, cfg))
+    feats = dc.compute_neighborhood_features(cloud=dc.global_cloud(clouds=clouds, model=model, poses=pc), neighborhoods=ns, cfg=cfg)
+    loss, _ = dc.min_eigval_loss(feats, normalization=True)
+    loss.backward()
+    nb_gpu, nb_cpu = ns[0].cpu(), cpu['neighbors']
+    same = bool(torch.equal(nb_gpu, nb_cpu))
+    if not same:       # exact ties may be ordered differently (cKDTree: traversal order): compare rows as sets
+        same = bool(torch.equal(nb_gpu.sort(dim=1).values, nb_cpu.sort(dim=1).values))
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+    out = {'neighbor_indices_identical': same, 'loss_rel_err': abs(loss.item() - cpu['loss']) / abs(cpu['loss']),
+           'w_grad_rel_err': rel(model.w.grad.cpu(), cpu['w_grad']), 'pose_grad_rel_err': rel(deltas.grad.cpu(), cpu['pose_grad']),
+           'n_points': int(nb_cpu.shape[0]), 'tolerance': 1e-5}
+    out['ok'] = bool(same and out['loss_rel_err'] < 1e-5 and out['w_grad_rel_err'] < 1e-5 and out['pose_grad_rel_err'] < 1e-5)
+    assert out['ok'], 'parity gate against the CPU baseline failed: %s' % out
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     rank = int(os.environ.get('RANK', 0))
@@ -180,204 +483,61 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     import depth_correction_b200 as dc
     from depth_correction_b200 import _lib as L
+    from depth_correction_b200 import fused as _fused
+    from depth_correction_b200.graph import clear_cell_hints
 
-    from depth_correction_b200.synthetic import make_poses
-    n_scans = 4 if args.profile else args.scans
-    n_scans_total = n_scans * world
-    # weak scaling: every rank ingests `n_scans` consecutive scans of one long corridor (scan-sharded ingestion)
-    pts_host, _ = host_scans(n_scans, args.pattern, first_scan=rank * n_scans)
-    my_scans = list(range(rank * n_scans, (rank + 1) * n_scans))
-    poses_np = make_poses(SCENE, n_scans_total)
-    cfg = dc.Config(nn_k=NN_K, nn_r=NN_R, pose_correction=dc.PoseCorrection.pose)
-    pts_pinned = [torch.from_numpy(p).pin_memory() for p in pts_host]
-    pts_dev = [p.to(dev, non_blocking=True) for p in pts_pinned]
-    ingested = local_features(dc, pts_dev, cfg)
-    poses = torch.as_tensor(poses_np, device=dev)
-    deltas = torch.zeros((n_scans_total, 6), dtype=torch.float64, device=dev, requires_grad=True)
-    model = dc.ScaledPolynomial(w=[0.0, 0.0], exponent=[2, 4], device=dev)
+    scaling = args.scaling if args.scaling != 'auto' else ('weak' if world == 1 else 'strong')
+    warmup = max(args.warmup, 3)
+    peak, peak_src = peaks()
 
-    def repartition(cl):
-        """spatial slabs + halo exchange over NCCL (one-time setup of a training run; part of e2e only)"""
-        if world == 1:
-            return cl, None
-        # points of all local scans in the initial map frame: one batched kernel (dc_world_points_batched)
-        from depth_correction_b200.preproc import _initial_map_points
-        wp = _initial_map_points(dc.global_cloud(clouds=cl, poses=poses[my_scans]))
-        part = dc.SlabPartitioner()
-        axis, bounds = part.plan(wp)
-        loc = part.exchange(cl, my_scans, wp, axis, bounds, halo=NN_R)
-        return loc.clouds, loc
+    def corridor_job(n_scans):
+        return Job(dc, dev, world, rank, 'corridor', range(rank * n_scans, (rank + 1) * n_scans), n_scans * world)
 
-    clouds, local = repartition(ingested)
-    n_local = sum(len(c) for c in clouds) if local is None else int(local.owned.sum().item())
-    n_resident = sum(len(c) for c in clouds)
+    def street_job(n_total):
+        # scans dealt to the ranks in contiguous blocks (a rank reads a stretch of the drive); the slab exchange moves
+        # every point to the rank that owns its slab of the street
+        per = (n_total + world - 1) // world
+        return Job(dc, dev, world, rank, 'street', range(rank * per, min((rank + 1) * per, n_total)), n_total)
 
-    def sync():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-
-    # warm-up (builds nothing persistent: every step searches again)
-    for _ in range(max(args.warmup, 3 if not args.profile else 1)):
-        loss, ns = one_step(dc, clouds, poses, deltas, model, cfg, local=local)
-    sync()
     if args.profile:
-        print(json.dumps({'profile_run': True, 'n_points': n_local, 'loss': loss.item()}))
+        job = corridor_job(4)
+        job.timed(L, 1, 1, profile_kernels=False, nvtx=True)
+        if rank == 0:
+            print(json.dumps({'profile_run': True, 'n_points': job.n_local}))
         return
 
+    line = {}
     sampler = ClockSampler(local_rank)
-    if not os.environ.get('DC_BENCH_NO_SAMPLER'):
-        sampler.start()
-    timers = []
-    launches0 = L.launch_count
-    L.profile = None if os.environ.get('DC_BENCH_NO_PROFILE') else {}
-    sync()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    prof = None
-    if os.environ.get('DC_BENCH_CPROFILE'):
-        import cProfile
-        prof = cProfile.Profile()
-        prof.enable()
-    t0.record()
-    # `ncu --profile-from-start off` profiles exactly the timed steps (cudaProfilerStart/Stop cover every thread, the
-    # autograd thread that launches the backward kernels included; an NVTX range only covers the pushing thread)
-    torch.cuda.profiler.start()
-    torch.cuda.nvtx.range_push('timed_steps')
-    for _ in range(args.steps):
-        loss, ns = one_step(dc, clouds, poses, deltas, model, cfg, timers=timers, local=local)
-        gl = loss.detach()
-    torch.cuda.nvtx.range_pop()
-    torch.cuda.profiler.stop()
-    t1.record()
-    sync()
-    if prof is not None:
-        import pstats
-        prof.disable()
-        pstats.Stats(prof, stream=sys.stderr).sort_stats('tottime').print_stats(14)
-    kernel_ms = L.collect_profile()
-    L.profile = None
-    launches = L.launch_count - launches0
+    main_job = corridor_job(args.scans) if scaling == 'weak' else street_job(args.scans_total)
+    m = main_job.timed(L, args.steps, warmup, sampler=None if os.environ.get('DC_BENCH_NO_SAMPLER') else sampler, nvtx=True)
     clocks = sampler.summary()
-    total_ms = t0.elapsed_time(t1)
-    search_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in timers]))
-    step_ms = float(np.mean([b.elapsed_time(c) for _, b, c in timers]))
-    if world > 1:
-        t = torch.tensor([total_ms, search_ms, step_ms, float(n_local)], device=dev, dtype=torch.float64)
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        total_ms, search_ms, step_ms = tmax[0].item(), tmax[1].item(), tmax[2].item()
-        n_total = int(t[3].item())
-    else:
-        n_total = n_local
-    ms_per_step = total_ms / args.steps
-    value = n_total / (ms_per_step * 1e-3)
-
-    # ---- steady state of a training run: the graph of the last search is REUSED (the reference searches once per
-    # run, preproc.py:168-191 / train.py:172-175)
-    L.profile = None
-    for _ in range(4):
-        one_step(dc, clouds, poses, deltas, model, cfg, ns=ns, local=local)
-    sync()
-    L.profile = None if os.environ.get('DC_BENCH_NO_PROFILE') else {}
-    f0 = torch.cuda.Event(enable_timing=True)
-    f1 = torch.cuda.Event(enable_timing=True)
-    n_fixed = max(args.steps, 5)
-    f0.record()
-    for _ in range(n_fixed):
-        loss_f, _ = one_step(dc, clouds, poses, deltas, model, cfg, ns=ns, local=local)
-    f1.record()
-    sync()
-    fixed_kernel_ms = L.collect_profile()
-    L.profile = None
-    fixed_ms = f0.elapsed_time(f1) / n_fixed
-    if world > 1:
-        t = torch.tensor([fixed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        fixed_ms = t.item()
-    # ---- full-size parity property: the gradients of the timed path (fp32 vector-reduction scatter on large maps)
+    ns = m['ns']
+    fixed_ms, fixed_kernel_ms = main_job.fixed_graph(L, ns, args.steps)
+    # ---- full-size parity property: the gradients of the timed path (float32 vector-reduction scatter on large maps)
     # against the deterministic fp64 gather form on the same graph and inputs
-    gw_fast, gd_fast = model.w.grad.detach().clone(), deltas.grad.detach().clone()
-    from depth_correction_b200 import fused as _fused
+    gw_fast, gd_fast = main_job.model.w.grad.detach().clone(), main_job.deltas.grad.detach().clone()
     _fused.set_backward_form('gather')
-    one_step(dc, clouds, poses, deltas, model, cfg, ns=ns, local=local)
+    main_job.step(ns=ns)
     _fused.set_backward_form('auto')
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
-    grad_check = {'w_grad_rel_err_vs_fp64_gather': rel(gw_fast, model.w.grad), 'pose_grad_rel_err_vs_fp64_gather': rel(gd_fast, deltas.grad)}
+    grad_check = {'w_grad_rel_err_vs_fp64_gather': rel(gw_fast, main_job.model.w.grad),
+                  'pose_grad_rel_err_vs_fp64_gather': rel(gd_fast, main_job.deltas.grad)}
+    alg, idx_fwd, idx_bwd = algorithmic_bytes(main_job, ns)
     ns.graph._transposed = None          # (release the reverse lists again)
+    # ---- a cold search: no remembered cell size (the timed searches reuse the estimate of the first one)
+    clear_cell_hints()
+    main_job.sync()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    dc.establish_neighborhoods(clouds=main_job.clouds, poses=main_job.poses if main_job.local is None
+                               else main_job.poses[main_job.local.scan_ids], cfg=main_job.cfg)
+    c1.record()
+    main_job.sync()
+    cold_search_ms = main_job.allmax([c0.elapsed_time(c1)])[0]
+    e2e_s, h2d, d2h = main_job.e2e(args.steps)
+    n_total = m['n_total']
 
-    # ---- end-to-end through the public API from pinned HOST buffers (H2D + D2H inside the timed region)
-    inc_host = [c.inc_angles.cpu().pin_memory() for c in ingested]
-    mask_host = [c.mask.cpu().pin_memory() for c in ingested]
-    poses_host = torch.as_tensor(poses_np).pin_memory()
-    h2d = sum(p.numel() * 4 for p in pts_pinned) + sum(x.numel() * 4 for x in inc_host) + sum(x.numel() for x in mask_host) \
-        + poses_host.numel() * 8
-
-    def e2e_step():
-        # host scans -> device -> DepthCloud -> [slab repartition + halo exchange] -> search -> step -> host
-        cl = []
-        for p, a, m in zip(pts_pinned, inc_host, mask_host):
-            c = dc.DepthCloud.from_points(p.to(dev, non_blocking=True))
-            c.inc_angles = a.to(dev, non_blocking=True)
-            c.mask = m.to(dev, non_blocking=True)
-            cl.append(c)
-        ps = poses_host.to(dev, non_blocking=True)
-        cl, loc = repartition(cl)
-        loss, _ = one_step(dc, cl, ps, deltas, model, cfg, local=loc)
-        out = torch.cat([loss.detach().reshape(1), model.w.grad.reshape(-1), deltas.grad.reshape(-1)]).cpu()
-        return out
-
-    e2e_step()
-    sync()
-    n_e2e = max(2, min(args.steps, 3))
-    eprof = None
-    if os.environ.get('DC_BENCH_E2E_CPROFILE') and rank == 0:
-        import cProfile
-        eprof = cProfile.Profile()
-        eprof.enable()
-    w0 = time.perf_counter()
-    for _ in range(n_e2e):
-        out = e2e_step()
-    sync()
-    e2e_s = (time.perf_counter() - w0) / n_e2e
-    if eprof is not None:
-        import pstats
-        eprof.disable()
-        pstats.Stats(eprof, stream=sys.stderr).sort_stats('cumulative').print_stats(35)
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = t.item()
-    d2h = out.numel() * 8
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline: algorithmic bytes per launch (DESIGN.md section 3: every array once per pass, gathers assumed
-    # L2-served) over the live CUDA-event duration of each kernel, for the timed region and for the steady state
-    g = ns.graph
-    idx_fwd = g.ell_idx.numel() * 4
-    idx_bwd = g._transposed.ell_idx.numel() * 4 if g._transposed is not None else idx_fwd
-    n_cells = g.map.n_cells if g.map.cell_start is not None else 0
-    nr = n_resident
-    alg = {
-        'dc_knn': nr * (32 + 8) + idx_fwd + 4 * n_cells,                    # records + keys + cell table in, lists out
-        'dc_cell_keys': nr * (24 + 8 + 4),
-        'dc_gather_points': nr * (24 + 4 + 32 + 4),
-        'dc_cell_table': nr * 8 + 4 * n_cells,
-        'dc_pack_records_batched': nr * (37 + 4 + 2 * 36),
-        'dc_world_points_batched': nr * (28 + 24),
-        'dc_step_points': nr * (36 + 32),
-        'dc_step_forward': idx_fwd + nr * (32 + 4 + 8 + 64),
-        'dc_step_backward': idx_bwd + nr * (32 + 4 + 24),                   # gather form (transposed graph)
-        # scatter form: stash, g zero + g reduce (float32 x 4 on maps of >= 2^20 points, else fp64 x 3)
-        'dc_step_backward_scatter': idx_fwd + nr * (64 + (32 if nr >= (1 << 20) else 48)),
-        'dc_step_chain': nr * ((16 if nr >= (1 << 20) else 24) + 36 + 4),
-    }
-    peak, peak_src = peaks()
+    tab_timed, tab_fixed = kernel_table(m['kernel_ms'], alg, peak), kernel_table(fixed_kernel_ms, alg, peak)
     traffic = {}
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
@@ -385,55 +545,94 @@ def run_ours(args):
         # from the captured point count to this run's
         tj = json.load(open(tpath))
         for kname, rec in tj.get('kernels', {}).items():
-            traffic[kname] = (rec['dram_read_bytes'] + rec['dram_write_bytes']) * nr / float(tj['n_points'])
-
-    def table(kms):
-        out = {}
-        for kname, v in kms.items():
-            if kname in alg and v['calls']:
-                ms = v['ms_total'] / v['calls']
-                gbs = alg[kname] / (ms * 1e-3) / 1e9
-                out[kname] = {'ms': round(ms, 4), 'algorithmic_bytes': alg[kname], 'GBps': round(gbs, 1), 'frac': round(gbs / peak, 4)}
-        return out
-
-    tab_timed, tab_fixed = table(kernel_ms), table(fixed_kernel_ms)
+            traffic[kname] = (rec['dram_read_bytes'] + rec['dram_write_bytes']) * main_job.n_resident / float(tj['n_points'])
     roofline = None
     if tab_timed:
         top = max(tab_timed, key=lambda kname: tab_timed[kname]['ms'])
-        step_names = ('dc_step_points', 'dc_step_forward', 'dc_step_backward', 'dc_step_backward_scatter', 'dc_step_chain')
-        fixed_alg = sum(alg[kname] for kname in tab_fixed if kname in step_names)
+        fixed_alg = sum(alg[kname] for kname in tab_fixed if kname in STEP_KERNELS)
+        nres = main_job.n_resident
         roofline = {'bound': 'hbm', 'kernel': top, 'achieved': tab_timed[top]['GBps'], 'peak': peak, 'unit': 'GB/s',
                     'frac': tab_timed[top]['frac'], 'traffic': traffic.get(top), 'peak_source': peak_src,
                     'avg_kernel_ms': tab_timed[top]['ms'], 'algorithmic_bytes': alg[top],
-                    'note': 'dominant kernel of the timed region; dc_knn is bound by fp64 issue and gather latency, not by HBM '
-                            '(profiles/); the HBM-bound kernels are the fixed-graph step kernels listed below',
+                    'note': 'dominant kernel of the timed region; dc_knn is bound by instruction issue and gather latency, not by '
+                            'HBM (profiles/r2_knn_experiments.md); the HBM-side kernels are the fixed-graph step kernels below',
+                    # the headline metric itself against the roofline, with SURVEY.md section 8(d)'s bytes per point
+                    'headline': {'bytes_per_point': HEADLINE_BYTES_PER_POINT,
+                                 'frac': round(HEADLINE_BYTES_PER_POINT * nres / (m['ms_per_step'] * 1e-3) / 1e9 / peak, 4)},
+                    'fixed_graph_step': {'ms': fixed_ms,
+                                         'frac_survey_bytes': round(SURVEY_STEP_BYTES_PER_POINT * nres / (fixed_ms * 1e-3) / 1e9 / peak, 4),
+                                         'survey_bytes_per_point': SURVEY_STEP_BYTES_PER_POINT,
+                                         'frac_layout_bytes': round(fixed_alg / (fixed_ms * 1e-3) / 1e9 / peak, 4),
+                                         'layout_bytes_per_point': round(fixed_alg / float(nres), 1)},
                     'kernels_timed_region': tab_timed,
-                    'kernels_fixed_graph_steady_state': tab_fixed,
-                    'fixed_graph_step_fraction_of_roofline': round(fixed_alg / (fixed_ms * 1e-3) / 1e9 / peak, 4)}
+                    'kernels_fixed_graph_steady_state': tab_fixed}
 
-    line = {
-        'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64 arithmetic on f32 records', 'data': 'synthetic',
-        'config': {'workload': SCENE + ', %d full-res %s scans per GPU, kNN k=%d within r=%.1f m, ScaledPolynomial[2,4] + '
-                               'min_eigval_loss(normalization) + per-scan SE(3) corrections' % (n_scans, args.pattern, NN_K, NN_R),
-                   'n_points': n_total, 'n_points_per_gpu': n_local, 'n_resident_per_gpu_incl_halo': n_resident, 'k': NN_K, 'r': NN_R,
-                   'l2_policy': 'inputs larger than L2 (point + index + stash arrays %.0f MB)' %
-                                ((n_resident * (32 + 64 + 36) + idx_fwd + idx_bwd) / 1e6),
-                   'parallelism': 'one process per GPU; equal-count spatial slabs along the corridor + halo (r) exchange at setup; one all-reduce of {loss_sum, count, dw, dpose} per step'},
-        'search_ms': search_ms, 'first_step_on_new_graph_ms': step_ms,
-        'search_points_per_s': n_total / (search_ms * 1e-3),
-        'fixed_graph_step_ms': fixed_ms, 'fixed_graph_step_points_per_s': n_total / (fixed_ms * 1e-3),
-        'loss': float(gl.item()), 'grad_check': grad_check,
-        'clocks': clocks, 'gpu_launches': launches,
-        'e2e': {'value': n_total / e2e_s, 'unit': 'points/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'ms_per_step': e2e_s * 1e3},
-        'roofline': roofline,
-        'entry_points_ms_per_step': {k: round(v['ms_total'] / args.steps, 4) for k, v in sorted(kernel_ms.items())},
-    }
-    if not args.no_cpu_baseline and world == 1:
-        line['cpu_baseline'] = cpu_baseline(args.cpu_scans, args.pattern, steps=1)
-    print(json.dumps(line))
+    if rank == 0:
+        scene, pattern = main_job.scene, main_job.pattern
+        per_gpu = 'per GPU' if scaling == 'weak' else 'in total (fixed map, spatially partitioned)'
+        line = {
+            'metric': METRIC, 'value': m['value'], 'unit': 'points/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
+            'ms_per_step': m['ms_per_step'], 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None,
+            'dtype': 'f64 arithmetic on f32 records', 'data': 'synthetic',
+            'config': {'workload': '%s, %d full-res %s scans %s, kNN k=%d within r=%.1f m, ScaledPolynomial[2,4] + '
+                                   'min_eigval_loss(normalization) + per-scan SE(3) corrections'
+                                   % (scene, len(main_job.scan_ids) if scaling == 'weak' else main_job.n_scans_total, pattern, per_gpu, NN_K, NN_R),
+                       'n_points': n_total, 'n_points_per_gpu': main_job.n_local, 'n_resident_per_gpu_incl_halo': main_job.n_resident,
+                       'k': NN_K, 'r': NN_R,
+                       'l2_policy': 'inputs larger than L2 (point + index arrays %.0f MB per GPU)' % ((main_job.n_resident * (32 + 36) + idx_fwd) / 1e6),
+                       'parallelism': 'one process per GPU; equal-count spatial slabs along the trajectory + halo (r) exchange at '
+                                      'setup; one all-reduce of {loss_sum, count, dw, dpose} per step'},
+            'search_ms': m['search_ms'], 'first_step_on_new_graph_ms': m['step_ms'],
+            'search_points_per_s': n_total / (m['search_ms'] * 1e-3),
+            'cold_search_ms': cold_search_ms,
+            'fixed_graph_step_ms': fixed_ms, 'fixed_graph_step_points_per_s': n_total / (fixed_ms * 1e-3),
+            'setup_ms': main_job.setup_ms,
+            'loss': m['loss'], 'grad_check': grad_check,
+            'clocks': clocks, 'gpu_launches': m['launches'],
+            'e2e': {'value': n_total / e2e_s, 'unit': 'points/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': e2e_s * 1e3},
+            'roofline': roofline,
+            'entry_points_ms_per_step': {k: round(v['ms_total'] / args.steps, 4) for k, v in sorted(m['kernel_ms'].items())},
+        }
+    del main_job, ns, m
+    L.release_workspace()
+    torch.cuda.empty_cache()
+
+    # ---- second workload
+    if world > 1:
+        par = multi_gpu_parity(dc, dev, world, rank)
+        wjob = corridor_job(args.scans)
+        wm = wjob.timed(L, args.steps, warmup, profile_kernels=False)
+        we2e_s, _, _ = wjob.e2e(args.steps)
+        if rank == 0:
+            line['multi_gpu_parity'] = par
+            line['weak'] = {'workload': 'corridor, %d OS0-128 scans per GPU' % args.scans, 'n_points': wm['n_total'],
+                            'value': wm['value'], 'ms_per_step': wm['ms_per_step'], 'setup_ms': wjob.setup_ms,
+                            'e2e': {'value': wm['n_total'] / we2e_s, 'ms_per_step': we2e_s * 1e3}}
+            line['strong_scaling'] = {'workload': line['config']['workload'], 'value': line['value'],
+                                      'ms_per_step': line['ms_per_step'],
+                                      'one_gpu_anchor': 'key strong_scaling.value of the --gpus 1 line (same map on one GPU)'}
+        del wjob
+    elif not args.no_strong_anchor and scaling == 'weak':
+        sjob = street_job(args.scans_total)
+        sm = sjob.timed(L, max(2, min(args.steps, 3)), 2, profile_kernels=False)
+        sfixed, _ = sjob.fixed_graph(L, sm['ns'], 3)
+        line['strong_scaling'] = {'workload': 'street, %d HDL-64 scans (BASELINE.json configs[2]) on ONE GPU: anchor of the --gpus N > 1 lines'
+                                              % args.scans_total, 'n_points': sm['n_total'], 'value': sm['value'],
+                                  'ms_per_step': sm['ms_per_step'], 'search_ms': sm['search_ms'], 'fixed_graph_step_ms': sfixed,
+                                  'headline_frac_of_roofline': round(HEADLINE_BYTES_PER_POINT * sm['n_total'] / (sm['ms_per_step'] * 1e-3) / 1e9 / peak, 4)}
+        del sjob, sm
+        L.release_workspace()
+        torch.cuda.empty_cache()
+
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            cpu = cpu_baseline(args.cpu_scans, 'os0-128', steps=1, keep=True)
+            line['parity_vs_cpu_baseline'] = parity_vs_cpu(dc, dev, cpu)
+            for key in ('scans', 'poses', 'neighbors', 'w_grad', 'pose_grad'):
+                cpu.pop(key)
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -441,7 +640,7 @@ def run_ours(args):
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference's CPU path on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_step(scans, poses, k, r):
+def cpu_step(scans, poses, k, r, keep=False):
     from oracle import oracle
     t0 = time.perf_counter()
     pts, _ = oracle.global_points(scans, poses)
@@ -453,7 +652,8 @@ def cpu_step(scans, poses, k, r):
                                       pose_deltas=torch.zeros((S, 6), dtype=torch.float64),
                                       loss='min_eigval_loss', normalization=True)
     t2 = time.perf_counter()
-    return len(pts), t1 - t0, t2 - t1, float(out['loss'])
+    extra = {'neighbors': nb, 'w_grad': out['w_grad'], 'pose_grad': out['pose_deltas_grad']} if keep else None
+    return len(pts), t1 - t0, t2 - t1, float(out['loss']), extra
 
 
 def cpu_workload(n_scans, pattern):
@@ -464,7 +664,7 @@ def cpu_workload(n_scans, pattern):
     for p in pts_host:
         p64 = torch.as_tensor(p.astype(np.float64))
         vps, dirs, depth = oracle.from_points(p64)
-        # local features are setup, not part of the timed step: planar corridor -> analytic-free cheap stand-in
+        # local features are setup, not part of the timed step
         _, nb = oracle.nearest_neighbors(p64, k=NN_K, r=NN_R)
         f = oracle.neighborhood_features(p64, nb, dirs=dirs)
         mask = oracle.eigenvalue_masks(f['eigvals'], (), [[0, 1, 0, 0.25], [1, 2, 0.25, 1.0]])
@@ -472,35 +672,40 @@ def cpu_workload(n_scans, pattern):
     return scans, torch.as_tensor(poses_np)
 
 
-def cpu_baseline(n_scans, pattern, steps=1):
+def cpu_baseline(n_scans, pattern, steps=1, keep=False):
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     scans, poses = cpu_workload(n_scans, pattern)
     best = None
     for _ in range(steps):
-        n, ts, tf, loss = cpu_step(scans, poses, NN_K, NN_R)
-        if best is None or ts + tf < best[1] + best[2]:
-            best = (n, ts, tf, loss)
-    n, ts, tf, loss = best
-    return {'value': n / (ts + tf), 'unit': 'points/s', 'cores': cores, 'kind': 'port',
-            'sample': '%d of the same OS0-128 corridor scans (%d points), cKDTree search %.2f s + torch fp64 step fwd+bwd %.2f s'
-                      % (n_scans, n, ts, tf),
-            'search_s': ts, 'fixed_graph_step_s': tf, 'loss': loss}
+        res = cpu_step(scans, poses, NN_K, NN_R, keep=keep)
+        if best is None or res[1] + res[2] < best[1] + best[2]:
+            best = res
+    n, ts, tf, loss, extra = best
+    out = {'value': n / (ts + tf), 'unit': 'points/s', 'cores': cores, 'kind': 'port',
+           'sample': '%d of the same OS0-128 corridor scans (%d points), cKDTree search %.2f s + torch fp64 step fwd+bwd %.2f s'
+                     % (n_scans, n, ts, tf),
+           'search_s': ts, 'fixed_graph_step_s': tf, 'loss': loss}
+    if keep:
+        out.update(extra)
+        out.update({'scans': scans, 'poses': poses})
+    return out
 
 
 def run_reference(args):
     """The reference's own CPU implementation of the path (oracle port: scipy cKDTree + torch fp64 autograd,
-    all host threads) on a bounded sample of the same workload.  Rank 0 only."""
+    all host threads) on a bounded sample of the same workload.  Rank 0 only.  Imports neither the package nor its
+    shared library."""
     if int(os.environ.get('RANK', 0)) != 0:
         return
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    scans, poses = cpu_workload(args.cpu_scans, args.pattern)
+    scans, poses = cpu_workload(args.cpu_scans, 'os0-128')
     for _ in range(min(args.warmup, 1)):
         cpu_step(scans, poses, NN_K, NN_R)
     times = []
     for _ in range(args.steps):
-        n, ts, tf, loss = cpu_step(scans, poses, NN_K, NN_R)
+        n, ts, tf, loss, _ = cpu_step(scans, poses, NN_K, NN_R)
         times.append((ts, tf))
     ts = float(np.mean([t[0] for t in times]))
     tf = float(np.mean([t[1] for t in times]))
@@ -508,11 +713,11 @@ def run_reference(args):
     sample = '%d of the same OS0-128 corridor scans (%d points) per step' % (args.cpu_scans, n)
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': (ts + tf) * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': SCENE + ', full-res %s scans, kNN k=%d within r=%.1f m, ScaledPolynomial[2,4] + '
+        'warmup': args.warmup, 'ms_per_step': (ts + tf) * 1e3, 'higher_is_better': True,
+        'scaling': 'weak' if args.gpus == 1 else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'corridor, full-res os0-128 scans, kNN k=%d within r=%.1f m, ScaledPolynomial[2,4] + '
                                'min_eigval_loss(normalization) + per-scan SE(3) corrections; bounded CPU sample: %s'
-                               % (args.pattern, NN_K, NN_R, sample), 'n_points': n, 'k': NN_K, 'r': NN_R},
+                               % (NN_K, NN_R, sample), 'n_points': n, 'k': NN_K, 'r': NN_R},
         'search_ms': ts * 1e3, 'fixed_graph_step_ms': tf * 1e3, 'loss': loss,
         'cpu_baseline': {'value': value, 'unit': 'points/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -521,7 +726,6 @@ def run_reference(args):
 
 if __name__ == '__main__':
     a = parse_args()
-    SCENE = a.scene
     if a.impl == 'reference':
         run_reference(a)
     else:

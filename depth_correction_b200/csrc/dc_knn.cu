@@ -24,17 +24,9 @@
 #define KNN_BINS 64
 
 // (d2, original index) lexicographic order.  The original index (dc_point.tag) -- not the position in the cell-sorted
-// map -- breaks exact ties, so the selected set does not depend on the cell size.  The tag is only loaded when two
-// squared distances are bit-equal; j >= n stands for "no candidate" and sorts last.
-__device__ __noinline__ bool knn_tie(const dc_point* __restrict__ P, int64_t n, int ja, int jb) {
-  // out of line: exact ties are rare, and inlined the 64-bit tag loads cost the scan loops eight registers
-  const long long ta = (ja >= 0 && (int64_t)ja < n) ? P[ja].tag : (ja < 0 ? -1LL : 0x7fffffffffffffffLL);
-  const long long tb = (jb >= 0 && (int64_t)jb < n) ? P[jb].tag : (jb < 0 ? -1LL : 0x7fffffffffffffffLL);
-  return ta < tb;
-}
-__device__ __forceinline__ bool knn_less(const dc_point* __restrict__ P, int64_t n, double a, int ja, double b, int jb) {
-  return a < b || (a == b && knn_tie(P, n, ja, jb));
-}
+// map -- breaks exact ties, so the selected set does not depend on the cell size.  The scans hand the tag of every
+// candidate to their callbacks (it is part of the record they load anyway); 0x7fffffff stands for "no candidate".
+__device__ __forceinline__ bool knn_less(double a, int ta, double b, int tb) { return a < b || (a == b && ta < tb); }
 
 __device__ __forceinline__ int knn_bin(double d2, double scale) {
   const int b = __double2int_rz(d2 * scale);
@@ -59,10 +51,11 @@ __device__ __forceinline__ void knn_scan(const dc_grid& g, const uint64_t* __res
         const dc_point p0 = dc_ld_point(P + j), p1 = dc_ld_point(P + j1);
         const dc_point p2 = dc_ld_point(P + j2), p3 = dc_ld_point(P + j3);
         const double d0 = dc_dist2(p0, pq), d1 = dc_dist2(p1, pq), d2 = dc_dist2(p2, pq), d3 = dc_dist2(p3, pq);
-        f(j, d0);
-        if (j + 1 < hi) f(j + 1, d1);
-        if (j + 2 < hi) f(j + 2, d2);
-        if (j + 3 < hi) f(j + 3, d3);
+        // third argument: the ORIGINAL index of the candidate (tag of its record, already loaded), the tie-break key
+        f(j, d0, (int)p0.tag);
+        if (j + 1 < hi) f(j + 1, d1, (int)p1.tag);
+        if (j + 2 < hi) f(j + 2, d2, (int)p2.tag);
+        if (j + 3 < hi) f(j + 3, d3, (int)p3.tag);
       }
     }
   }
@@ -74,7 +67,7 @@ __device__ __forceinline__ void knn_scan(const dc_grid& g, const uint64_t* __res
 // histogram level splits the boundary bin when it holds more than 8 candidates.
 // ---------------------------------------------------------------------------------------------
 template <typename Emit>
-__device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
+__device__ __forceinline__ bool knn_thread_query(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
                                                  const dc_grid& g, const int32_t* __restrict__ cell_start,
                                                  const dc_point& pq, int c0, int c1, int c2, int k, double r2cap,
                                                  int max_ring, int first_ring, unsigned short* h, Emit&& emit) {
@@ -92,7 +85,7 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
 #pragma unroll
     for (int b = 0; b < KNN_BINS; ++b) h[b * KNN_THREADS] = (unsigned short)0;
     n_in = 0u;
-    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
+    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2, int tag) {
       if (d2 < bound2) {
         const int b = knn_bin(d2, scale1);
         const unsigned short v = h[b * KNN_THREADS];
@@ -105,10 +98,10 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
   }
   if (n_in <= (unsigned int)k) {
     // everything inside the bound is a neighbour (fewer than k exist within r / in the map)
-    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
+    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2, int tag) {
       if (d2 < bound2) emit(j, d2);
     });
-    return;
+    return true;
   }
   // ---- level 1: bin of the k-th distance
   unsigned int c_lo = 0u, cnt1 = 0u;
@@ -125,7 +118,7 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
     // ---- 2. level-2 histogram inside bin b1
 #pragma unroll
     for (int b = 0; b < KNN_BINS; ++b) h[b * KNN_THREADS] = (unsigned short)0;
-    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
+    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2, int tag) {
       if (d2 < bound2) {
         const double s = d2 * scale1;
         int b = __double2int_rz(s);
@@ -152,7 +145,7 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
   // column, which is no longer needed) and ranked afterwards with the warp converged: ranking inside the scan ran one lane at a time and
   // cost 17 % of all instructions of the kernel.
   int nb = 0;
-  knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
+  knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2, int tag) {
     if (d2 < bound2) {
       const double s = d2 * scale1;
       int b = __double2int_rz(s);
@@ -171,52 +164,56 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
           if (take_all) {
             emit(j, d2);
           } else if (use_list && nb < 8) {
-            // the histogram is dead by now: entry nb lives in this thread's counters 6 nb .. 6 nb + 5
-            // (four 16-bit pieces of d2, two of j), which keeps the block at 16 KB of shared memory
+            // the histogram is dead by now: entry nb lives in this thread's counters 8 nb .. 8 nb + 7 (four 16-bit
+            // pieces of d2, two of j, two of the original index = tie-break key): 8 entries fill the 64 counters
+            // exactly, which keeps the block at 16 KB of shared memory
             const unsigned long long u = (unsigned long long)__double_as_longlong(d2);
-            unsigned short* e = h + 6 * nb * KNN_THREADS;
+            unsigned short* e = h + 8 * nb * KNN_THREADS;
             e[0] = (unsigned short)u;
             e[KNN_THREADS] = (unsigned short)(u >> 16);
             e[2 * KNN_THREADS] = (unsigned short)(u >> 32);
             e[3 * KNN_THREADS] = (unsigned short)(u >> 48);
             e[4 * KNN_THREADS] = (unsigned short)j;
             e[5 * KNN_THREADS] = (unsigned short)((unsigned int)j >> 16);
+            e[6 * KNN_THREADS] = (unsigned short)tag;
+            e[7 * KNN_THREADS] = (unsigned short)((unsigned int)tag >> 16);
             ++nb;
           }
         }
       }
     }
   });
-  if (take_all) return;
+  if (take_all) return true;
   if (use_list) {
     double bd[8];
-    int bj[8];
+    int bj[8], bt[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const unsigned short* e = h + 6 * i * KNN_THREADS;
+      const unsigned short* e = h + 8 * i * KNN_THREADS;
       const unsigned long long u = (unsigned long long)e[0] | ((unsigned long long)e[KNN_THREADS] << 16) |
                                    ((unsigned long long)e[2 * KNN_THREADS] << 32) | ((unsigned long long)e[3 * KNN_THREADS] << 48);
       const int j = (int)((unsigned int)e[4 * KNN_THREADS] | ((unsigned int)e[5 * KNN_THREADS] << 16));
       bd[i] = i < nb ? __longlong_as_double((long long)u) : INFINITY;
       bj[i] = i < nb ? j : 0x7fffffff;
+      bt[i] = i < nb ? (int)((unsigned int)e[6 * KNN_THREADS] | ((unsigned int)e[7 * KNN_THREADS] << 16)) : 0x7fffffff;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      unsigned int rank = 0u;          // candidates of the bin that precede candidate i in (d2, index) order
+      unsigned int rank = 0u;          // candidates of the bin that precede candidate i in (d2, original index) order
 #pragma unroll
-      for (int m = 0; m < 8; ++m) rank += knn_less(P, n, bd[m], bj[m], bd[i], bj[i]) ? 1u : 0u;
+      for (int m = 0; m < 8; ++m) rank += knn_less(bd[m], bt[m], bd[i], bt[i]) ? 1u : 0u;
       if (i < nb && rank < t) emit(bj[i], bd[i]);
     }
-    return;
+    return true;
   }
   // more than 8 candidates share the boundary sub-bin (exact ties / duplicates): repeated minimum
-  // selection in (d2, index) order -- O(t * candidates), rare
+  // selection in (d2, original index) order -- O(t * candidates), rare
   double last_d = -1.0;
-  int last_j = -1;
+  int last_t = -1;
   for (unsigned int s_ = 0; s_ < t; ++s_) {
     double best_d = INFINITY;
-    int best_j = 0x7fffffff;
-    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
+    int best_j = 0x7fffffff, best_t = 0x7fffffff;
+    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2, int tag) {
       if (d2 < bound2) {
         const double s = d2 * scale1;
         int b = __double2int_rz(s);
@@ -227,17 +224,19 @@ __device__ __forceinline__ void knn_thread_query(const dc_point* __restrict__ P,
             bb = __double2int_rz((s - (double)b1) * (double)KNN_BINS);
             bb = bb < 0 ? 0 : (bb > KNN_BINS - 1 ? KNN_BINS - 1 : bb);
           }
-          if (bb == b2 && knn_less(P, n, last_d, last_j, d2, j) && knn_less(P, n, d2, j, best_d, best_j)) {
+          if (bb == b2 && knn_less(last_d, last_t, d2, tag) && knn_less(d2, tag, best_d, best_t)) {
             best_d = d2;
             best_j = j;
+            best_t = tag;
           }
         }
       }
     });
     emit(best_j, best_d);
     last_d = best_d;
-    last_j = best_j;
+    last_t = best_t;
   }
+  return true;
 }
 
 __global__ void __launch_bounds__(KNN_THREADS, 8)
@@ -792,7 +791,7 @@ knn_cell_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pke
 }
 
 // the queries the cell kernel could not finish, one per thread, exact fp64 selection
-__global__ void __launch_bounds__(KNN_THREADS)
+__global__ void __launch_bounds__(KNN_THREADS, 8)
 knn_thread_list_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
                        const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, dc_grid g,
                        const int32_t* __restrict__ cell_start, int k, double r2cap, int max_ring,
@@ -938,7 +937,7 @@ __global__ void knn_sort_rows_kernel(const dc_point* __restrict__ P, int64_t n, 
     if (jj < 0) continue;
     const double dd = pd[(int64_t)c * DC_SLICE];
     int pos = m++;
-    while (pos > 0 && knn_less(P, n, dd, jj, d[pos - 1], j[pos - 1])) { d[pos] = d[pos - 1]; j[pos] = j[pos - 1]; --pos; }
+    while (pos > 0 && knn_less(dd, (int)P[jj].tag, d[pos - 1], (int)P[j[pos - 1]].tag)) { d[pos] = d[pos - 1]; j[pos] = j[pos - 1]; --pos; }
     d[pos] = dd;
     j[pos] = jj;
   }
@@ -989,3 +988,4 @@ extern "C" int dc_knn_distances(const void* P, const void* Q, int k, const int32
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
+

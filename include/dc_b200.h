@@ -108,7 +108,7 @@ int dc_radius_fill(const void* P, const uint64_t* pkeys, int64_t n, const void* 
 int dc_knn(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
            const dc_grid_spec* spec_host, const int32_t* cell_start, int k, double r, int32_t* ell_idx, double* ell_d2,
            void* stream);
-/* The same search, one WARP per occupied query cell (the fast path for k <= 128): the candidate block of a cell is
+/* The same search, one WARP per occupied query cell (k <= 128; an independent second implementation, used as a cross-check): the candidate block of a cell is
  * staged once in registers as fp32 offsets from the cell centre, the cell's queries are streamed through it with a
  * shared-memory histogram select, and every query whose fp32 classification is not provably the fp64 one (plus cells
  * whose block exceeds the register slots or needs more than four rings) is finished by the fp64 one-thread-per-query

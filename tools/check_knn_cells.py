@@ -27,7 +27,7 @@ def rows_sorted(g):
 
 def timed_search(pts, query, k, r, path, cell=None, reps=3):
     os.environ['DC_KNN'] = path
-    name = 'dc_knn_cells' if path == 'cells' else 'dc_knn'
+    name = {'cells': 'dc_knn_cells', 'thread': 'dc_knn'}[path]
     best, g = None, None
     for _ in range(reps):
         del g
