@@ -220,6 +220,8 @@ class Job(object):
         self.deltas = torch.zeros((n_scans_total, 6), dtype=torch.float64, device=dev, requires_grad=True)
         self.model = dc.ScaledPolynomial(w=[0.0, 0.0], exponent=[2, 4], device=dev)
         self.setup_ms = 0.0
+        if world > 1:
+            self.repartition(self.ingested)          # (first exchange of the process: NCCL connection set-up, untimed)
         self.clouds, self.local = self.repartition(self.ingested, timed=True)
         self.n_local = sum(len(c) for c in self.clouds) if self.local is None else int(self.local.owned.sum().item())
         self.n_resident = sum(len(c) for c in self.clouds)
@@ -620,6 +622,7 @@ def run_ours(args):
         line['strong_scaling'] = {'workload': 'street, %d HDL-64 scans (BASELINE.json configs[2]) on ONE GPU: anchor of the --gpus N > 1 lines'
                                               % args.scans_total, 'n_points': sm['n_total'], 'value': sm['value'],
                                   'ms_per_step': sm['ms_per_step'], 'search_ms': sm['search_ms'], 'fixed_graph_step_ms': sfixed,
+                                  'loss': sm['loss'],
                                   'headline_frac_of_roofline': round(HEADLINE_BYTES_PER_POINT * sm['n_total'] / (sm['ms_per_step'] * 1e-3) / 1e9 / peak, 4)}
         del sjob, sm
         L.release_workspace()

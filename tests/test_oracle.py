@@ -1,5 +1,7 @@
 """Pins the CPU oracle (oracle/oracle.py) to golden vectors produced by the unmodified
 reference (oracle/make_golden.py), and live to the reference when /root/reference exists."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -165,3 +167,18 @@ def test_icp_loss_against_reference(golden, tag, p2pl, use_masks):
     assert abs(loss - float(g[tag + '_loss'])) <= 1e-5 * abs(float(g[tag + '_loss']))
     assert rel_err_norm(gw, g[tag + '_w_grad']) < 1e-4
     assert rel_err_norm(gp, g[tag + '_poses_grad']) < 1e-4
+
+
+def test_dropin_fixture_is_the_reference_loop():
+    """tests/golden/dropin_loop.txt (executed on the GPU box by tests/test_dropin.py) is still, verbatim, the loop body
+    of the reference's scripts/model_poses_learning."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    if not os.path.exists('/root/reference/scripts/model_poses_learning'):
+        pytest.skip('reference tree not present')
+    spec = importlib.util.spec_from_file_location('make_dropin_fixture', os.path.join(here, 'golden', 'make_dropin_fixture.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    body, first, last = mod.loop_body()
+    assert (first, last) == (121, 135)
+    assert body == open(os.path.join(here, 'golden', 'dropin_loop.txt')).read()
