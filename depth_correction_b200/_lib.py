@@ -95,7 +95,7 @@ SIGNATURES = {
     'dc_icp_backward': [_P, _P, _I, _P, _P, _I, _P, _P, _D, _P, _P, _L, _I, _P, _P, _P, _P, _P, _P],
     'dc_f64_sort_keys': [_P, _L, _P, _P, _P],
     'dc_f64_from_sort_keys': [_P, _L, _P, _P],
-    'dc_route_count': [_P, _I, _L, _P, _I, _D, _P, _P, _P, _P],
+    'dc_route_count': [_P, _I, _L, _P, _I, _D, _P, _P, _I, _P, _P, _P, _P, _I, _P],
     'dc_route_pack': [_P, _P, _P, _I, _L, _I, _P, _I, _P, _I, _D, _P, _P, _P, _P, _P, _P, _P],
     'dc_axis_histogram': [_P, _I, _L, _D, _D, _I, _P, _P],
     'dc_route_keys': [_P, _L, _P, _P, _P],

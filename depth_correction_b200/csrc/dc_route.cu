@@ -18,7 +18,7 @@ struct dc_scan_ptrs {
 #define DC_ROUTE_MAX_RANKS 64
 
 struct dc_route_bounds {
-  double inner[DC_ROUTE_MAX_RANKS];     // inner[g] = lower boundary of slab g + 1 (n_ranks - 1 values)
+  const double* inner;                  // DEVICE array: inner[g] = lower boundary of slab g + 1 (n_ranks - 1 values)
   int n_ranks;
   double halo;
 };
@@ -35,12 +35,16 @@ __device__ __forceinline__ int dc_route_find_scan(const int64_t* __restrict__ fi
 // number of inner boundaries <= v  (== torch.bucketize(v, inner, right=True))
 __device__ __forceinline__ int dc_route_bucket(const dc_route_bounds& b, double v) {
   int c = 0;
-  for (int g = 0; g < b.n_ranks - 1; ++g) c += (b.inner[g] <= v);
+  for (int g = 0; g < b.n_ranks - 1; ++g) c += (__ldg(b.inner + g) <= v);
   return c;
 }
 
+// scan_counts (optional): int32 [n_ranks][scan_stride], records per (destination, GLOBAL scan id) -- lets the receiver
+// know the size of every scan it will hold without looking at the data (no read-back after the exchange)
 __global__ void route_count_kernel(const double* __restrict__ wp, int axis, int64_t n, dc_route_bounds b,
-                                   uint8_t* __restrict__ gmin, uint8_t* __restrict__ gmax, int32_t* __restrict__ counts) {
+                                   const int64_t* __restrict__ first, const int32_t* __restrict__ scan_ids, int n_scans,
+                                   uint8_t* __restrict__ gmin, uint8_t* __restrict__ gmax, int32_t* __restrict__ counts,
+                                   int32_t* __restrict__ scan_counts, int scan_stride) {
   __shared__ int s_cnt[DC_ROUTE_MAX_RANKS];
   if (threadIdx.x < DC_ROUTE_MAX_RANKS) s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -51,6 +55,16 @@ __global__ void route_count_kernel(const double* __restrict__ wp, int axis, int6
     gmin[i] = (uint8_t)lo;
     gmax[i] = (uint8_t)hi;
     for (int g = lo; g <= hi; ++g) atomicAdd(&s_cnt[g], 1);
+    if (scan_counts) {
+      // consecutive points belong to the same scan and mostly to the same slab: aggregate equal (scan, destination)
+      // pairs inside the warp before touching the global counter
+      const int sid = scan_ids[dc_route_find_scan(first, n_scans, i)];
+      for (int g = lo; g <= hi; ++g) {
+        const unsigned key = (unsigned)sid * DC_ROUTE_MAX_RANKS + (unsigned)g;
+        const unsigned peers = __match_any_sync(__activemask(), key);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&scan_counts[(int64_t)g * scan_stride + sid], __popc(peers));
+      }
+    }
   }
   __syncthreads();
   if (threadIdx.x < b.n_ranks && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
@@ -90,17 +104,22 @@ __global__ void route_pack_kernel(const dc_scan_ptrs* __restrict__ tbl, const in
 }
 
 extern "C" int dc_route_count(const double* world_points, int axis, int64_t n, const double* inner_boundaries, int n_ranks,
-                              double halo, uint8_t* gmin, uint8_t* gmax, int32_t* counts, void* stream) {
+                              double halo, const int64_t* first, const int32_t* scan_ids, int n_scans, uint8_t* gmin,
+                              uint8_t* gmax, int32_t* counts, int32_t* scan_counts, int scan_stride, void* stream) {
   if (n_ranks < 1 || n_ranks > DC_ROUTE_MAX_RANKS) return dc_set_error(DC_ERR_ARG, "dc_route_count: 1..64 ranks");
   if (axis < 0 || axis > 2) return dc_set_error(DC_ERR_ARG, "dc_route_count: axis must be 0, 1 or 2");
+  if (scan_counts && (!first || !scan_ids || n_scans < 1 || scan_stride < 1))
+    return dc_set_error(DC_ERR_ARG, "dc_route_count: scan_counts needs the scan table");
   cudaStream_t st = (cudaStream_t)stream;
   DC_CUDA_CHECK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_ranks, st));
+  if (scan_counts) DC_CUDA_CHECK(cudaMemsetAsync(scan_counts, 0, sizeof(int32_t) * (size_t)n_ranks * scan_stride, st));
   if (n <= 0) return DC_OK;
   dc_route_bounds b;
   b.n_ranks = n_ranks;
   b.halo = halo;
-  for (int g = 0; g < n_ranks - 1; ++g) b.inner[g] = inner_boundaries[g];      // HOST array
-  route_count_kernel<<<dc_blocks(n, 256), 256, 0, st>>>(world_points, axis, n, b, gmin, gmax, counts);
+  b.inner = inner_boundaries;      // DEVICE array (the slab plan stays on the device)
+  route_count_kernel<<<dc_blocks(n, 256), 256, 0, st>>>(world_points, axis, n, b, first, scan_ids, n_scans, gmin, gmax, counts,
+                                                        scan_counts, scan_stride);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
@@ -116,7 +135,7 @@ extern "C" int dc_route_pack(const void* scan_ptr_table, const int64_t* first, c
   dc_route_bounds b;
   b.n_ranks = n_ranks;
   b.halo = halo;
-  for (int g = 0; g < n_ranks - 1; ++g) b.inner[g] = inner_boundaries[g];
+  b.inner = inner_boundaries;      // DEVICE array
   const dc_scan_ptrs* tbl = (const dc_scan_ptrs*)scan_ptr_table;
   if (dtype == DC_F32)
     route_pack_kernel<float><<<dc_blocks(n, 256), 256, 0, st>>>(tbl, first, scan_ids, n_scans, n, world_points, axis, b, gmin, gmax, dest_offset,

@@ -27,6 +27,7 @@ from .depth_cloud import DepthCloud
 __all__ = ['LocalMap', 'SlabPartitioner', 'distributed_quantile', 'reduce_step', 'sharded_inlier_sum_count']
 
 N_HIST_BINS = 1 << 14
+SCAN_ID_CAP = 4096          # global scan ids the GPU exchange counts per destination (more scans: torch form)
 
 
 class LocalMap(object):
@@ -38,7 +39,7 @@ class LocalMap(object):
         self.owned = owned              # bool [N_local] in concatenated order: this rank owns the loss term
         self.global_ids = global_ids    # int64 [N_local, 2] = (global scan id, row inside that scan)
         self.axis = axis
-        self.bounds = bounds            # (lo, hi) of this rank's slab along `axis`
+        self.bounds = bounds            # (lo, hi) of this rank's slab along `axis` (floats, or a device tensor [2])
 
     def __len__(self):
         return int(self.owned.numel())
@@ -121,7 +122,7 @@ class SlabPartitioner(object):
         """
         assert len(clouds) == len(scan_ids)
         G = self.world
-        if clouds and clouds[0].depth.is_cuda and G <= 64:
+        if clouds and clouds[0].depth.is_cuda and G <= 64 and max(int(s) for s in scan_ids) < SCAN_ID_CAP:
             return self._exchange_cuda(clouds, scan_ids, world_points, axis, boundaries, halo)
         dev = clouds[0].depth.device if clouds else torch.device('cpu')
         dt = clouds[0].depth.dtype if clouds else torch.float32
@@ -194,11 +195,11 @@ class SlabPartitioner(object):
                         (float(boundaries[self.rank]), float(boundaries[self.rank + 1])))
 
     def _exchange_cuda(self, clouds, scan_ids, world_points, axis, boundaries, halo):
-        """GPU form of SlabPartitioner.exchange: routing, packing and unpacking in four kernels (dc_route_*), two
-        all-to-alls, three small read-backs (send counts, receive counts, per-scan sizes).  Same result as the torch
-        form above (which the CPU / gloo tests exercise) up to the arbitrary order inside a destination, which the
-        (scan, row) sort on the receiving side removes."""
-        import ctypes
+        """GPU form of SlabPartitioner.exchange: routing, packing and unpacking in four kernels (dc_route_*), one small
+        and two payload all-to-alls, and ONE host read-back (the send / receive counts NCCL needs on the host; the same
+        transfer carries the size of every scan this rank will hold, counted per (destination, scan) while routing).
+        The slab boundaries stay on the device.  Same result as the torch form above (which the CPU / gloo tests
+        exercise) up to the arbitrary order inside a destination, which the (scan, row) sort on the receiving side removes."""
         from . import _lib as L
         from .fused import scan_table
         G = self.world
@@ -211,21 +212,35 @@ class SlabPartitioner(object):
         wp = wp.detach().reshape(-1, 3).to(torch.float64).contiguous()
         assert wp.shape[0] == n
         tbl, first, _keep = scan_table(clouds, dt)
-        sid_t = L.upload([int(s) for s in scan_ids], torch.int32, dev)
-        inner = [float(v) for v in boundaries[1:-1].tolist()]
-        inner_c = (ctypes.c_double * max(len(inner), 1))(*inner)
+        ids_host = [int(s) for s in scan_ids]
+        sid_t = L.upload(ids_host, torch.int32, dev)
+        S_cap = SCAN_ID_CAP
+        assert max(ids_host) < S_cap, 'scan ids must be below %d' % S_cap
+        inner = boundaries[1:-1].to(device=dev, dtype=torch.float64).contiguous()
+        if inner.numel() == 0:
+            inner = torch.zeros(1, dtype=torch.float64, device=dev)
         gmin = torch.empty(n, dtype=torch.uint8, device=dev)
         gmax = torch.empty(n, dtype=torch.uint8, device=dev)
+        # header row g = {records for destination g, records of every scan for destination g}
+        header = torch.empty((G, 1 + S_cap), dtype=torch.int32, device=dev)
         counts = torch.empty(G, dtype=torch.int32, device=dev)
-        L.call('dc_route_count', L.ptr(wp), int(axis), n, inner_c, G, float(halo), L.ptr(gmin), L.ptr(gmax), L.ptr(counts), st)
-        counts64 = counts.long()
-        recv = torch.empty_like(counts64)
+        scan_counts = torch.empty((G, S_cap), dtype=torch.int32, device=dev)
+        L.call('dc_route_count', L.ptr(wp), int(axis), n, L.ptr(inner), G, float(halo), L.ptr(first), L.ptr(sid_t), len(clouds),
+               L.ptr(gmin), L.ptr(gmax), L.ptr(counts), L.ptr(scan_counts), S_cap, st)
+        header[:, 0] = counts
+        header[:, 1:] = scan_counts
+        recv_header = torch.empty_like(header)
         if G > 1:
-            dist.all_to_all_single(recv, counts64, group=self.group)
+            dist.all_to_all_single(recv_header, header, group=self.group)
         else:
-            recv.copy_(counts64)
-        both = torch.stack([counts64, recv]).tolist()                 # read-back 1 + 2
-        send_counts, recv_counts = both[0], both[1]
+            recv_header.copy_(header)
+        # THE host read-back: send counts, receive counts, sizes of the scans this rank will hold
+        scan_sizes = recv_header[:, 1:].sum(dim=0, dtype=torch.int64)
+        host = torch.cat([counts.long(), recv_header[:, 0].long(), scan_sizes]).cpu()
+        send_counts, recv_counts = host[:G].tolist(), host[G:2 * G].tolist()
+        sizes_all = host[2 * G:]
+        present = torch.nonzero(sizes_all)[:, 0]
+        sids_host, sizes_l = present.tolist(), sizes_all[present].tolist()
         offs = [0]
         for c in send_counts[:-1]:
             offs.append(offs[-1] + c)
@@ -234,11 +249,12 @@ class SlabPartitioner(object):
         cursor = torch.empty(G, dtype=torch.int32, device=dev)
         send_f = torch.empty((m_send, 8), dtype=dt, device=dev)
         send_i = torch.empty((m_send, 4), dtype=torch.int32, device=dev)
-        L.call('dc_route_pack', L.ptr(tbl), L.ptr(first), L.ptr(sid_t), len(clouds), n, code, L.ptr(wp), int(axis), inner_c, G, float(halo),
+        L.call('dc_route_pack', L.ptr(tbl), L.ptr(first), L.ptr(sid_t), len(clouds), n, code, L.ptr(wp), int(axis), L.ptr(inner), G, float(halo),
                L.ptr(gmin), L.ptr(gmax), L.ptr(dest_offset), L.ptr(cursor), L.ptr(send_f), L.ptr(send_i), st)
         rf = self._all_to_all(send_f, send_counts, recv_counts)
         ri = self._all_to_all(send_i, send_counts, recv_counts)
         m = rf.shape[0]
+        assert m == sum(sizes_l)
         keys = torch.empty(m, dtype=torch.int64, device=dev)
         ids = torch.empty(m, dtype=torch.int32, device=dev)
         skeys = torch.empty(m, dtype=torch.int64, device=dev)
@@ -252,17 +268,19 @@ class SlabPartitioner(object):
         gid = torch.empty((m, 2), dtype=torch.int64, device=dev)
         if m > 0:
             L.call('dc_route_keys', L.ptr(ri), m, L.ptr(keys), L.ptr(ids), st)
-            L.call_with_temp('dc_sort_pairs', dev, L.ptr(keys), L.ptr(skeys), L.ptr(ids), L.ptr(order), m, 63, after=(st,))
+            # keys = scan id << 32 | row: only the bits that can be set are sorted
+            key_bits = 32 + max(1, int(max(sids_host)).bit_length())
+            L.call_with_temp('dc_sort_pairs', dev, L.ptr(keys), L.ptr(skeys), L.ptr(ids), L.ptr(order), m, key_bits, after=(st,))
             L.call('dc_route_unpack', L.ptr(rf), L.ptr(ri), L.ptr(order), m, code, L.ptr(f_vps), L.ptr(f_dirs), L.ptr(f_depth), L.ptr(f_inc),
                    L.ptr(f_mask.view(torch.uint8)), L.ptr(f_owned.view(torch.uint8)), L.ptr(gid), st)
-        sids, sizes_l = torch.unique_consecutive(gid[:, 0], return_counts=True)          # read-back 3
         local_clouds, first_row = [], 0
-        for sz in sizes_l.tolist():
+        for sz in sizes_l:
             local_clouds.append(DepthCloud(vps=f_vps[first_row:first_row + sz], dirs=f_dirs[first_row:first_row + sz],
                                            depth=f_depth[first_row:first_row + sz], inc_angles=f_inc[first_row:first_row + sz],
                                            mask=f_mask[first_row:first_row + sz]))
             first_row += sz
-        return LocalMap(local_clouds, sids, f_owned, gid, axis, (float(boundaries[self.rank]), float(boundaries[self.rank + 1])))
+        sids = L.upload(sids_host, torch.int64, dev)
+        return LocalMap(local_clouds, sids, f_owned, gid, axis, boundaries[self.rank:self.rank + 2])
 
 
 def reduce_step(sum_count, params, group=None):

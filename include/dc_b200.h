@@ -334,10 +334,14 @@ int dc_f64_from_sort_keys(const uint64_t* keys, int64_t n, double* x, void* stre
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU slab exchange (no counterpart in the single-process reference).  Slab g of
- * n_ranks owns b[g] <= x < b[g+1] along the split axis (inner_boundaries = b[1] .. b[n_ranks-1], a HOST array);
+ * n_ranks owns b[g] <= x < b[g+1] along the split axis (inner_boundaries = b[1] .. b[n_ranks-1], a DEVICE array:
+ * the slab plan never leaves the device);
  * a point is sent to every slab with b[g] - halo <= x < b[g+1] + halo.
  *   dc_route_count : gmin / gmax (uint8 [n]) = first / last destination of every point of world_points (fp64 [n,3]),
- *                    counts int32 [n_ranks] = records per destination
+ *                    counts int32 [n_ranks] = records per destination; scan_counts (optional) int32 [n_ranks][scan_stride]
+ *                    = records per (destination, GLOBAL scan id scan_ids[s] < scan_stride) with first / scan_ids / n_scans
+ *                    as in dc_route_pack, so that a receiver learns the size of every scan it will hold from the count
+ *                    exchange alone
  *   dc_route_pack  : send_f [M,8] (cloud dtype: vp.xyz, dir.xyz, depth, inc_angle) and send_i int32 [M,4] (scan id,
  *                    row, model mask, owned) contiguous per destination (dest_offset int64 [n_ranks] = exclusive sum of
  *                    counts; cursor int32 [n_ranks] scratch), read through the scan pointer table of
@@ -347,7 +351,8 @@ int dc_f64_from_sort_keys(const uint64_t* keys, int64_t n, double* x, void* stre
  *                    uint8 [m], gid int64 [m,2] = (scan id, row)
  * ------------------------------------------------------------------------------------------- */
 int dc_route_count(const double* world_points, int axis, int64_t n, const double* inner_boundaries, int n_ranks, double halo,
-                   uint8_t* gmin, uint8_t* gmax, int32_t* counts, void* stream);
+                   const int64_t* first, const int32_t* scan_ids, int n_scans, uint8_t* gmin, uint8_t* gmax, int32_t* counts,
+                   int32_t* scan_counts, int scan_stride, void* stream);
 int dc_route_pack(const void* scan_ptr_table, const int64_t* first, const int32_t* scan_ids, int n_scans, int64_t n, int dtype,
                   const double* world_points, int axis, const double* inner_boundaries, int n_ranks, double halo,
                   const uint8_t* gmin, const uint8_t* gmax, const int64_t* dest_offset, int32_t* cursor, void* send_f,
