@@ -21,7 +21,7 @@ SLICE = 32
 
 class GridSpec(ctypes.Structure):
     _fields_ = [('origin', ctypes.c_double * 3), ('cell', ctypes.c_double),
-                ('dims', ctypes.c_int32 * 3), ('axis', ctypes.c_int32 * 3)]
+                ('dims', ctypes.c_int32 * 3), ('axis', ctypes.c_int32 * 3), ('sub_bits', ctypes.c_int32)]
 
 
 class DcError(RuntimeError):
@@ -51,7 +51,7 @@ SIGNATURES = {
     'dc_cell_keys': [_P, _I, _L, _SPEC, _P, _P, _P],
     'dc_sort_pairs': [_P, _P, _P, _P, _L, _I, _P, _SZP, _P],
     'dc_gather_points': [_P, _I, _P, _L, _P, _P, _P],
-    'dc_cell_table': [_P, _L, _L, _P, _P],
+    'dc_cell_table': [_P, _L, _L, _I, _P, _P],
     'dc_radius_count': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _D, _P, _P, _P],
     'dc_ell_offsets': [_P, _L, _P, _P, _SZP, _P],
     'dc_radius_fill': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _D, _P, _P, _P],

@@ -94,7 +94,18 @@ __global__ void cell_keys_kernel(const T* __restrict__ pts, int64_t n, dc_grid g
   const double p[3] = {(double)pts[3 * i], (double)pts[3 * i + 1], (double)pts[3 * i + 2]};
   int c0, c1, c2;
   dc_cell_coords(g, p, c0, c1, c2);
-  keys[i] = dc_cell_key(g, c0, c1, c2);
+  uint64_t key = dc_cell_key(g, c0, c1, c2);
+  if (g.sub_bits) {
+    // 4x4x4 sub-cell of the point inside its cell, Morton-interleaved: the order of the points INSIDE a cell (any order
+    // is correct for the search) becomes spatially coherent
+    const double f0 = (p[g.ax[0]] - g.org[0]) * g.inv_cell - (double)c0, f1 = (p[g.ax[1]] - g.org[1]) * g.inv_cell - (double)c1,
+                 f2 = (p[g.ax[2]] - g.org[2]) * g.inv_cell - (double)c2;
+    const unsigned s0 = (unsigned)dc_clampi((int)(f0 * 4.0), 0, 3), s1 = (unsigned)dc_clampi((int)(f1 * 4.0), 0, 3),
+                   s2 = (unsigned)dc_clampi((int)(f2 * 4.0), 0, 3);
+    const unsigned m = (s0 & 1u) | ((s1 & 1u) << 1) | ((s2 & 1u) << 2) | ((s0 & 2u) << 2) | ((s1 & 2u) << 3) | ((s2 & 2u) << 4);
+    key = (key << g.sub_bits) | (uint64_t)m;
+  }
+  keys[i] = key;
   ids[i] = (int32_t)i;
 }
 
@@ -125,6 +136,8 @@ int dc_make_grid(const dc_grid_spec* spec, dc_grid* g) {
     g->d[a] = spec->dims[spec->axis[a]];
     g->org[a] = spec->origin[spec->axis[a]];
   }
+  if (spec->sub_bits != 0 && spec->sub_bits != 6) return dc_set_error(DC_ERR_ARG, "grid spec: sub_bits must be 0 or 6");
+  g->sub_bits = spec->sub_bits;
   g->cell = spec->cell;
   g->inv_cell = 1.0 / spec->cell;
   const double cells = (double)g->d[0] * (double)g->d[1] * (double)g->d[2];
@@ -209,13 +222,13 @@ extern "C" int dc_gather_points(const void* pts, int dtype, const int32_t* order
 // (key[s-1], key[s]] (and position n the cells above the last key); a warp fills the gaps of its 32 positions
 // cooperatively, so a long run of empty cells costs one coalesced sweep instead of one thread's serial loop
 // (the previous version did a 23-step binary search for each of the ~14 M cells of the bench grid).
-__global__ void cell_table_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t n_cells, int32_t* __restrict__ cell_start) {
+__global__ void cell_table_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t n_cells, int sub_bits, int32_t* __restrict__ cell_start) {
   const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;     // 0 .. n (inclusive), rounded up to a warp
   const int lane = threadIdx.x & 31;
   int64_t first = 0, last = -1;      // cells first .. last get the value s
   if (s <= n) {
-    first = s == 0 ? 0 : (int64_t)keys[s - 1] + 1;
-    last = s == n ? n_cells : (int64_t)keys[s];
+    first = s == 0 ? 0 : (int64_t)(keys[s - 1] >> sub_bits) + 1;
+    last = s == n ? n_cells : (int64_t)(keys[s] >> sub_bits);
   }
   const int64_t len = last - first + 1;
   if (len > 0 && len <= 4) {         // the common case: a handful of empty cells between occupied ones
@@ -231,10 +244,10 @@ __global__ void cell_table_kernel(const uint64_t* __restrict__ keys, int64_t n, 
   }
 }
 
-extern "C" int dc_cell_table(const uint64_t* keys_sorted, int64_t n, int64_t n_cells, int32_t* cell_start, void* stream) {
+extern "C" int dc_cell_table(const uint64_t* keys_sorted, int64_t n, int64_t n_cells, int sub_bits, int32_t* cell_start, void* stream) {
   if (n_cells < 0 || n < 0) return dc_set_error(DC_ERR_ARG, "dc_cell_table: negative size");
   const int64_t threads = ((n + 1 + 31) / 32) * 32;
-  cell_table_kernel<<<dc_blocks(threads, 256), 256, 0, (cudaStream_t)stream>>>(keys_sorted, n, n_cells, cell_start);
+  cell_table_kernel<<<dc_blocks(threads, 256), 256, 0, (cudaStream_t)stream>>>(keys_sorted, n, n_cells, sub_bits, cell_start);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

@@ -9,6 +9,7 @@ struct dc_grid {
   double cell, inv_cell;
   int d[3];          // dims in permuted axes (d[0] fastest)
   int ax[3];         // permuted axis a reads xyz component ax[a]
+  int sub_bits;      // low key bits holding the sub-cell Morton code (0 or 6); cell = key >> sub_bits
   int64_t n_cells;
 };
 
@@ -28,18 +29,19 @@ __device__ __forceinline__ uint64_t dc_cell_key(const dc_grid& g, int c0, int c1
 }
 
 __device__ __forceinline__ void dc_key_coords(const dc_grid& g, uint64_t key, int& c0, int& c1, int& c2) {
+  key >>= g.sub_bits;
   c0 = (int)(key % (uint64_t)g.d[0]);
   const uint64_t t = key / (uint64_t)g.d[0];
   c1 = (int)(t % (uint64_t)g.d[1]);
   c2 = (int)(t / (uint64_t)g.d[1]);
 }
 
-// first position in sorted keys[0..n) with keys[pos] >= key
-__device__ __forceinline__ int64_t dc_lower_bound(const uint64_t* __restrict__ keys, int64_t n, uint64_t key) {
+// first position in sorted keys[0..n) whose cell (keys[pos] >> sub_bits) is >= cell
+__device__ __forceinline__ int64_t dc_lower_bound(const uint64_t* __restrict__ keys, int64_t n, uint64_t cell, int sub_bits) {
   int64_t lo = 0, hi = n;
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
-    if (__ldg(keys + mid) < key) lo = mid + 1; else hi = mid;
+    if ((__ldg(keys + mid) >> sub_bits) < cell) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
@@ -59,8 +61,8 @@ __device__ __forceinline__ void dc_row_range(const dc_grid& g, const uint64_t* _
     lo = __ldg(cell_start + k0);
     hi = __ldg(cell_start + k1);
   } else {
-    lo = (int)dc_lower_bound(keys, n, k0);
-    hi = (int)dc_lower_bound(keys, n, k1);
+    lo = (int)dc_lower_bound(keys, n, k0, g.sub_bits);
+    hi = (int)dc_lower_bound(keys, n, k1, g.sub_bits);
   }
 }
 

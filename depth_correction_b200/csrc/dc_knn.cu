@@ -819,7 +819,8 @@ knn_thread_list_kernel(const dc_point* __restrict__ P, const uint64_t* __restric
 
 struct kt_is_cell_start {
   const uint64_t* keys;
-  __host__ __device__ bool operator()(int i) const { return i == 0 || keys[i] != keys[i - 1]; }
+  int sub_bits;
+  __host__ __device__ bool operator()(int i) const { return i == 0 || (keys[i] >> sub_bits) != (keys[i - 1] >> sub_bits); }
 };
 
 __global__ void knn_cells_init_kernel(int32_t* header, int32_t* ell_idx, int64_t nq, int k) {
@@ -844,7 +845,7 @@ extern "C" int dc_knn_cells(const void* P, const uint64_t* pkeys, int64_t n, con
   const size_t off_tasks = 64, off_fb = off_tasks + (((size_t)nq1 * 4 + 15) / 16) * 16, off_cub = off_fb + (size_t)nq1 * 8;
   size_t cub_bytes = 0;
   cub::CountingInputIterator<int> iota(0);
-  kt_is_cell_start pred{qkeys};
+  kt_is_cell_start pred{qkeys, spec ? spec->sub_bits : 0};
   DC_CUDA_CHECK(cub::DeviceSelect::If(nullptr, cub_bytes, iota, (int32_t*)nullptr, (int32_t*)nullptr, (int)nq, pred, st));
   const size_t need = off_cub + cub_bytes;
   if (!temp) { *temp_bytes = need; return DC_OK; }

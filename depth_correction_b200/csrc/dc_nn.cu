@@ -104,13 +104,7 @@ extern "C" int dc_radius_fill(const void* P, const uint64_t* pkeys, int64_t n, c
   return radius_launch(true, P, pkeys, n, Q, qkeys, nq, spec, cell_start, r, nullptr, nullptr, slice_ptr, ell_idx, stream);
 }
 
-// ---------------------------------------------------------------------------------------------
-// kNN / kNN within r.  Shells of cells at Chebyshev distance rho = 0, 1, 2 ... are scanned until
-// the k-th best distance is provably final: every unscanned point is farther than rho * cell.
-// The k best (d2, original index) pairs live in a per-thread sorted list in local memory
-// (L1-resident); candidates that lose against the current k-th are rejected with one compare.
-// ---------------------------------------------------------------------------------------------
-// (implemented in dc_knn.cu)
+// (kNN / kNN within r: dc_knn.cu)
 
 // ---------------------------------------------------------------------------------------------
 // Export / import between sliced-ELL (sorted space, int32) and the reference layout
@@ -295,8 +289,8 @@ __global__ void transpose_kernel(const uint64_t* __restrict__ pairs, int64_t n_e
   const bool live = col < n_cols;
   int64_t lo = 0, hi = 0;
   if (live) {
-    lo = dc_lower_bound(pairs, n_edges, (uint64_t)col << 32);
-    hi = dc_lower_bound(pairs, n_edges, (uint64_t)(col + 1) << 32);
+    lo = dc_lower_bound(pairs, n_edges, (uint64_t)col << 32, 0);
+    hi = dc_lower_bound(pairs, n_edges, (uint64_t)(col + 1) << 32, 0);
   }
   const int deg = (int)(hi - lo);
   if (!ell_idx_t) {

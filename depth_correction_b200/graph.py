@@ -71,8 +71,11 @@ class SortedMap(object):
             axes = sorted(range(3), key=lambda a: (-ext[a], a))
         for i, a in enumerate(axes):
             spec.axis[i] = a
+        # points of one cell in Morton order of their 4x4x4 sub-cell (6 extra key bits): consecutive queries of a warp
+        # are neighbours in space.  DC_SUB_ORDER=0 keeps the order of the caller inside a cell.
+        spec.sub_bits = 6 if os.environ.get('DC_SUB_ORDER', '1') == '1' else 0
         n_cells = int(spec.dims[0]) * int(spec.dims[1]) * int(spec.dims[2])
-        if n_cells >= (1 << 62):
+        if n_cells >= (1 << 56):
             raise OverflowError('search grid has too many cells; increase the cell size')
         return spec, axes, n_cells
 
@@ -89,8 +92,9 @@ class SortedMap(object):
         ids = L.scratch('ids', n, torch.int32, dev)
         skeys = L.scratch('skeys', n, torch.int64, dev)
         L.call('dc_cell_keys', L.ptr(points), L.dtype_code(points.dtype), n, ctypes.byref(spec), L.ptr(keys), L.ptr(ids), st)
-        L.call_with_temp('dc_sort_keys', dev, L.ptr(keys), L.ptr(skeys), n, 0, max(1, int(n_cells - 1).bit_length()), after=(st,))
-        n_occ = int((skeys[1:] != skeys[:-1]).sum().item()) + 1
+        sb = int(spec.sub_bits)
+        L.call_with_temp('dc_sort_keys', dev, L.ptr(keys), L.ptr(skeys), n, sb, sb + max(1, int(n_cells - 1).bit_length()), after=(st,))
+        n_occ = int(((skeys[1:] >> sb) != (skeys[:-1] >> sb)).sum().item()) + 1
         return n / n_occ
 
     def __init__(self, points, cell, also_cover=None, bounds=None):
@@ -105,7 +109,7 @@ class SortedMap(object):
         lo, hi = bounds if bounds is not None else SortedMap.bounds_of(points, also_cover)
         self.cell = float(cell)
         self.spec, self.axes, self.n_cells = SortedMap.make_spec(lo, hi, self.cell)
-        self.key_bits = max(1, int(self.n_cells - 1).bit_length())
+        self.key_bits = max(1, int(self.n_cells - 1).bit_length()) + int(self.spec.sub_bits)
 
         keys = L.scratch('keys', n, torch.int64, dev)     # uint64 bit patterns (< 2^62)
         ids = L.scratch('ids', n, torch.int32, dev)
@@ -122,7 +126,7 @@ class SortedMap(object):
         self.cell_start = None
         if 0 < self.n_cells <= DENSE_TABLE_MAX_CELLS and n > 0:
             self.cell_start = torch.empty(self.n_cells + 1, dtype=torch.int32, device=dev)
-            L.call('dc_cell_table', L.ptr(self.keys), n, self.n_cells, L.ptr(self.cell_start), st)
+            L.call('dc_cell_table', L.ptr(self.keys), n, self.n_cells, int(self.spec.sub_bits), L.ptr(self.cell_start), st)
 
     def sort_queries(self, query):
         """Sort a query set by the same grid -> (Q records, qkeys, q_order)."""
@@ -147,7 +151,8 @@ class SortedMap(object):
         """Mean number of points per occupied cell."""
         if self.n == 0:
             return 0.0
-        n_occ = int((self.keys[1:] != self.keys[:-1]).sum().item()) + 1
+        sb = int(self.spec.sub_bits)
+        n_occ = int(((self.keys[1:] >> sb) != (self.keys[:-1] >> sb)).sum().item()) + 1
         return self.n / n_occ
 
 

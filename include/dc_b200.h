@@ -56,6 +56,9 @@ typedef struct dc_grid_spec {
   double cell;      /* cell edge length */
   int32_t dims[3];  /* cells along x, y, z */
   int32_t axis[3];  /* axis[0] = fastest varying axis of the cell key ... axis[2] = slowest */
+  int32_t sub_bits; /* 0 or 6: low key bits = Morton code of the point's 4x4x4 sub-cell, so that points of one cell are
+                       stored in a spatially coherent order (consecutive queries of a warp are neighbours in space);
+                       the cell of a key is key >> sub_bits */
 } dc_grid_spec;
 
 const char* dc_last_error(void);
@@ -70,7 +73,8 @@ int dc_version(void);
 /* min/max over rows of pts[n,3]: out6 = {minx,miny,minz,maxx,maxy,maxz}; bad_count = #non-finite rows */
 int dc_bounds(const void* pts, int dtype, int64_t n, double* out6, int32_t* bad_count, void* stream);
 
-/* cell key of every row (linear index with spec->axis ordering) and ids = 0..n-1 */
+/* cell key of every row (linear index with spec->axis ordering, shifted left by spec->sub_bits with the sub-cell Morton
+ * code below it) and ids = 0..n-1 */
 int dc_cell_keys(const void* pts, int dtype, int64_t n, const dc_grid_spec* spec_host, uint64_t* keys, int32_t* ids,
                  void* stream);
 
@@ -82,8 +86,9 @@ int dc_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const int32_t* id
 int dc_gather_points(const void* pts, int dtype, const int32_t* order, int64_t n, void* sorted_points,
                      int32_t* inv_order, void* stream);
 
-/* dense table cell_start[c] = first sorted position with key >= c, c in [0, n_cells] (optional accelerator) */
-int dc_cell_table(const uint64_t* keys_sorted, int64_t n, int64_t n_cells, int32_t* cell_start, void* stream);
+/* dense table cell_start[c] = first sorted position whose cell (key >> sub_bits) is >= c, c in [0, n_cells]
+ * (optional accelerator) */
+int dc_cell_table(const uint64_t* keys_sorted, int64_t n, int64_t n_cells, int sub_bits, int32_t* cell_start, void* stream);
 
 /* radius mode, pass 1: counts[q] = #{p : |p - q|^2 <= r^2} (fp64, same summation order as cKDTree),
  * slice_width[t] = max count in slice t.  Queries must be sorted by the same grid (self query: Q == P). */

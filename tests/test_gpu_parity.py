@@ -168,7 +168,7 @@ def test_cell_table_is_lower_bound_of_sorted_keys(dc, dev):
                           [[-7.0, -7.0, -7.0]]]).astype(np.float32)
     for p, cell in ((pts, 0.11), (pts[:1], 0.5), (pts, 3.0)):
         smap = SortedMap(torch.as_tensor(p, device=dev), cell)
-        ref = torch.searchsorted(smap.keys, torch.arange(smap.n_cells + 1, device=dev, dtype=torch.int64))
+        ref = torch.searchsorted(smap.keys >> int(smap.spec.sub_bits), torch.arange(smap.n_cells + 1, device=dev, dtype=torch.int64))
         assert torch.equal(smap.cell_start.long(), ref)
 
 
