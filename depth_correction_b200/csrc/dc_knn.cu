@@ -24,8 +24,8 @@
 #define KNN_BINS 64
 
 // (d2, original index) lexicographic order.  The original index (dc_point.tag) -- not the position in the cell-sorted
-// map -- breaks exact ties, so the selected set does not depend on the cell size.  The scans hand the tag of every
-// candidate to their callbacks (it is part of the record they load anyway); 0x7fffffff stands for "no candidate".
+// map -- breaks exact ties, so the selected set does not depend on the cell size.  Tags are read for the candidates
+// of the boundary bin only; 0x7fffffff stands for "no candidate".
 __device__ __forceinline__ bool knn_less(double a, int ta, double b, int tb) { return a < b || (a == b && ta < tb); }
 
 __device__ __forceinline__ int knn_bin(double d2, double scale) {
@@ -51,11 +51,10 @@ __device__ __forceinline__ void knn_scan(const dc_grid& g, const uint64_t* __res
         const dc_point p0 = dc_ld_point(P + j), p1 = dc_ld_point(P + j1);
         const dc_point p2 = dc_ld_point(P + j2), p3 = dc_ld_point(P + j3);
         const double d0 = dc_dist2(p0, pq), d1 = dc_dist2(p1, pq), d2 = dc_dist2(p2, pq), d3 = dc_dist2(p3, pq);
-        // third argument: the ORIGINAL index of the candidate (tag of its record, already loaded), the tie-break key
-        f(j, d0, (int)p0.tag);
-        if (j + 1 < hi) f(j + 1, d1, (int)p1.tag);
-        if (j + 2 < hi) f(j + 2, d2, (int)p2.tag);
-        if (j + 3 < hi) f(j + 3, d3, (int)p3.tag);
+        f(j, d0);
+        if (j + 1 < hi) f(j + 1, d1);
+        if (j + 2 < hi) f(j + 2, d2);
+        if (j + 3 < hi) f(j + 3, d3);
       }
     }
   }
@@ -85,7 +84,7 @@ __device__ __forceinline__ bool knn_thread_query(const dc_point* __restrict__ P,
 #pragma unroll
     for (int b = 0; b < KNN_BINS; ++b) h[b * KNN_THREADS] = (unsigned short)0;
     n_in = 0u;
-    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2, int tag) {
+    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
       if (d2 < bound2) {
         const int b = knn_bin(d2, scale1);
         const unsigned short v = h[b * KNN_THREADS];
@@ -98,7 +97,7 @@ __device__ __forceinline__ bool knn_thread_query(const dc_point* __restrict__ P,
   }
   if (n_in <= (unsigned int)k) {
     // everything inside the bound is a neighbour (fewer than k exist within r / in the map)
-    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2, int tag) {
+    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
       if (d2 < bound2) emit(j, d2);
     });
     return true;
@@ -118,7 +117,7 @@ __device__ __forceinline__ bool knn_thread_query(const dc_point* __restrict__ P,
     // ---- 2. level-2 histogram inside bin b1
 #pragma unroll
     for (int b = 0; b < KNN_BINS; ++b) h[b * KNN_THREADS] = (unsigned short)0;
-    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2, int tag) {
+    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
       if (d2 < bound2) {
         const double s = d2 * scale1;
         int b = __double2int_rz(s);
@@ -145,7 +144,7 @@ __device__ __forceinline__ bool knn_thread_query(const dc_point* __restrict__ P,
   // column, which is no longer needed) and ranked afterwards with the warp converged: ranking inside the scan ran one lane at a time and
   // cost 17 % of all instructions of the kernel.
   int nb = 0;
-  knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2, int tag) {
+  knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
     if (d2 < bound2) {
       const double s = d2 * scale1;
       int b = __double2int_rz(s);
@@ -167,6 +166,9 @@ __device__ __forceinline__ bool knn_thread_query(const dc_point* __restrict__ P,
             // the histogram is dead by now: entry nb lives in this thread's counters 8 nb .. 8 nb + 7 (four 16-bit
             // pieces of d2, two of j, two of the original index = tie-break key): 8 entries fill the 64 counters
             // exactly, which keeps the block at 16 KB of shared memory
+            // (the tag is re-read here, for the <= 8 boundary candidates of a query, instead of being carried through
+            // the scan for every candidate: that cost the scan loop four live registers and 4 % of the kernel)
+            const int tag = (int)P[j].tag;
             const unsigned long long u = (unsigned long long)__double_as_longlong(d2);
             unsigned short* e = h + 8 * nb * KNN_THREADS;
             e[0] = (unsigned short)u;
@@ -213,7 +215,7 @@ __device__ __forceinline__ bool knn_thread_query(const dc_point* __restrict__ P,
   for (unsigned int s_ = 0; s_ < t; ++s_) {
     double best_d = INFINITY;
     int best_j = 0x7fffffff, best_t = 0x7fffffff;
-    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2, int tag) {
+    knn_scan(g, pkeys, n, cell_start, P, pq, c0, c1, c2, rho, [&](int j, double d2) {
       if (d2 < bound2) {
         const double s = d2 * scale1;
         int b = __double2int_rz(s);
@@ -224,10 +226,13 @@ __device__ __forceinline__ bool knn_thread_query(const dc_point* __restrict__ P,
             bb = __double2int_rz((s - (double)b1) * (double)KNN_BINS);
             bb = bb < 0 ? 0 : (bb > KNN_BINS - 1 ? KNN_BINS - 1 : bb);
           }
-          if (bb == b2 && knn_less(last_d, last_t, d2, tag) && knn_less(d2, tag, best_d, best_t)) {
-            best_d = d2;
-            best_j = j;
-            best_t = tag;
+          if (bb == b2) {
+            const int tag = (int)P[j].tag;
+            if (knn_less(last_d, last_t, d2, tag) && knn_less(d2, tag, best_d, best_t)) {
+              best_d = d2;
+              best_j = j;
+              best_t = tag;
+            }
           }
         }
       }

@@ -325,9 +325,9 @@ def _knn_cell_size(points, k, r, bounds, use_hint=True):
     # a disc of radius c on a surface with `occ` points per c^2 holds pi * occ points; the mean occupancy is dominated
     # by sparse cells (a typical QUERY sits in a cell 2x as full)
     target = max(float(occ_env) * k, 2.0)
-    for _ in range(4):
+    for _ in range(5):
         occ = SortedMap.occupancy_of(points, lo, hi, c0)
-        if 0.8 * target <= occ <= 1.25 * target:
+        if 0.9 * target <= occ <= 1.11 * target:
             break
         c0 = c0 * min(max(math.sqrt(target / occ), 1.0 / 8.0), 8.0)
         if r and c0 > r:

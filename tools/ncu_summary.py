@@ -83,6 +83,7 @@ def main():
         # per-launch DRAM traffic by C-ABI entry point -> profiles/traffic.json (bench.py fills roofline.traffic from it)
         import json
         entry = {'knn_thread_kernel': 'dc_knn', 'step_points_kernel': 'dc_step_points', 'step_forward_kernel': 'dc_step_forward',
+                 'step_forward_scatter': 'dc_step_forward_scatter',
                  'step_backward_gather_kernel': 'dc_step_backward', 'step_backward_scatter_kernel': 'dc_step_backward_scatter',
                  'step_chain_kernel': 'dc_step_chain'}
         rd, wr, du = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('gpu__time_duration.sum')
@@ -91,6 +92,9 @@ def main():
         out = {'source': '%s (ncu --set full, timed NVTX region of bench.py)' % rep.split('/')[-1], 'n_points': int(sys.argv[5]), 'kernels': {}}
         for r in data:
             base = r[name_i].split('(')[0].replace('void ', '').split('<')[0].strip()
+            targs = r[name_i].split('(')[0].split('<')[1] if '<' in r[name_i].split('(')[0] else ''
+            if base == 'step_forward_kernel' and ('true' in targs or targs.replace(' ', '').endswith(',1>')):
+                base = 'step_forward_scatter'        # SCAT = true: forward + float32 backward scatter in one kernel
             if base in entry and entry[base] not in out['kernels']:
                 out['kernels'][entry[base]] = {'kernel': r[name_i].split('(')[0], 'dram_read_bytes': float(r[rd]) * scale[units[rd]],
                                                'dram_write_bytes': float(r[wr]) * scale[units[wr]],
