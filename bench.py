@@ -74,6 +74,7 @@ def parse_args():
     ap.add_argument('--cpu-scans', type=int, default=6, help='scans in the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-strong-anchor', action='store_true', help='N = 1: skip the 60 M point street map')
+    ap.add_argument('--no-other-configs', action='store_true', help='N = 1: skip the small-map configs[0] / configs[3] lines')
     ap.add_argument('--profile', action='store_true', help='small fixed workload for ncu (no baseline, no e2e)')
     return ap.parse_args()
 
@@ -471,6 +472,90 @@ def parity_vs_cpu(dc, dev, cpu):
     return out
 
 
+def other_configs(dc, dev):
+    """BASELINE.json configs[0] and configs[3] (small maps, radius graphs, the regime of the reference's own runs):
+    search once + fixed-graph training iterations, timed on the device; configs[0] also runs on the CPU oracle on the
+    very same records (it is the reference's CPU-runnable case), so its speed-up and parity are like for like."""
+    from oracle import oracle
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def prepare(scene, n_scans, cfg, **seq_kw):
+        scans_np, poses_gt, poses_init = make_sequence(scene, n_scans=n_scans, pattern='os0-128', seed=5, **seq_kw)
+        clouds = []
+        for sc in scans_np:
+            c = dc.filtered_cloud(dc.DepthCloud.from_points(torch.as_tensor(sc['points'], device=dev)), cfg)
+            clouds.append(dc.local_feature_cloud(c, cfg))
+        return clouds, torch.as_tensor(poses_init, device=dev)
+
+    def timed_loop(clouds, poses, cfg, loss_fn, iters=20):
+        model = dc.ScaledPolynomial(w=[0.0, 0.0], exponent=[2, 4], device=dev)
+        deltas = torch.zeros((len(clouds), 6), dtype=torch.float64, device=dev, requires_grad=True)
+        opt = torch.optim.Adam([{'params': deltas, 'lr': 1e-3}, {'params': model.parameters(), 'lr': 1e-3}])
+        s0, s1 = ev(), ev()
+        dc.establish_neighborhoods(clouds=clouds, poses=poses, cfg=cfg)           # warm
+        torch.cuda.synchronize()
+        s0.record()
+        ns = dc.establish_neighborhoods(clouds=clouds, poses=poses, cfg=cfg)
+        s1.record()
+
+        def it():
+            pc = torch.stack(dc.create_corrected_poses(poses, deltas, cfg))
+            feats = dc.compute_neighborhood_features(cloud=dc.global_cloud(clouds=clouds, model=model, poses=pc), neighborhoods=ns, cfg=cfg)
+            loss, _ = loss_fn(feats)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(3):
+            it()
+        torch.cuda.synchronize()
+        t0, t1 = ev(), ev()
+        t0.record()
+        for _ in range(iters):
+            loss = it()
+        t1.record()
+        torch.cuda.synchronize()
+        n = sum(len(c) for c in clouds)
+        return {'n_points': n, 'n_scans': len(clouds), 'search_ms': s0.elapsed_time(s1), 'train_iteration_ms': t0.elapsed_time(t1) / iters,
+                'iterations_points_per_s': n / (t0.elapsed_time(t1) / iters * 1e-3), 'max_neighbors': int(ns.graph.width),
+                'loss_after_%d_iterations' % (iters + 3): float(loss.item())}, ns
+
+    # configs[0]: planar corridor, 10 OS0-128 scans, the reference's filters (depth 1-25 m, 0.2 m voxels), radius graph r = 0.4
+    cfg0 = dc.Config(min_depth=1.0, max_depth=25.0, grid_res=0.2, nn_k=0, nn_r=NN_R, pose_correction=dc.PoseCorrection.pose)
+    clouds, poses = prepare('corridor', 10, cfg0, depth_clip=(1.0, 25.0))
+    r0, ns = timed_loop(clouds, poses, cfg0, lambda f: dc.min_eigval_loss(f, normalization=True))
+    scans = [{'vps': c.vps.double().cpu().expand(len(c), 3), 'dirs': c.dirs.double().cpu(), 'depth': c.depth.double().cpu(),
+              'inc_angles': c.inc_angles.double().cpu(), 'mask': c.mask.cpu()} for c in clouds]
+    torch.set_num_threads(os.cpu_count())
+    w0 = time.perf_counter()
+    pts0, _ = oracle.global_points(scans, poses.cpu())
+    _, nb = oracle.nearest_neighbors(pts0, r=NN_R)
+    w1 = time.perf_counter()
+    ref = oracle.map_consistency_step(scans, poses.cpu(), nb, torch.zeros((1, 2), dtype=torch.float64), torch.tensor([[2.0, 4.0]], dtype=torch.float64),
+                                      pose_deltas=torch.zeros((len(scans), 6), dtype=torch.float64), loss='min_eigval_loss', normalization=True)
+    w2 = time.perf_counter()
+    model = dc.ScaledPolynomial(w=[0.0, 0.0], exponent=[2, 4], device=dev)
+    deltas = torch.zeros((len(clouds), 6), dtype=torch.float64, device=dev, requires_grad=True)
+    pc = torch.stack(dc.create_corrected_poses(poses, deltas, cfg0))
+    loss, _ = dc.min_eigval_loss(dc.compute_neighborhood_features(cloud=dc.global_cloud(clouds=clouds, model=model, poses=pc), neighborhoods=ns, cfg=cfg0),
+                                 normalization=True)
+    loss.backward()
+    r0.update({'workload': 'configs[0]: corridor, 10 OS0-128 scans, depth 1-25 m, 0.2 m voxel filter, radius graph r=0.4, min_eigval_loss(normalization)',
+               'cpu_search_ms': (w1 - w0) * 1e3, 'cpu_step_ms': (w2 - w1) * 1e3, 'cpu_cores': os.cpu_count(),
+               'neighbor_indices_identical': bool(torch.equal(ns[0].cpu(), nb)),
+               'loss_rel_err_vs_cpu': abs(loss.item() - float(ref['loss'])) / abs(float(ref['loss'])),
+               'pose_grad_rel_err_vs_cpu': float((deltas.grad.cpu() - ref['pose_deltas_grad']).abs().max() / ref['pose_deltas_grad'].abs().max())})
+    out['cfg0'] = r0
+    # configs[3]: FEE-corridor-shaped scene (side room, stairs), noisy initial poses, joint model + pose learning, trace_loss
+    cfg3 = dc.Config(min_depth=1.0, max_depth=25.0, grid_res=0.1, nn_k=0, nn_r=0.25, loss='trace_loss', pose_correction=dc.PoseCorrection.pose)
+    clouds, poses = prepare('fee', 12, cfg3, pose_noise=(0.01, 0.005), bias_w=[-0.01], bias_exponent=[4.0])
+    r3, _ = timed_loop(clouds, poses, cfg3, lambda f: dc.trace_loss(f, sqrt=False))
+    r3['workload'] = 'configs[3]: fee scene, 12 OS0-128 scans, 0.1 m voxel filter, radius graph r=0.25, trace_loss, ScaledPolynomial + per-scan SE(3) corrections, Adam'
+    out['cfg3'] = r3
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     rank = int(os.environ.get('RANK', 0))
@@ -628,6 +713,8 @@ def run_ours(args):
         L.release_workspace()
         torch.cuda.empty_cache()
 
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        line['other_configs'] = other_configs(dc, dev)
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             cpu = cpu_baseline(args.cpu_scans, 'os0-128', steps=1, keep=True)

@@ -10,7 +10,8 @@ scenes
   corridor : 3 m x 3 m box cross-section, unbounded along x, sensor 1 m above the floor,
              poses every `step` metres along x with a small yaw (BASELINE.json configs 0/1)
   street   : ground plane + two facades 12 m apart (KITTI-360-shaped, config 2)
-  fee      : corridor with noisy initial poses (first pose exact), for pose learning (config 3)
+  fee      : the corridor with a side room behind a doorway and a flight of stairs up to a landing (FEE-corridor
+             shaped, config 3); used with noisy initial poses (first pose exact) for pose learning
 patterns
   os0-128  : 128 rings x 1024 azimuths, elevation +-45 deg
   hdl-64   : 64 rings (+2 ... -24.8 deg) x 1900 azimuths
@@ -38,12 +39,35 @@ def beam_pattern(name, rings=None, azimuths=None):
     return el.ravel(), az.ravel()
 
 
+INF = float('inf')
+
+
 def scene_planes(scene):
-    """Planes as (normal[3], offset) with n.x = offset; rays hit the nearest plane in front."""
-    if scene in ('corridor', 'fee'):
-        return [((0, 0, 1), 0.0), ((0, 0, 1), 3.0), ((0, 1, 0), -1.5), ((0, 1, 0), 1.5)]
+    """Surfaces as (normal[3], offset, lo[3], hi[3]): the part of the plane n.x = offset inside the axis-aligned box
+    [lo, hi] (infinite bounds = the whole plane); rays hit the nearest surface in front."""
+    whole = ((-INF, -INF, -INF), (INF, INF, INF))
+    if scene == 'corridor':
+        return [((0, 0, 1), 0.0) + whole, ((0, 0, 1), 3.0) + whole, ((0, 1, 0), -1.5) + whole, ((0, 1, 0), 1.5) + whole]
     if scene == 'street':
-        return [((0, 0, 1), 0.0), ((0, 1, 0), -6.0), ((0, 1, 0), 6.0)]
+        return [((0, 0, 1), 0.0) + whole, ((0, 1, 0), -6.0) + whole, ((0, 1, 0), 6.0) + whole]
+    if scene == 'fee':
+        # corridor 3 m x 3 m along x; side room x in [6, 12], y in [1.5, 5.5] behind a doorway x in [8, 10];
+        # stairs from x = 20: eight steps of 0.5 m x 0.15 m up to a landing at z = 1.2 m (x >= 24)
+        srf = [((0, 0, 1), 3.0) + whole,                                              # ceiling
+               ((0, 1, 0), -1.5) + whole,                                             # right wall
+               ((0, 0, 1), 0.0, (-INF, -INF, -INF), (20.0, INF, INF)),                # floor up to the stairs
+               ((0, 1, 0), 1.5, (-INF, -INF, -INF), (8.0, INF, INF)),                 # left wall before the door
+               ((0, 1, 0), 1.5, (10.0, -INF, -INF), (INF, INF, INF)),                 # left wall after the door
+               ((0, 1, 0), 5.5, (6.0, -INF, -INF), (12.0, INF, INF)),                 # side room: back wall
+               ((1, 0, 0), 6.0, (-INF, 1.5, -INF), (INF, 5.5, INF)),                  # side room: side walls
+               ((1, 0, 0), 12.0, (-INF, 1.5, -INF), (INF, 5.5, INF)),
+               ((0, 0, 1), 1.2, (24.0, -INF, -INF), (INF, INF, INF))]                 # landing
+        for i in range(8):
+            x0 = 20.0 + 0.5 * i
+            srf.append(((1, 0, 0), x0, (-INF, -INF, 0.15 * i), (INF, INF, 0.15 * (i + 1))))          # riser
+            if i < 7:
+                srf.append(((0, 0, 1), 0.15 * (i + 1), (x0, -INF, -INF), (x0 + 0.5, INF, INF)))      # tread
+        return srf
     raise ValueError(scene)
 
 
@@ -105,12 +129,16 @@ def make_sequence(scene='corridor', n_scans=10, pattern='os0-128', seed=0, step=
         o = T[:3, 3]
         depth = np.full(len(d_world), np.inf)
         cosi = np.zeros(len(d_world))
-        for n, off in planes:
+        for n, off, lo, hi in planes:
             n = np.asarray(n, dtype=np.float64)
             denom = d_world @ n
             with np.errstate(divide='ignore', invalid='ignore'):
                 t = (off - o @ n) / denom
             hit = (t > 0) & (t < depth)
+            if np.isfinite(lo).any() or np.isfinite(hi).any():
+                with np.errstate(invalid='ignore'):
+                    pt = o + t[:, None] * d_world
+                    hit &= np.all((pt >= np.asarray(lo) - 1e-9) & (pt <= np.asarray(hi) + 1e-9), axis=1)
             depth = np.where(hit, t, depth)
             cosi = np.where(hit, np.abs(denom), cosi)
         keep = np.isfinite(depth) & (depth >= depth_clip[0]) & (depth <= depth_clip[1])
