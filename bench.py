@@ -159,12 +159,10 @@ def host_scans(n_scans, pattern='os0-128', first_scan=0, scene='corridor', scan_
 
 def local_features(dc, pts_dev, cfg):
     """Per-scan constants of the optimisation: incidence angles and planarity mask (preproc.py:35-64)."""
-    clouds = []
-    for p in pts_dev:
-        c = dc.local_feature_cloud(dc.DepthCloud.from_points(p), cfg)
-        # keep only what the loop reads; drop the per-scan graph and feature tensors
-        clouds.append(dc.DepthCloud(vps=c.vps, dirs=c.dirs, depth=c.depth, inc_angles=c.inc_angles, mask=c.mask))
-    return clouds
+    # all scans through one stacked search + one neighbourhood pass (the reference loops over the scans, train.py:97-104)
+    feats = dc.local_feature_clouds([dc.DepthCloud.from_points(p) for p in pts_dev], cfg)
+    # keep only what the loop reads; contiguous per-scan copies (the batched arrays are released)
+    return [dc.DepthCloud(vps=c.vps, dirs=c.dirs, depth=c.depth, inc_angles=c.inc_angles.clone(), mask=c.mask.clone()) for c in feats]
 
 
 def one_step(dc, clouds, poses, deltas, model, cfg, ns=None, timers=None, local=None):

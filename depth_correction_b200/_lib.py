@@ -49,6 +49,7 @@ _SPEC = ctypes.POINTER(GridSpec)
 SIGNATURES = {
     'dc_bounds': [_P, _I, _L, _P, _P, _P],
     'dc_cell_keys': [_P, _I, _L, _SPEC, _P, _P, _P],
+    'dc_cell_keys_stacked': [_P, _I, _L, _SPEC, _P, _I, _I, _I, _P, _P, _P],
     'dc_sort_pairs': [_P, _P, _P, _P, _L, _I, _P, _SZP, _P],
     'dc_gather_points': [_P, _I, _P, _L, _P, _P, _P],
     'dc_cell_table': [_P, _L, _L, _I, _P, _P],
@@ -82,6 +83,7 @@ SIGNATURES = {
     'dc_pose_compose': [_P, _P, _I, _I, _P, _P],
     'dc_pose_compose_backward': [_P, _P, _I, _I, _P, _P, _P],
     'dc_features': [_P, _I, _L, _P, _P, _I, _P, _P, _P],
+    'dc_local_features_finish': [_P, _P, _P, _P, _I, _L, _I, _P, _P, _P, _P, _P],
     'dc_feature_mask': [_P, _I, _L, _I, _P, _I, _P, _L, _I, _P, _P],
     'dc_features_backward': [_P, _I, _L, _P, _P, _I, _P, _P, _P, _P],
     'dc_eigh3': [_P, _I, _L, _P, _P, _P],

@@ -365,3 +365,48 @@ extern "C" int dc_feature_mask(const void* vals, int dtype, int64_t n, int strid
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Per-point features of MANY clouds at once (local_feature_cloud of every scan, preproc.py:35-64): the neighbourhood
+// pass is dc_step_forward on the stacked graph (sorted space, fp64); this kernel turns its outputs into the
+// reference's per-point fields in the caller's order and dtype: eigvals, mean, oriented normals
+// (depth_cloud.py:401-415) and incidence angles (:417-424).  stash: [n,8] = {mean xyz, v0 xyz, ., .} per sorted row.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void local_finish_kernel(const double* __restrict__ stash, const double* __restrict__ eig_sorted,
+                                    const int32_t* __restrict__ order, const T* __restrict__ dirs, int64_t n, int use_normal_sign,
+                                    T* __restrict__ eigvals, T* __restrict__ mean, T* __restrict__ normals, T* __restrict__ inc) {
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int64_t o = order[s];
+  const double* st = stash + 8 * s;
+  if (eigvals) { eigvals[3 * o] = (T)eig_sorted[3 * s]; eigvals[3 * o + 1] = (T)eig_sorted[3 * s + 1]; eigvals[3 * o + 2] = (T)eig_sorted[3 * s + 2]; }
+  if (mean) { mean[3 * o] = (T)st[0]; mean[3 * o + 1] = (T)st[1]; mean[3 * o + 2] = (T)st[2]; }
+  // the normal goes through the cloud's dtype like the staged path (eigvecs are stored in T there)
+  const double d[3] = {(double)dirs[3 * o], (double)dirs[3 * o + 1], (double)dirs[3 * o + 2]};
+  double v[3] = {(double)(T)st[3], (double)(T)st[4], (double)(T)st[5]};
+  const double c = d[0] * v[0] + d[1] * v[1] + d[2] * v[2];
+  const double sgn = c > 0.0 ? 1.0 : (c < 0.0 ? -1.0 : (c == 0.0 ? 0.0 : c));
+  v[0] = -sgn * v[0]; v[1] = -sgn * v[1]; v[2] = -sgn * v[2];
+  if (normals) { normals[3 * o] = (T)v[0]; normals[3 * o + 1] = (T)v[1]; normals[3 * o + 2] = (T)v[2]; }
+  if (inc) {
+    double cn = d[0] * v[0] + d[1] * v[1] + d[2] * v[2];
+    if (fabs(cn) > 1.0 && fabs(cn) < 1.0 + 1e-6) cn = cn > 0.0 ? 1.0 : -1.0;      // rounding overshoot (see dc_normals_angles)
+    inc[o] = (T)acos(use_normal_sign ? -cn : fabs(cn));
+  }
+}
+
+extern "C" int dc_local_features_finish(const double* stash, const double* eigvals_sorted, const int32_t* order, const void* dirs,
+                                        int dtype, int64_t n, int use_normal_sign, void* eigvals, void* mean, void* normals,
+                                        void* inc_angles, void* stream) {
+  if (n <= 0) return DC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DC_F32)
+    local_finish_kernel<float><<<dc_blocks(n, 256), 256, 0, st>>>(stash, eigvals_sorted, order, (const float*)dirs, n, use_normal_sign,
+                                                                 (float*)eigvals, (float*)mean, (float*)normals, (float*)inc_angles);
+  else
+    local_finish_kernel<double><<<dc_blocks(n, 256), 256, 0, st>>>(stash, eigvals_sorted, order, (const double*)dirs, n, use_normal_sign,
+                                                                  (double*)eigvals, (double*)mean, (double*)normals, (double*)inc_angles);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}

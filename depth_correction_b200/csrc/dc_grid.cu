@@ -123,6 +123,56 @@ extern "C" int dc_cell_keys(const void* pts, int dtype, int64_t n, const dc_grid
   return DC_OK;
 }
 
+// Stacked form for many small clouds searched at once (per-scan features of all scans in one launch,
+// preproc.py:35-64 / train.py:97-104): cloud s gets its own band of `period` cell layers along the slowest key axis,
+// [s * period, s * period + band) with band = period - guard, so that no ring of cells of one cloud ever reaches the
+// points of another.  Coordinates are untouched: distances are the true ones, bit for bit.
+template <typename T>
+__global__ void cell_keys_stacked_kernel(const T* __restrict__ pts, int64_t n, dc_grid g, const int64_t* __restrict__ first,
+                                         int n_clouds, int period, int band, uint64_t* keys, int32_t* ids) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = n_clouds;          // largest s with first[s] <= i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(first + mid) <= i) lo = mid; else hi = mid;
+  }
+  const double p[3] = {(double)pts[3 * i], (double)pts[3 * i + 1], (double)pts[3 * i + 2]};
+  int c0, c1, c2;
+  dc_cell_coords(g, p, c0, c1, c2);
+  const double f2raw = (p[g.ax[2]] - g.org[2]) * g.inv_cell;
+  c2 = dc_clampi((int)floor(f2raw), 0, band - 1);
+  uint64_t key = dc_cell_key(g, c0, c1, c2 + lo * period);
+  if (g.sub_bits) {
+    const double f0 = (p[g.ax[0]] - g.org[0]) * g.inv_cell - (double)c0, f1 = (p[g.ax[1]] - g.org[1]) * g.inv_cell - (double)c1,
+                 f2 = f2raw - (double)c2;
+    const unsigned s0 = (unsigned)dc_clampi((int)(f0 * 4.0), 0, 3), s1 = (unsigned)dc_clampi((int)(f1 * 4.0), 0, 3),
+                   s2 = (unsigned)dc_clampi((int)(f2 * 4.0), 0, 3);
+    const unsigned m = (s0 & 1u) | ((s1 & 1u) << 1) | ((s2 & 1u) << 2) | ((s0 & 2u) << 2) | ((s1 & 2u) << 3) | ((s2 & 2u) << 4);
+    key = (key << g.sub_bits) | (uint64_t)m;
+  }
+  keys[i] = key;
+  ids[i] = (int32_t)i;
+}
+
+extern "C" int dc_cell_keys_stacked(const void* pts, int dtype, int64_t n, const dc_grid_spec* spec, const int64_t* first,
+                                    int n_clouds, int period, int guard, uint64_t* keys, int32_t* ids, void* stream) {
+  if (n <= 0) return DC_OK;
+  if (n > 2147483647LL) return dc_set_error(DC_ERR_OVERFLOW, "dc_cell_keys_stacked: more than 2^31-1 points");
+  dc_grid g;
+  int rc = dc_make_grid(spec, &g);
+  if (rc) return rc;
+  if (n_clouds < 1 || guard < 1 || period <= guard || (int64_t)n_clouds * period != (int64_t)g.d[2])
+    return dc_set_error(DC_ERR_ARG, "dc_cell_keys_stacked: the slowest grid dimension must equal n_clouds * period, period > guard >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DC_F32)
+    cell_keys_stacked_kernel<float><<<dc_blocks(n, 256), 256, 0, st>>>((const float*)pts, n, g, first, n_clouds, period, period - guard, keys, ids);
+  else
+    cell_keys_stacked_kernel<double><<<dc_blocks(n, 256), 256, 0, st>>>((const double*)pts, n, g, first, n_clouds, period, period - guard, keys, ids);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
 int dc_make_grid(const dc_grid_spec* spec, dc_grid* g) {
   if (!spec || !(spec->cell > 0.0)) return dc_set_error(DC_ERR_ARG, "grid spec: cell size must be positive");
   int seen[3] = {0, 0, 0};

@@ -97,7 +97,9 @@ class SortedMap(object):
         n_occ = int(((skeys[1:] >> sb) != (skeys[:-1] >> sb)).sum().item()) + 1
         return n / n_occ
 
-    def __init__(self, points, cell, also_cover=None, bounds=None):
+    def __init__(self, points, cell, also_cover=None, bounds=None, stack=None):
+        """stack = (first int64 [S+1] on the device, S, guard): S clouds stored one after the other in `points`, searched
+        at once but never paired with each other (dc_cell_keys_stacked)."""
         points = _as_points(points)
         dev = points.device
         self.device = dev
@@ -109,6 +111,17 @@ class SortedMap(object):
         lo, hi = bounds if bounds is not None else SortedMap.bounds_of(points, also_cover)
         self.cell = float(cell)
         self.spec, self.axes, self.n_cells = SortedMap.make_spec(lo, hi, self.cell)
+        self.stack = None
+        if stack is not None:
+            first, n_clouds, guard = stack
+            slow = self.axes[2]
+            band = int(self.spec.dims[slow])
+            period = band + int(guard)
+            self.spec.dims[slow] = n_clouds * period
+            self.n_cells = int(self.spec.dims[0]) * int(self.spec.dims[1]) * int(self.spec.dims[2])
+            if self.n_cells >= (1 << 56):
+                raise OverflowError('stacked search grid has too many cells; increase the cell size')
+            self.stack = (first, int(n_clouds), period, int(guard))
         self.key_bits = max(1, int(self.n_cells - 1).bit_length()) + int(self.spec.sub_bits)
 
         keys = L.scratch('keys', n, torch.int64, dev)     # uint64 bit patterns (< 2^62)
@@ -117,7 +130,12 @@ class SortedMap(object):
         self.order = torch.empty(n, dtype=torch.int32, device=dev)
         self.P = torch.empty((n, 4), dtype=torch.float64, device=dev)
         if n > 0:
-            L.call('dc_cell_keys', L.ptr(points), code, n, ctypes.byref(self.spec), L.ptr(keys), L.ptr(ids), st)
+            if self.stack is None:
+                L.call('dc_cell_keys', L.ptr(points), code, n, ctypes.byref(self.spec), L.ptr(keys), L.ptr(ids), st)
+            else:
+                first, n_clouds, period, guard = self.stack
+                L.call('dc_cell_keys_stacked', L.ptr(points), code, n, ctypes.byref(self.spec), L.ptr(first), n_clouds, period,
+                       guard, L.ptr(keys), L.ptr(ids), st)
             L.call_with_temp('dc_sort_pairs', dev, L.ptr(keys), L.ptr(self.keys), L.ptr(ids), L.ptr(self.order), n,
                              self.key_bits, after=(st,))
         self.inv_order = torch.empty(n, dtype=torch.int32, device=dev)
@@ -342,21 +360,35 @@ def clear_cell_hints():
     _cell_hint.clear()
 
 
-def search(points, query=None, k=None, r=None, cell=None):
+def search(points, query=None, k=None, r=None, cell=None, stack_first=None):
     """Neighbour search -> Graph.  Modes follow nearest_neighbors.py:47-53:
-    k (and optionally r as a strict upper bound) -> kNN graph; r only -> radius graph (<= r)."""
+    k (and optionally r as a strict upper bound) -> kNN graph; r only -> radius graph (<= r).
+
+    stack_first (int64 [S+1] on the device): `points` holds S clouds one after the other (cloud s = rows
+    stack_first[s] .. stack_first[s+1]); each is searched on its own (self query, needs r), all in the same launches."""
     assert k or r
     points = _as_points(points)
     n = points.shape[0]
     dev = points.device
     self_query = query is None or query is points
     bounds = SortedMap.bounds_of(points, None if self_query else query)
+    stack = None
+    if stack_first is not None:
+        assert self_query and r, 'the stacked search is a self query with a radius (the guard band between clouds)'
+        n_clouds = int(stack_first.numel()) - 1
     if cell is None:
         if k:
-            cell = _knn_cell_size(points, int(k), r, bounds) if n > 0 else 1.0
+            if stack_first is not None and n > 0:
+                # occupancy of ONE cloud (the clouds overlap in their common frame)
+                n0 = max(n // n_clouds, 1)
+                cell = _knn_cell_size(points[:n0], int(k), r, bounds, use_hint=False)
+            else:
+                cell = _knn_cell_size(points, int(k), r, bounds) if n > 0 else 1.0
         else:
             cell = float(r) * (1.0 + 1e-6)   # a hair above r: one ring of cells is always enough
-    smap = SortedMap(points, cell, bounds=bounds)
+    if stack_first is not None:
+        stack = (stack_first, n_clouds, int(math.ceil(float(r) / cell)))
+    smap = SortedMap(points, cell, bounds=bounds, stack=stack)
     st = L.stream()
     if self_query:
         Q, qkeys, qorder, nq = smap.P, smap.keys, None, n

@@ -25,7 +25,7 @@ __all__ = [
     'establish_neighborhoods',
     'filtered_cloud',
     'global_cloud',
-    'global_cloud_mask',
+    'global_cloud_mask', 'local_feature_clouds',
     'GlobalCloud',
     'local_feature_cloud',
     'Neighborhoods',
@@ -198,6 +198,78 @@ def local_feature_cloud(cloud, cfg):
             filter_eigenvalues(cloud, cfg.eigenvalue_bounds, only_mask=True, log=True)
             filter_eigenvalue_ratios(cloud, cfg.eigenvalue_ratio_bounds, only_mask=True, log=True)
     return cloud
+
+
+LOCAL_FEATURES_CHUNK = 1 << 23
+
+
+def local_feature_clouds(clouds, cfg):
+    """[local_feature_cloud(c, cfg) for c in clouds] (the setup loop of train.py:97-104 / scripts/model_poses_learning:85-86)
+    in a handful of launches instead of ~15 per scan: ONE stacked neighbour search (every scan in its own band of cell
+    layers: dc_cell_keys_stacked), ONE pass over the neighbourhoods (dc_step_forward: mean, covariance, eigen in fp64),
+    one kernel for normals / incidence angles (dc_local_features_finish) and one for the masks (dc_feature_mask).
+
+    Sets points, mean, eigvals, normals, inc_angles and mask on every cloud (cov, eigvecs and the per-scan neighbour
+    lists, which only the staged API reads, are not kept).  Same neighbour sets as the per-scan search; eigenvalues agree
+    to rounding (the fused pass treats |lambda0| <= 1e-14 lambda2 as exactly 0, so masks can differ on rank-deficient
+    neighbourhoods only).  Falls back to the per-scan loop for host clouds, a shadow filter, or kNN without a radius."""
+    from . import _lib as L
+    clouds = list(clouds)
+    batchable = (len(clouds) > 1 and all(isinstance(c, DepthCloud) and c.depth.is_cuda for c in clouds) and cfg.nn_r
+                 and not getattr(cfg, 'shadow_angle_bounds', None) and len({c.depth.dtype for c in clouds}) == 1
+                 and cfg.nn_type == NeighborhoodType.ball)
+    if not batchable:
+        return [local_feature_cloud(c, cfg) for c in clouds]
+    total = sum(len(c) for c in clouds)
+    if total > LOCAL_FEATURES_CHUNK:
+        # bound the temporaries (graph + fp64 records + stash of ALL scans at once): groups of up to ~8 M points
+        out, group, count = [], [], 0
+        for c in clouds:
+            if group and count + len(c) > LOCAL_FEATURES_CHUNK:
+                out += local_feature_clouds(group, cfg) if len(group) > 1 else [local_feature_cloud(group[0], cfg)]
+                group, count = [], 0
+            group.append(c)
+            count += len(c)
+        out += local_feature_clouds(group, cfg) if len(group) > 1 else [local_feature_cloud(group[0], cfg)]
+        return out
+    dev, dt = clouds[0].depth.device, clouds[0].depth.dtype
+    st = L.stream()
+    sizes = [len(c) for c in clouds]
+    n = sum(sizes)
+    pts = torch.cat([c.get_points().detach() for c in clouds]).contiguous()
+    dirs = torch.cat([c.dirs.detach() for c in clouds]).contiguous()
+    first_host = [0]
+    for m in sizes:
+        first_host.append(first_host[-1] + m)
+    first = L.upload(first_host, torch.int64, dev)
+    graph = search(pts, None, k=cfg.nn_k, r=cfg.nn_r, stack_first=first)
+    smap = graph.map
+    meta = torch.full((n,), 3, dtype=torch.int32, device=dev)
+    stash = torch.empty((n, 8), dtype=torch.float64, device=dev)
+    eig_sorted = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    L.call('dc_step_forward', L.ptr(smap.P), L.ptr(meta), n, L.ptr(graph.slice_ptr), L.ptr(graph.ell_idx), L.LOSS_MIN_EIGVAL,
+           L.FLAG_RAW, None, L.ptr(stash), L.ptr(eig_sorted), None, None, 0, st)
+    eigvals = torch.empty((n, 3), dtype=dt, device=dev)
+    mean = torch.empty((n, 3), dtype=dt, device=dev)
+    normals = torch.empty((n, 3), dtype=dt, device=dev)
+    inc = torch.empty((n, 1), dtype=dt, device=dev)
+    L.call('dc_local_features_finish', L.ptr(stash), L.ptr(eig_sorted), L.ptr(smap.order), L.ptr(dirs), L.dtype_code(dt), n, 0,
+           L.ptr(eigvals), L.ptr(mean), L.ptr(normals), L.ptr(inc), st)
+    mask = None
+    if cfg.eigenvalue_bounds or cfg.eigenvalue_ratio_bounds:
+        start = None
+        if any(c.mask is not None for c in clouds):
+            start = torch.cat([c.mask if c.mask is not None else torch.ones(m, dtype=torch.bool, device=dev) for c, m in zip(clouds, sizes)])
+        holder = DepthCloud(dirs=dirs[:1], depth=inc[:1])          # (feature_mask only reads .eigvals of its argument)
+        holder.eigvals = eigvals
+        mask = feature_mask(holder, eigenvalue_bounds=cfg.eigenvalue_bounds, eigenvalue_ratio_bounds=cfg.eigenvalue_ratio_bounds, mask=start)
+    for s, c in enumerate(clouds):
+        a, b = first_host[s], first_host[s + 1]
+        c.points = pts[a:b]
+        c.mean, c.eigvals, c.normals, c.inc_angles = mean[a:b], eigvals[a:b], normals[a:b], inc[a:b]
+        if mask is not None:
+            c.mask = mask[a:b]
+    return clouds
 
 
 def offset_cloud(clouds, model):

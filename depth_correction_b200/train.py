@@ -22,7 +22,7 @@ from .icp import nanquantile
 from .graph import search
 from .loss import create_loss
 from .model import load_model
-from .preproc import (compute_neighborhood_features, establish_neighborhoods, global_cloud, global_cloud_mask,
+from .preproc import (compute_neighborhood_features, establish_neighborhoods, global_cloud, global_cloud_mask, local_feature_clouds,
                       local_feature_cloud)
 
 __all__ = ['TrainCallbacks', 'train']
@@ -54,14 +54,15 @@ def _prepare(datasets, cfg):
     """Per-scan feature clouds and poses of every sequence (train.py:92-110)."""
     all_clouds, all_poses = [], []
     for ds in datasets:
+        if cfg.nn_type != NeighborhoodType.ball:
+            raise NotImplementedError('plane neighbourhoods are out of scope of the B200 hot path')
         clouds, poses = [], []
         for cloud, pose in ds:
-            if cfg.nn_type == NeighborhoodType.ball:
-                cloud = local_feature_cloud(cloud, cfg)
-            else:
-                raise NotImplementedError('plane neighbourhoods are out of scope of the B200 hot path')
             clouds.append(cloud)
             poses.append(np.asarray(pose.detach().cpu() if isinstance(pose, torch.Tensor) else pose))
+        # the reference calls local_feature_cloud scan by scan (train.py:97-104); here all scans of a sequence go through
+        # one stacked search and one neighbourhood pass
+        clouds = local_feature_clouds(clouds, cfg)
         all_clouds.append(clouds)
         all_poses.append(torch.as_tensor(np.stack(poses).astype(np.float64), device=cfg.device))
     return all_clouds, all_poses

@@ -78,6 +78,14 @@ int dc_bounds(const void* pts, int dtype, int64_t n, double* out6, int32_t* bad_
 int dc_cell_keys(const void* pts, int dtype, int64_t n, const dc_grid_spec* spec_host, uint64_t* keys, int32_t* ids,
                  void* stream);
 
+/* the same for MANY clouds stacked along the slowest key axis (cloud s = rows first[s] .. first[s+1] of pts) so that one
+ * search serves all of them without ever pairing points of different clouds: cloud s owns the cell layers
+ * [s * period, s * period + period - guard) of that axis, guard >= the largest ring of cells the search will visit
+ * (ceil(r / cell)); spec->dims of the slowest axis must be n_clouds * period.  Batched form of the per-scan searches
+ * of local_feature_cloud (preproc.py:50, train.py:97-104). */
+int dc_cell_keys_stacked(const void* pts, int dtype, int64_t n, const dc_grid_spec* spec_host, const int64_t* first,
+                         int n_clouds, int period, int guard, uint64_t* keys, int32_t* ids, void* stream);
+
 /* stable radix sort of (key, id) pairs on key bits [0, end_bit) */
 int dc_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const int32_t* ids_in, int32_t* ids_out, int64_t n,
                   int end_bit, void* temp, size_t* temp_bytes, void* stream);
@@ -256,6 +264,14 @@ int dc_pose_compose_backward(const double* poses, const double* deltas, int n_sc
  * ------------------------------------------------------------------------------------------- */
 int dc_features(const void* points, int dtype, int64_t n, const int64_t* neighbors, const float* weights, int K,
                 void* mean, void* cov, void* stream);
+/* Per-point features of many clouds at once, second half (the first is dc_step_forward on the stacked graph with
+ * points = the sorted records of the search): stash fp64 [n,8] and eigvals_sorted fp64 [n,3] per SORTED row ->
+ * eigvals / mean / normals [n,3] and inc_angles [n] in the caller's order and dtype (any output may be NULL).
+ * Replaces update_mean / update_eig / update_normals / update_incidence_angles of every scan
+ * (depth_cloud.py:291-295, 376-424) called from local_feature_cloud (preproc.py:50). */
+int dc_local_features_finish(const double* stash, const double* eigvals_sorted, const int32_t* order, const void* dirs, int dtype,
+                             int64_t n, int use_normal_sign, void* eigvals, void* mean, void* normals, void* inc_angles,
+                             void* stream);
 /* Feature masks in one launch: filter_valid_neighbors / filter_eigenvalue(s) / filter_eigenvalue_ratio(s) /
  * within_bounds (filters.py:85-113, 184-254), as composed by local_feature_cloud (preproc.py:53-62) and
  * global_cloud_mask (preproc.py:130-142).  vals: [n, stride] values of `dtype` (eigvals: stride 3; a scalar field such

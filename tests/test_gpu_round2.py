@@ -214,3 +214,32 @@ def test_loss_mask_and_scan_records_are_snapshots(dc, dev):
     feats = dc.compute_neighborhood_features(cloud=dc.global_cloud(clouds=fresh_clouds, model=model, poses=poses_t), neighborhoods=ns, cfg=cfg)
     fresh = dc.min_eigval_loss(feats, normalization=True)[0].item()
     assert edited == fresh and edited != base
+
+
+@pytest.mark.parametrize('kw', [dict(nn_k=0, nn_r=0.4), dict(nn_k=12, nn_r=0.5)])
+def test_batched_local_features_equal_the_per_scan_loop(dc, dev, kw):
+    """local_feature_clouds (one stacked search + one neighbourhood pass for all scans) against
+    [local_feature_cloud(c) for c in scans] (preproc.py:35-64 per scan): same neighbourhoods -> eigenvalues, normals and
+    incidence angles agree to rounding; masks agree except on rank-deficient neighbourhoods."""
+    from depth_correction_b200.synthetic import make_sequence
+    scans_np, _, _ = make_sequence('fee', n_scans=5, pattern='os0-128', seed=6, rings=48, azimuths=384, depth_clip=(1.0, 20.0))
+    cfg = dc.Config(min_depth=0.0, grid_res=0.0, **kw)
+    pts = [torch.as_tensor(s['points'], device=dev) for s in scans_np]
+    ref = [dc.local_feature_cloud(dc.DepthCloud.from_points(p), cfg) for p in pts]
+    got = dc.local_feature_clouds([dc.DepthCloud.from_points(p) for p in pts], cfg)
+    assert len(got) == len(ref)
+    n_all = n_diff = 0
+    for a, b in zip(got, ref):
+        assert a.eigvals.shape == b.eigvals.shape and a.inc_angles.shape == b.inc_angles.shape and a.mask.dtype == torch.bool
+        ea, eb = a.eigvals.double(), b.eigvals.double()
+        scale = eb[:, 2:3].clamp_min(1e-12)
+        assert float(((ea - eb).abs() / scale).max()) < 2e-5                     # relative to the largest eigenvalue (float32 storage)
+        planar = (eb[:, 0] < 0.05 * eb[:, 1]) & (eb[:, 1] > 1e-4) & ((b.neighbors >= 0).sum(dim=1) >= 6)      # well-defined normal
+        assert planar.float().mean() > 0.3
+        assert float((a.inc_angles - b.inc_angles).abs()[planar].max()) < 2e-3
+        cos = (a.normals * b.normals).sum(dim=1)[planar]
+        assert float(cos.min()) > 1.0 - 1e-5
+        assert float((a.mean - b.mean).abs().max()) < 1e-4
+        n_all += a.mask.numel()
+        n_diff += int((a.mask != b.mask).sum())
+    assert n_diff <= 2e-3 * n_all, (n_diff, n_all)
