@@ -289,8 +289,10 @@ def reduce_step(sum_count, params, group=None):
     sum_count: tensor [2] from the fused loss (sum over owned points, number of owned points) with autograd
     history; params: tensors whose .grad the step fills (model.w, pose deltas ...).  Returns the global mean
     loss; every rank ends with identical, globally normalised .grad tensors."""
-    sum_count[0].backward()
-    grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+    # gradients of THIS step only (torch.autograd.grad, not .backward(): whatever a caller left in p.grad must not be
+    # summed into the all-reduce and divided by the count)
+    got = torch.autograd.grad(sum_count[0], list(params), allow_unused=True)
+    grads = [g if g is not None else torch.zeros_like(p) for g, p in zip(got, params)]
     buf = torch.cat([sum_count.detach().reshape(-1).double()] + [g.reshape(-1).double() for g in grads])
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, group=group)
