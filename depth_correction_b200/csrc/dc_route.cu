@@ -76,7 +76,21 @@ __global__ void route_pack_kernel(const dc_scan_ptrs* __restrict__ tbl, const in
                                   const uint8_t* __restrict__ gmin, const uint8_t* __restrict__ gmax,
                                   const int64_t* __restrict__ dest_offset, int32_t* __restrict__ cursor,
                                   T* __restrict__ send_f, int32_t* __restrict__ send_i) {
+  // Slots inside a destination's region are reserved per BLOCK: positions within the block from shared-memory counters,
+  // one global atomic per (block, destination).  (One global atomicAdd per record on the n_ranks cursors serialised the
+  // whole kernel: 5.7 ms for 8.4 M records, 74 % of the exchange.)
+  __shared__ int s_cnt[DC_ROUTE_MAX_RANKS], s_base[DC_ROUTE_MAX_RANKS];
+  if (threadIdx.x < DC_ROUTE_MAX_RANKS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int pos[4] = {0, 0, 0, 0};
+  if (i < n) {
+    const int lo = gmin[i], hi = gmax[i];
+    for (int g = lo; g <= hi && g - lo < 4; ++g) pos[g - lo] = atomicAdd(&s_cnt[g], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < b.n_ranks) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0;
+  __syncthreads();
   if (i >= n) return;
   const int s = dc_route_find_scan(first, n_scans, i);
   const int64_t li = i - first[s];
@@ -94,7 +108,8 @@ __global__ void route_pack_kernel(const dc_scan_ptrs* __restrict__ tbl, const in
   const int owner = dc_route_bucket(b, wp[3 * i + axis]);
   const int mm = (!mask || mask[li]) ? 1 : 0;
   for (int g = gmin[i]; g <= gmax[i]; ++g) {
-    const int64_t slot = dest_offset[g] + atomicAdd(&cursor[g], 1);
+    // (a point within the halo of more than four slabs -- slabs thinner than the halo -- reserves the rest one by one)
+    const int64_t slot = dest_offset[g] + (g - gmin[i] < 4 ? s_base[g] + pos[g - gmin[i]] : atomicAdd(&cursor[g], 1));
     T* f = send_f + 8 * slot;
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = rec[k];
