@@ -371,7 +371,7 @@ class Job(object):
 
         run()
         self.sync()
-        n_e2e = max(2, min(steps, 3))
+        n_e2e = max(3, min(steps, 10))
         w0 = time.perf_counter()
         for _ in range(n_e2e):
             out = run()
