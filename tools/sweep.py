@@ -35,9 +35,9 @@ def main():
     dev = torch.device('cuda:0')
     peak = 6548.5
     lines = ['# Sweep (BASELINE.json configs[4]): kNN-within-r search and fixed-graph step on corridor maps of full-resolution OS0-128 scans',
-             '', 'CUDA-event times, best of 3; step = `dc_step_points` + `dc_step_forward` + backward + chain on a reused graph '
+             '', 'CUDA-event times, best of 3; step = `dc_step_points` + `dc_step_forward_scatter` (or the two-kernel forms below 2^20 points) + chain on a reused graph '
              '(ScaledPolynomial[2,4], min_eigval_loss(normalization), per-scan pose corrections); roofline fraction = '
-             '(328 + 8K) B/point / step time / %.1f GB/s.' % peak, '',
+             '(206 + 8K) B/point (SURVEY.md section 8(d)) / step time / %.1f GB/s.' % peak, '',
              '| points | k | r [m] | mean valid neighbours | search ms | search Mpts/s | step ms | step Mpts/s | step frac of HBM roofline |', '|---|---|---|---|---|---|---|---|---|']
     for n_scans in (8, 77, 763):
         if n_scans > max_scans:
@@ -74,7 +74,7 @@ def main():
                     return loss
                 step()
                 ms_step, _ = timed(step, reps=4)
-                frac = (328 + 8 * k) * n / (ms_step * 1e-3) / 1e9 / peak
+                frac = (206 + 8 * k) * n / (ms_step * 1e-3) / 1e9 / peak
                 lines.append('| %d | %d | %.1f | %.1f | %.2f | %.0f | %.2f | %.0f | %.3f |'
                              % (n, k, r, deg, ms_search, n / ms_search / 1e3, ms_step, n / ms_step / 1e3, frac))
                 print(lines[-1], flush=True)
