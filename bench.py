@@ -399,7 +399,8 @@ def algorithmic_bytes(job, ns):
     idx_bwd = g._transposed.ell_idx.numel() * 4 if g._transposed is not None else idx_fwd
     n_cells = g.map.n_cells if g.map.cell_start is not None else 0
     nr = job.n_resident
-    big = nr >= (1 << 20)
+    from depth_correction_b200.fused import SCATTER_F32_MIN_POINTS
+    big = nr >= SCATTER_F32_MIN_POINTS
     return {
         'dc_knn': nr * (32 + 8) + idx_fwd + 4 * n_cells,                    # records + keys + cell table in, lists out
         'dc_cell_keys': nr * (24 + 8 + 4),
@@ -536,9 +537,27 @@ def other_configs(dc, dev):
         t1.record()
         torch.cuda.synchronize()
         n = sum(len(c) for c in clouds)
-        return {'n_points': n, 'n_scans': len(clouds), 'search_ms': s0.elapsed_time(s1), 'train_iteration_ms': t0.elapsed_time(t1) / iters,
-                'iterations_points_per_s': n / (t0.elapsed_time(t1) / iters * 1e-3), 'max_neighbors': int(ns.graph.width),
-                'loss_after_%d_iterations' % (iters + 3): float(loss.item())}, ns
+        res = {'n_points': n, 'n_scans': len(clouds), 'search_ms': s0.elapsed_time(s1), 'train_iteration_ms': t0.elapsed_time(t1) / iters,
+               'iterations_points_per_s': n / (t0.elapsed_time(t1) / iters * 1e-3), 'max_neighbors': int(ns.graph.width),
+               'loss_after_%d_iterations' % (iters + 3): float(loss.item())}
+        # the same iteration recorded into a CUDA graph (capture.py): the eager loop above is bound by ~1 ms of Python
+        # per iteration at this size, the replay by the kernels.  Same start, same number of iterations, same loss.
+        model = dc.ScaledPolynomial(w=[0.0, 0.0], exponent=[2, 4], device=dev)
+        deltas = torch.zeros((len(clouds), 6), dtype=torch.float64, device=dev, requires_grad=True)
+        opt = torch.optim.Adam([{'params': deltas, 'lr': 1e-3}, {'params': model.parameters(), 'lr': 1e-3}], capturable=True)
+        step = dc.CapturedIteration(it, warmup=3)
+        torch.cuda.synchronize()
+        t0.record()
+        for _ in range(iters):
+            loss_c = step()
+        t1.record()
+        torch.cuda.synchronize()
+        cap_ms = t0.elapsed_time(t1) / iters
+        res.update({'captured_iteration_ms': cap_ms, 'captured_iterations_points_per_s': n / (cap_ms * 1e-3),
+                    'captured_library_launches': step.library_launches,
+                    'captured_loss_rel_diff': abs(float(loss_c) - float(loss.item())) / abs(float(loss.item()))})
+        assert res['captured_loss_rel_diff'] < 1e-6, res
+        return res, ns
 
     # configs[0]: planar corridor, 10 OS0-128 scans, the reference's filters (depth 1-25 m, 0.2 m voxels), radius graph r = 0.4
     cfg0 = dc.Config(min_depth=1.0, max_depth=25.0, grid_res=0.2, nn_k=0, nn_r=NN_R, pose_correction=dc.PoseCorrection.pose)

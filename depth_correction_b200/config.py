@@ -79,7 +79,7 @@ class Config(object):
         self.n_opt_iters = 100
         self.optimize_model = True
         self.log_dir = None                  # train() creates a temporary directory when unset
-        # how dL/dp is accumulated by the fused step: 'auto' (float32 L2 reductions on maps of >= 2^20 points, fast, not
+        # how dL/dp is accumulated by the fused step: 'auto' (float32 L2 reductions on maps of >= 2^19 points, fast, not
         # bitwise reproducible), 'gather' (fp64, atomic-free: deterministic like the reference's autograd), 'scatter'
         self.backward_form = 'auto'
         self.train_names = []

@@ -23,10 +23,11 @@ TRANSPOSE_AFTER = 2                     # backward passes served by the scatter 
 # The scatter form accumulates dL/dp in float32 (one vector reduction per edge instead of three fp64 ones, 3x faster)
 # on maps of at least this many points: there the fp32 rounding of the per-point sums (random, 6e-8 relative per
 # addition) averages out over the points the chain stage adds up in fp64 (measured: gradients agree with the fp64
-# gather form to ~1e-7 on the bench map, tests/test_gpu_parity.py::test_scatter_f32_agrees_with_gather_form).
+# gather form to ~1e-7 on the bench map and to < 1e-6 on a 0.5 M point map,
+# tests/test_gpu_parity.py::test_scatter_f32_agrees_with_gather_form).
 # DC_SCATTER_F32=0 / 1 forces the choice; DC_BACKWARD=gather forces the deterministic fp64 gather form (bitwise
 # reproducible gradients), DC_BACKWARD=scatter the scatter form.
-SCATTER_F32_MIN_POINTS = 1 << 20
+SCATTER_F32_MIN_POINTS = 1 << 19
 # 'auto' (policy above) | 'gather' (fp64, atomic-free, bitwise reproducible gradients) | 'scatter'.  Set through
 # set_backward_form() / Config.backward_form; the environment variable DC_BACKWARD only provides the initial value.
 BACKWARD_FORM = os.environ.get('DC_BACKWARD', 'auto')
@@ -35,7 +36,7 @@ _form_logged = set()
 
 def set_backward_form(form):
     """Select how dL/dp is accumulated: 'auto', 'gather' (deterministic fp64) or 'scatter' (L2 reductions; float32 on
-    maps of >= 2^20 points).  The reference's autograd is deterministic: use 'gather' for bit-reproducible runs."""
+    maps of >= 2^19 points).  The reference's autograd is deterministic: use 'gather' for bit-reproducible runs."""
     global BACKWARD_FORM
     assert form in ('auto', 'gather', 'scatter'), form
     BACKWARD_FORM = form

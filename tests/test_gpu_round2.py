@@ -243,3 +243,47 @@ def test_batched_local_features_equal_the_per_scan_loop(dc, dev, kw):
         n_all += a.mask.numel()
         n_diff += int((a.mask != b.mask).sum())
     assert n_diff <= 2e-3 * n_all, (n_diff, n_all)
+
+
+@pytest.mark.parametrize('kw', [dict(nn_k=0, nn_r=0.25), dict(nn_k=10, nn_r=0.4)])
+def test_captured_iteration_follows_the_eager_loop(dc, dev, kw):
+    """The optimisation iteration of scripts/model_poses_learning:121-135 recorded into a CUDA graph
+    (depth_correction_b200/capture.py) takes the same trajectory as the eager loop: same losses, same parameters."""
+    from depth_correction_b200.synthetic import make_sequence
+    cfg = dc.Config(min_depth=1.0, max_depth=15.0, grid_res=0.1, loss='min_eigval_loss',
+                    pose_correction=dc.PoseCorrection.pose, **kw)
+    scans, _, poses_init = make_sequence('fee', n_scans=5, pattern='os0-32', seed=9, pose_noise=(0.01, 0.005),
+                                         bias_w=[-0.01], bias_exponent=[4.0])
+    poses = torch.as_tensor(poses_init, device=dev)
+
+    def setup():
+        clouds = dc.local_feature_clouds([dc.filtered_cloud(dc.DepthCloud.from_points(torch.as_tensor(s['points'], device=dev)), cfg)
+                                          for s in scans], cfg)
+        model = dc.ScaledPolynomial(w=[0.0, 0.0], exponent=[2, 4], device=dev)
+        deltas = torch.zeros((len(clouds), 6), dtype=torch.float64, device=dev, requires_grad=True)
+        opt = torch.optim.Adam([{'params': deltas, 'lr': 1e-3}, {'params': model.parameters(), 'lr': 1e-3}], capturable=True)
+        ns = dc.establish_neighborhoods(clouds=clouds, poses=poses, cfg=cfg)
+
+        def iteration():
+            pc = torch.stack(dc.create_corrected_poses(poses, deltas, cfg))
+            feats = dc.compute_neighborhood_features(cloud=dc.global_cloud(clouds=clouds, model=model, poses=pc),
+                                                     neighborhoods=ns, cfg=cfg)
+            loss, _ = dc.min_eigval_loss(feats)
+            opt.zero_grad()
+            loss.backward()
+            deltas.grad[0].zero_()                       # first pose fixed (train.py:281-284)
+            opt.step()
+            return loss
+        return iteration, model, deltas
+
+    it_e, model_e, deltas_e = setup()
+    eager = [float(it_e()) for _ in range(9)]
+    it_c, model_c, deltas_c = setup()
+    step = dc.CapturedIteration(it_c, warmup=3)
+    assert step.library_launches >= 5
+    captured = [float(x) for x in step.warmup_outputs] + [float(step().clone()) for _ in range(6)]
+    assert eager[-1] < eager[0]
+    np.testing.assert_allclose(captured, eager, rtol=1e-9, atol=0)
+    assert rel_err_norm(model_c.w.detach().cpu(), model_e.w.detach().cpu()) < 1e-8
+    assert rel_err_norm(deltas_c.detach().cpu(), deltas_e.detach().cpu()) < 1e-8
+    assert step.replays == 6

@@ -35,7 +35,7 @@ def main():
     dev = torch.device('cuda:0')
     peak = 6548.5
     lines = ['# Sweep (BASELINE.json configs[4]): kNN-within-r search and fixed-graph step on corridor maps of full-resolution OS0-128 scans',
-             '', 'CUDA-event times, best of 3; step = `dc_step_points` + `dc_step_forward_scatter` (or the two-kernel forms below 2^20 points) + chain on a reused graph '
+             '', 'CUDA-event times, best of 3; step = `dc_step_points` + `dc_step_forward_scatter` (or the two-kernel forms below 2^19 points) + chain on a reused graph '
              '(ScaledPolynomial[2,4], min_eigval_loss(normalization), per-scan pose corrections); roofline fraction = '
              '(206 + 8K) B/point (SURVEY.md section 8(d)) / step time / %.1f GB/s.' % peak, '',
              '| points | k | r [m] | mean valid neighbours | search ms | search Mpts/s | step ms | step Mpts/s | step frac of HBM roofline |', '|---|---|---|---|---|---|---|---|---|']
