@@ -2,6 +2,8 @@
 // format conversions (sliced-ELL <-> the reference's padded int64 [N,K]) and the transposed graph.
 // Replaces cKDTree.query / query_ball_point and the Python padding loop of
 // nearest_neighbors.py:46-73.
+#include <cstdlib>
+#include <cstring>
 #include <cub/cub.cuh>
 #include "dc_common.cuh"
 #include "dc_grid.cuh"
@@ -68,6 +70,70 @@ radius_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys
   }
 }
 
+// Fill pass with coalesced list stores.  The sliced-ELL layout keeps the c-th neighbour of the 32 queries of a slice
+// in one 128-byte line, so a lane that stores its own matches as it finds them touches a different line per store (one
+// LSU wavefront each: the stores, not the distance tests, were 75 % of the fill pass).  Here every lane parks its
+// matches in a private shared-memory column (RF_ROWS deep; bank = lane, no conflicts, no synchronisation: a lane only
+// reads what it wrote) and the warp flushes row by row: for row R every lane that holds its R-th neighbour writes it,
+// one partially-masked 128-byte store per row.  The loops over candidates are made warp-uniform (trip count = the
+// longest row range of the warp) so that the flush can be taken by all lanes together.
+#define RF_ROWS 64
+
+__global__ void __launch_bounds__(NN_THREADS)
+radius_fill_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
+                   const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
+                   const int32_t* __restrict__ cell_start, double r2, int rings, const int64_t* __restrict__ slice_ptr,
+                   int32_t* __restrict__ ell_idx) {
+  __shared__ int32_t s_tile[NN_THREADS / 32][RF_ROWS * 32];
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  if ((q >> 5) > ((nq - 1) >> 5)) return;                       // whole warp beyond the last slice
+  int32_t* tile = s_tile[threadIdx.x >> 5] + lane;
+  const int64_t base = slice_ptr[q >> 5];
+  const int width = (int)((slice_ptr[(q >> 5) + 1] - base) >> 5);
+  int32_t* out = ell_idx + base + lane;
+  const bool live = q < nq;                                     // lanes past the end of the last slice only pad
+  int cnt = 0, done = 0;                                        // matches found / already written (per lane)
+  dc_point pq = {0.0, 0.0, 0.0, 0.0};
+  int c0 = 0, c1 = 0, c2 = 0;
+  if (live) {
+    pq = dc_ld_point(Q + q);
+    dc_key_coords(g, qkeys[q], c0, c1, c2);
+  }
+  for (int e2 = -rings; e2 <= rings; ++e2) {
+    for (int e1 = -rings; e1 <= rings; ++e1) {
+      int lo = 0, hi = 0;
+      if (live) dc_row_range(g, pkeys, n, cell_start, c0 - rings, c0 + rings, c1 + e1, c2 + e2, lo, hi);
+      const int trips = __reduce_max_sync(0xffffffffu, (hi - lo + 3) >> 2);
+      for (int it = 0; it < trips; ++it) {
+        const int j = lo + 4 * it;
+        if (j < hi) {
+          const int last = hi - 1;
+          const int j1 = j + 1 < last ? j + 1 : last, j2 = j + 2 < last ? j + 2 : last, j3 = j + 3 < last ? j + 3 : last;
+          const dc_point p0 = dc_ld_point(P + j), p1 = dc_ld_point(P + j1);
+          const dc_point p2 = dc_ld_point(P + j2), p3 = dc_ld_point(P + j3);
+          const bool in0 = dc_dist2(p0, pq) <= r2, in1 = j + 1 < hi && dc_dist2(p1, pq) <= r2;
+          const bool in2 = j + 2 < hi && dc_dist2(p2, pq) <= r2, in3 = j + 3 < hi && dc_dist2(p3, pq) <= r2;
+          if (in0) { tile[(cnt - done) * 32] = j; ++cnt; }
+          if (in1) { tile[(cnt - done) * 32] = j + 1; ++cnt; }
+          if (in2) { tile[(cnt - done) * 32] = j + 2; ++cnt; }
+          if (in3) { tile[(cnt - done) * 32] = j + 3; ++cnt; }
+        }
+        if (__any_sync(0xffffffffu, cnt - done > RF_ROWS - 4)) {
+          const int r_lo = __reduce_min_sync(0xffffffffu, done), r_hi = __reduce_max_sync(0xffffffffu, cnt);
+          for (int R = r_lo; R < r_hi; ++R)
+            if (R >= done && R < cnt) out[(int64_t)R * DC_SLICE] = tile[(R - done) * 32];
+          done = cnt;
+        }
+      }
+    }
+  }
+  // remaining matches, then the -1 padding, still row by row
+  const int r_lo = __reduce_min_sync(0xffffffffu, done);
+  for (int R = r_lo; R < width; ++R)
+    if (R >= done) out[(int64_t)R * DC_SLICE] = R < cnt ? tile[(R - done) * 32] : -1;
+}
+
 static int radius_launch(bool fill, const void* P, const uint64_t* pkeys, int64_t n, const void* Q,
                          const uint64_t* qkeys, int64_t nq, const dc_grid_spec* spec, const int32_t* cell_start,
                          double r, int32_t* counts, int32_t* slice_width, const int64_t* slice_ptr, int32_t* ell_idx,
@@ -82,7 +148,11 @@ static int radius_launch(bool fill, const void* P, const uint64_t* pkeys, int64_
   const double r2 = r * r;
   const int blocks = dc_blocks(((nq + 31) / 32) * 32, NN_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
-  if (fill)
+  static const bool direct_stores = getenv("DC_RADIUS_FILL") && !strcmp(getenv("DC_RADIUS_FILL"), "direct");   // A/B switch
+  if (fill && !direct_stores)
+    radius_fill_kernel<<<blocks, NN_THREADS, 0, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq, g, cell_start,
+                                                       r2, rings, slice_ptr, ell_idx);
+  else if (fill)
     radius_kernel<true><<<blocks, NN_THREADS, 0, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq, g,
                                                         cell_start, r2, rings, counts, slice_width, slice_ptr, ell_idx);
   else

@@ -1,7 +1,10 @@
-"""Radius-mode search + fixed-graph step on voxel-filtered scans (the reference's default setting: grid_res 0.1-0.2 m,
-nn_r 0.25-0.4 m, nn_k 0).  Developer tool, GPU box."""
+"""Radius-mode search (count + fill passes) on three maps; run twice (DC_RADIUS_FILL=direct / default) to A/B the fill
+kernel.  Prints per-entry-point CUDA-event times and a checksum of the lists.
+
+    python tools/prof_radius.py
+"""
+import os
 import sys
-import time
 
 import numpy as np
 import torch
@@ -9,57 +12,32 @@ import torch
 sys.path.insert(0, '.')
 import depth_correction_b200 as dc                      # noqa: E402
 from depth_correction_b200 import _lib as L             # noqa: E402
-from depth_correction_b200.synthetic import make_sequence, make_poses   # noqa: E402
+from depth_correction_b200.graph import search         # noqa: E402
+from depth_correction_b200.synthetic import make_sequence  # noqa: E402
+
+dev = torch.device('cuda:0')
+print('DC_RADIUS_FILL =', os.environ.get('DC_RADIUS_FILL', '(staged rows)'))
 
 
-def main():
-    dev = torch.device('cuda:0')
-    n_scans = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-    scans, _, _ = make_sequence('corridor', n_scans=n_scans, pattern='os0-128', seed=0)
-    poses = torch.as_tensor(make_poses('corridor', n_scans), device=dev)
-    for grid_res, r in ((0.1, 0.25), (0.1, 0.4), (0.05, 0.15), (0.2, 0.4)):
-        cfg = dc.Config(nn_k=0, nn_r=r, grid_res=grid_res, min_depth=1.0, max_depth=25.0, pose_correction=dc.PoseCorrection.pose)
-        t0 = time.perf_counter()
-        clouds = []
-        for s in scans:
-            c = dc.filtered_cloud(dc.DepthCloud.from_points(torch.from_numpy(s['points']).to(dev)), cfg)
-            c.inc_angles = torch.rand((len(c), 1), device=dev)
-            clouds.append(c)
+def world(scene, n_scans, grid_res, pattern='os0-128', **kw):
+    scans, poses, _ = make_sequence(scene, n_scans=n_scans, pattern=pattern, seed=5, grid_res=grid_res, **kw)
+    return torch.as_tensor(np.concatenate([s['points'].astype(np.float64) @ T[:3, :3].T + T[:3, 3] for s, T in zip(scans, poses)]).astype(np.float32), device=dev)
+
+
+for name, pts, r in (('fee 12 scans 0.1 m voxels, r=0.25', world('fee', 12, 0.1), 0.25),
+                     ('corridor 16 full scans, r=0.15', world('corridor', 16, 0.0), 0.15),
+                     ('street 8 HDL-64 scans, r=0.4', world('street', 8, 0.0, pattern='hdl-64', depth_clip=(5.0, 80.0)), 0.4)):
+    for rep in range(3):
+        L.profile = {} if rep == 2 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g = search(pts, k=0, r=r)
+        e1.record()
         torch.cuda.synchronize()
-        t_filter = (time.perf_counter() - t0) * 1e3
-        n = sum(len(c) for c in clouds)
-        deltas = torch.zeros((n_scans, 6), dtype=torch.float64, device=dev, requires_grad=True)
-        model = dc.ScaledPolynomial(w=[0.0, 0.0], exponent=[2, 4], device=dev)
-        best_s = best_f = 1e9
-        for rep in range(3):
-            L.profile = {}
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            ns = dc.establish_neighborhoods(clouds=clouds, poses=poses, cfg=cfg)
-            torch.cuda.synchronize()
-            best_s = min(best_s, (time.perf_counter() - t0) * 1e3)
-            prof_s = L.collect_profile()
-            L.profile = None
-
-            def step():
-                model.zero_grad(set_to_none=True)
-                deltas.grad = None
-                pc = torch.stack(dc.create_corrected_poses(poses, deltas, cfg))
-                feats = dc.compute_neighborhood_features(cloud=dc.global_cloud(clouds=clouds, model=model, poses=pc), neighborhoods=ns, cfg=cfg)
-                loss, _ = dc.min_eigval_loss(feats, normalization=True)
-                loss.backward()
-            step()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            step()
-            torch.cuda.synchronize()
-            best_f = min(best_f, (time.perf_counter() - t0) * 1e3)
-        deg = ns.graph.degrees().double()
-        print('grid %.2f r %.2f: %d points (filter_grid of %d scans %.1f ms), neighbours mean %.1f max %d; search %.2f ms (%s), step %.2f ms'
-              % (grid_res, r, n, n_scans, t_filter, deg.mean().item(), int(deg.max().item()), best_s,
-                 ', '.join('%s %.2f' % (k, v['ms_total']) for k, v in sorted(prof_s.items(), key=lambda kv: -kv[1]['ms_total'])[:3]), best_f),
-              flush=True)
-
-
-if __name__ == '__main__':
-    main()
+    times = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in L.profile.items()}
+    L.profile = None
+    idx = g.ell_idx.long()
+    chk = int(((idx + 2) * (torch.arange(idx.numel(), device=dev) % 1000003 + 1)).sum() % (1 << 61))
+    print('%-40s n=%8d width=%4d mean=%6.1f search %.3f ms  count %.3f  fill %.3f  checksum %d' % (
+        name, len(pts), g.width, float((g.ell_idx >= 0).sum()) / len(pts), e0.elapsed_time(e1),
+        times.get('dc_radius_count', 0), times.get('dc_radius_fill', 0), chk))
