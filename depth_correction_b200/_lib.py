@@ -58,6 +58,7 @@ SIGNATURES = {
     'dc_radius_fill': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _D, _P, _P, _P],
     'dc_knn': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _I, _D, _P, _P, _P],
     'dc_knn_cells': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _I, _D, _P, _P, _SZP, _P],
+    'dc_knn_recorded': [_P, _P, _L, _P, _P, _L, _SPEC, _P, _I, _D, _P, _P, _SZP, _P],
     'dc_knn_sort_rows': [_P, _L, _I, _P, _P, _L, _P],
     'dc_knn_distances': [_P, _P, _I, _P, _L, _P, _P],
     'dc_ell_to_padded': [_P, _P, _L, _P, _P, _I, _P, _P],

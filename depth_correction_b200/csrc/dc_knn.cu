@@ -19,8 +19,9 @@
 #include "dc_common.cuh"
 #include "dc_grid.cuh"
 
-#define KNN_THREADS 128
+#define KNN_THREADS 64
 #define KNN_WARPS (KNN_THREADS / 32)
+#define KNN_BLOCKS (1024 / KNN_THREADS)   // resident blocks per SM the register allocation is held to (64 registers)
 #define KNN_BINS 64
 
 // (d2, original index) lexicographic order.  The original index (dc_point.tag) -- not the position in the cell-sorted
@@ -244,7 +245,7 @@ __device__ __forceinline__ bool knn_thread_query(const dc_point* __restrict__ P,
   return true;
 }
 
-__global__ void __launch_bounds__(KNN_THREADS, 8)
+__global__ void __launch_bounds__(KNN_THREADS, KNN_BLOCKS)
 knn_thread_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
                   const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
                   const int32_t* __restrict__ cell_start, int k, double r2cap, int max_ring,
@@ -796,14 +797,18 @@ knn_cell_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pke
 }
 
 // the queries the cell kernel could not finish, one per thread, exact fp64 selection
-__global__ void __launch_bounds__(KNN_THREADS, 8)
+__global__ void __launch_bounds__(KNN_THREADS, KNN_BLOCKS)
 knn_thread_list_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
                        const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, dc_grid g,
                        const int32_t* __restrict__ cell_start, int k, double r2cap, int max_ring,
                        const int2* __restrict__ fb_list, const int32_t* __restrict__ counters, int32_t* __restrict__ ell_idx) {
   __shared__ unsigned short hist[KNN_BINS][KNN_THREADS];
   const int count = counters[1];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+  // entry i goes to lane i / n_warps of warp i % n_warps: a short list of heavy queries is spread over all warps
+  // instead of filling the first few with 32 heavy queries each
+  const int n_warps = gridDim.x * (blockDim.x >> 5);
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (int i = warp + (threadIdx.x & 31) * n_warps; i < count; i += 32 * n_warps) {
     const int2 e = fb_list[i];
     const int q = e.x;
     int32_t* out_j = ell_idx + (int64_t)(q >> 5) * k * DC_SLICE + (q & 31);
@@ -820,6 +825,322 @@ knn_thread_list_kernel(const dc_point* __restrict__ P, const uint64_t* __restric
                      });
     for (int c = cnt; c < k; ++c) out_j[(int64_t)c * DC_SLICE] = -1;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Recorded path (dc_knn_recorded): one query per thread like dc_knn, but ONE distance pass.
+//
+// The histogram pass of dc_knn already visits every candidate of the block and knows the bin of each one inside the
+// bound; dc_knn then walks all rows again (loads, fp64 distances, bins) to emit.  Here the first pass records the bin
+// of every visited candidate -- one byte, 255 = outside the bound, four candidates per 32-bit word, one word per
+// iteration of the four-wide scan loop -- in a thread-private array (local memory), and the later passes walk the same
+// rows reading the record instead of the map: only the candidates OF the boundary bin (a handful) are re-read to be
+// ranked by (fp64 d2, original index) with the very arithmetic of dc_knn.  The word index is the thread's own iteration
+// counter: the lanes of a warp that sit in the same cell walk identical rows, so their counters agree and a warp's
+// access touches as many 128-byte lines as it has cells (about three), like the candidate loads themselves.  (A record
+// of (index, bin) pairs of the in-range candidates only -- shorter, but at lane-private positions, one line per lane
+// and access -- was no faster than re-walking the rows.)  Same result as dc_knn bit for bit, same order inside a row.
+// Iterations beyond KR_WORDS (long scans: many rings, dense cells) are not recorded and are recomputed by the later
+// passes, so there is no cliff; queries with more than 8 candidates tied in the boundary sub-bin (exact ties,
+// duplicates) go to a list that knn_thread_list_kernel finishes.
+// ---------------------------------------------------------------------------------------------
+#define KR_WORDS 256
+
+// rows of knn_scan in the same order, one callback per four-wide iteration: f(j, hi) with j the first candidate
+template <typename F>
+__device__ __forceinline__ void knn_rows(const dc_grid& g, const uint64_t* __restrict__ pkeys, int64_t n,
+                                         const int32_t* __restrict__ cell_start, int c0, int c1, int c2, int rho, F&& f) {
+  for (int e2 = -rho; e2 <= rho; ++e2) {
+    for (int e1 = -rho; e1 <= rho; ++e1) {
+      int lo, hi;
+      dc_row_range(g, pkeys, n, cell_start, c0 - rho, c0 + rho, c1 + e1, c2 + e2, lo, hi);
+      for (int j = lo; j < hi; j += 4) f(j, hi);
+    }
+  }
+}
+
+// the same rows, sixteen candidates per callback
+template <typename F>
+__device__ __forceinline__ void knn_rows16(const dc_grid& g, const uint64_t* __restrict__ pkeys, int64_t n,
+                                           const int32_t* __restrict__ cell_start, int c0, int c1, int c2, int rho, F&& f) {
+  for (int e2 = -rho; e2 <= rho; ++e2) {
+    for (int e1 = -rho; e1 <= rho; ++e1) {
+      int lo, hi;
+      dc_row_range(g, pkeys, n, cell_start, c0 - rho, c0 + rho, c1 + e1, c2 + e2, lo, hi);
+      for (int j = lo; j < hi; j += 16) f(j, hi);
+    }
+  }
+}
+
+// bins of the four candidates j .. j+3 of a row ending at hi (255 = outside the bound / past the end): what the first
+// pass records, recomputed for the iterations a long scan could not record
+__device__ __forceinline__ unsigned int knn_word(const dc_point* __restrict__ P, const dc_point& pq, int j, int hi, double bound2,
+                                              double scale1) {
+  const int lastj = hi - 1;
+  const int j1 = j + 1 < lastj ? j + 1 : lastj, j2 = j + 2 < lastj ? j + 2 : lastj, j3 = j + 3 < lastj ? j + 3 : lastj;
+  const dc_point p0 = dc_ld_point(P + j), p1 = dc_ld_point(P + j1);
+  const dc_point p2 = dc_ld_point(P + j2), p3 = dc_ld_point(P + j3);
+  const double d0 = dc_dist2(p0, pq), d1 = dc_dist2(p1, pq), d2 = dc_dist2(p2, pq), d3 = dc_dist2(p3, pq);
+  unsigned int w = 0xffffffffu;
+  if (d0 < bound2) w ^= (unsigned int)(knn_bin(d0, scale1) ^ 255);
+  if (j + 1 < hi && d1 < bound2) w ^= (unsigned int)(knn_bin(d1, scale1) ^ 255) << 8;
+  if (j + 2 < hi && d2 < bound2) w ^= (unsigned int)(knn_bin(d2, scale1) ^ 255) << 16;
+  if (j + 3 < hi && d3 < bound2) w ^= (unsigned int)(knn_bin(d3, scale1) ^ 255) << 24;
+  return w;
+}
+
+__global__ void __launch_bounds__(KNN_THREADS, KNN_BLOCKS)
+knn_record_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
+                  const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
+                  const int32_t* __restrict__ cell_start, int k, double r2cap, int max_ring,
+                  int2* __restrict__ fb_list, int32_t* __restrict__ counters, int32_t* __restrict__ ell_idx) {
+  __shared__ unsigned short hist[KNN_BINS][KNN_THREADS];
+  unsigned int rec[KR_WORDS];
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  if (nq <= 0 || (q >> 5) > ((nq - 1) >> 5)) return;
+  int32_t* out_j = ell_idx + (q >> 5) * (int64_t)k * DC_SLICE + lane;
+  int cnt = 0;
+  bool fallback = false;
+  if (q < nq) {
+    unsigned short* h = &hist[0][threadIdx.x];
+    const dc_point pq = dc_ld_point(Q + q);
+    int c0, c1, c2;
+    dc_key_coords(g, qkeys[q], c0, c1, c2);
+    const double slack_cell = g.cell * (1.0 - 1e-9);
+    // ---- 1. ring growth + level-1 histogram + record
+    int rho = 1;
+    double bound2, scale1;
+    unsigned int n_in;
+    int n_words;
+    for (;;) {
+      if (rho > max_ring) rho = max_ring;
+      const bool last = rho >= max_ring;
+      const double reach = rho * slack_cell;
+      bound2 = last ? r2cap : fmin(reach * reach, r2cap);
+      scale1 = (double)KNN_BINS / bound2;
+#pragma unroll
+      for (int b = 0; b < KNN_BINS; ++b) h[b * KNN_THREADS] = (unsigned short)0;
+      n_in = 0u;
+      n_words = 0;
+      knn_rows(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int j, int hi) {
+        const int lastj = hi - 1;
+        const int j1 = j + 1 < lastj ? j + 1 : lastj, j2 = j + 2 < lastj ? j + 2 : lastj, j3 = j + 3 < lastj ? j + 3 : lastj;
+        const dc_point p0 = dc_ld_point(P + j), p1 = dc_ld_point(P + j1);
+        const dc_point p2 = dc_ld_point(P + j2), p3 = dc_ld_point(P + j3);
+        const double d0 = dc_dist2(p0, pq), d1 = dc_dist2(p1, pq), d2 = dc_dist2(p2, pq), d3 = dc_dist2(p3, pq);
+        unsigned int w = 0xffffffffu;
+        auto visit = [&](double dd, int slot) {
+          if (dd < bound2) {
+            const int b = knn_bin(dd, scale1);
+            const unsigned short v = h[b * KNN_THREADS];
+            h[b * KNN_THREADS] = v == 65535 ? v : (unsigned short)(v + 1);
+            ++n_in;
+            w ^= (unsigned int)(b ^ 255) << (8 * slot);
+          }
+        };
+        visit(d0, 0);
+        if (j + 1 < hi) visit(d1, 1);
+        if (j + 2 < hi) visit(d2, 2);
+        if (j + 3 < hi) visit(d3, 3);
+        if (n_words < KR_WORDS) rec[n_words] = w;
+        ++n_words;
+      });
+      if (n_in >= (unsigned int)k || last) break;
+      rho = rho < 4 ? rho + 1 : rho * 2;
+    }
+    if (n_in <= (unsigned int)k) {
+      // everything inside the bound is a neighbour (fewer than k exist within r / in the map)
+      int it = 0;
+      knn_rows(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int j, int hi) {
+        const unsigned int w = it < KR_WORDS ? rec[it] : knn_word(P, pq, j, hi, bound2, scale1);
+        ++it;
+        if (w == 0xffffffffu) return;
+#pragma unroll
+        for (int s_ = 0; s_ < 4; ++s_)
+          if (((w >> (8 * s_)) & 255u) != 255u) out_j[(int64_t)(cnt++) * DC_SLICE] = j + s_;
+      });
+    } else {
+      // ---- level 1: bin of the k-th distance
+      unsigned int c_lo = 0u, cnt1 = 0u;
+      int b1 = 0;
+      for (; b1 < KNN_BINS; ++b1) {
+        cnt1 = h[b1 * KNN_THREADS];
+        if (c_lo + cnt1 >= (unsigned int)k) break;
+        c_lo += cnt1;
+      }
+      int b2 = KNN_BINS;
+      unsigned int cnt2 = cnt1;
+      const bool lvl2 = cnt1 > 8u && c_lo + cnt1 > (unsigned int)k;
+      if (lvl2) {
+        // ---- 2. level-2 histogram over the recorded candidates of bin b1
+#pragma unroll
+        for (int b = 0; b < KNN_BINS; ++b) h[b * KNN_THREADS] = (unsigned short)0;
+        int it = 0;
+        knn_rows(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int j, int hi) {
+          const unsigned int w = it < KR_WORDS ? rec[it] : knn_word(P, pq, j, hi, bound2, scale1);
+        ++it;
+          if (w == 0xffffffffu) return;
+#pragma unroll
+          for (int s_ = 0; s_ < 4; ++s_) {
+            if ((int)((w >> (8 * s_)) & 255u) != b1) continue;
+            const double s = dc_dist2(dc_ld_point(P + j + s_), pq) * scale1;
+            int bb = __double2int_rz((s - (double)b1) * (double)KNN_BINS);
+            bb = bb < 0 ? 0 : (bb > KNN_BINS - 1 ? KNN_BINS - 1 : bb);
+            const unsigned short v = h[bb * KNN_THREADS];
+            h[bb * KNN_THREADS] = v == 65535 ? v : (unsigned short)(v + 1);
+          }
+        });
+        for (b2 = 0; b2 < KNN_BINS; ++b2) {
+          cnt2 = h[b2 * KNN_THREADS];
+          if (c_lo + cnt2 >= (unsigned int)k) break;
+          c_lo += cnt2;
+        }
+      }
+      const unsigned int t = (unsigned int)k - c_lo;
+      const bool take_all = (t == cnt2);
+      if (!take_all && cnt2 > 8u) {
+        fallback = true;                     // more than 8 candidates tied in the boundary sub-bin: repeated selection, rare
+      } else {
+        // ---- 3. emit from the record
+        int nb = 0;
+        int it = 0;
+        // four words of the record per step, loaded together: the record comes back from L2 (480 KB per SM do not
+        // stay in L1) and one dependent load per word left the pass waiting on it for 12 % of the kernel
+        knn_rows16(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int jg, int hi) {
+          const int left = hi - jg;
+          const int nw = left >= 16 ? 4 : (left + 3) >> 2;
+          unsigned int w0, w1 = 0xffffffffu, w2 = 0xffffffffu, w3 = 0xffffffffu;
+          if (it + 3 < KR_WORDS) {
+            w0 = rec[it]; w1 = rec[it + 1]; w2 = rec[it + 2]; w3 = rec[it + 3];      // words past nw: ignored below
+          } else {
+            w0 = it < KR_WORDS ? rec[it] : knn_word(P, pq, jg, hi, bound2, scale1);
+            if (nw > 1) w1 = it + 1 < KR_WORDS ? rec[it + 1] : knn_word(P, pq, jg + 4, hi, bound2, scale1);
+            if (nw > 2) w2 = it + 2 < KR_WORDS ? rec[it + 2] : knn_word(P, pq, jg + 8, hi, bound2, scale1);
+            if (nw > 3) w3 = it + 3 < KR_WORDS ? rec[it + 3] : knn_word(P, pq, jg + 12, hi, bound2, scale1);
+          }
+          it += nw;
+          for (int i = 0; i < nw; ++i) {
+          const unsigned int w = i == 0 ? w0 : (i == 1 ? w1 : (i == 2 ? w2 : w3));
+          if (w == 0xffffffffu) continue;
+          const int j0 = jg + 4 * i;
+#pragma unroll
+          for (int s_ = 0; s_ < 4; ++s_) {
+            const int b = (int)((w >> (8 * s_)) & 255u);
+            const int j = j0 + s_;
+            if (b < b1) {
+              out_j[(int64_t)(cnt++) * DC_SLICE] = j;
+            } else if (b == b1) {
+              if (take_all && !lvl2) {
+                out_j[(int64_t)(cnt++) * DC_SLICE] = j;
+              } else {
+                const dc_point pj = dc_ld_point(P + j);
+                const double d2 = dc_dist2(pj, pq);
+                bool boundary = true;
+                if (lvl2) {
+                  int bb = __double2int_rz((d2 * scale1 - (double)b1) * (double)KNN_BINS);
+                  bb = bb < 0 ? 0 : (bb > KNN_BINS - 1 ? KNN_BINS - 1 : bb);
+                  if (bb < b2) out_j[(int64_t)(cnt++) * DC_SLICE] = j;
+                  boundary = (bb == b2);
+                }
+                if (boundary) {
+                  if (take_all) {
+                    out_j[(int64_t)(cnt++) * DC_SLICE] = j;
+                  } else if (nb < 8) {
+                    const int tag = (int)pj.tag;
+                    const unsigned long long u = (unsigned long long)__double_as_longlong(d2);
+                    unsigned short* e = h + 8 * nb * KNN_THREADS;
+                    e[0] = (unsigned short)u;
+                    e[KNN_THREADS] = (unsigned short)(u >> 16);
+                    e[2 * KNN_THREADS] = (unsigned short)(u >> 32);
+                    e[3 * KNN_THREADS] = (unsigned short)(u >> 48);
+                    e[4 * KNN_THREADS] = (unsigned short)j;
+                    e[5 * KNN_THREADS] = (unsigned short)((unsigned int)j >> 16);
+                    e[6 * KNN_THREADS] = (unsigned short)tag;
+                    e[7 * KNN_THREADS] = (unsigned short)((unsigned int)tag >> 16);
+                    ++nb;
+                  }
+                }
+              }
+            }
+          }
+          }
+        });
+        if (!take_all) {
+          double bd[8];
+          int bj[8], bt[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const unsigned short* e = h + 8 * i * KNN_THREADS;
+            const unsigned long long u = (unsigned long long)e[0] | ((unsigned long long)e[KNN_THREADS] << 16) |
+                                         ((unsigned long long)e[2 * KNN_THREADS] << 32) | ((unsigned long long)e[3 * KNN_THREADS] << 48);
+            const int j = (int)((unsigned int)e[4 * KNN_THREADS] | ((unsigned int)e[5 * KNN_THREADS] << 16));
+            bd[i] = i < nb ? __longlong_as_double((long long)u) : INFINITY;
+            bj[i] = i < nb ? j : 0x7fffffff;
+            bt[i] = i < nb ? (int)((unsigned int)e[6 * KNN_THREADS] | ((unsigned int)e[7 * KNN_THREADS] << 16)) : 0x7fffffff;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            unsigned int rank = 0u;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) rank += knn_less(bd[m], bt[m], bd[i], bt[i]) ? 1u : 0u;
+            if (i < nb && rank < t) out_j[(int64_t)(cnt++) * DC_SLICE] = bj[i];
+          }
+        }
+      }
+    }
+    if (fallback) {
+      const int slot = atomicAdd(counters + 1, 1);
+      fb_list[slot] = make_int2((int)q, rho);
+    }
+  }
+  if (!fallback)
+    for (int c = cnt; c < k; ++c) out_j[(int64_t)c * DC_SLICE] = -1;
+}
+
+__global__ void knn_record_init_kernel(int32_t* counters) { counters[0] = 0; counters[1] = 0; }
+
+extern "C" int dc_knn_recorded(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
+                               const dc_grid_spec* spec, const int32_t* cell_start, int k, double r, int32_t* ell_idx,
+                               void* temp, size_t* temp_bytes, void* stream) {
+  if (!temp_bytes) return dc_set_error(DC_ERR_ARG, "dc_knn_recorded: temp_bytes is NULL");
+  if (k < 1) return dc_set_error(DC_ERR_ARG, "dc_knn_recorded: k must be positive");
+  if (nq > 2147483647LL || n > 2147483647LL) return dc_set_error(DC_ERR_OVERFLOW, "dc_knn_recorded: more than 2^31-1 points");
+  // workspace: 64-byte header (counters) | fallback list int2[nq]
+  const size_t need = 64 + (size_t)(nq > 0 ? nq : 1) * 8;
+  if (!temp) { *temp_bytes = need; return DC_OK; }
+  if (*temp_bytes < need) return dc_set_error(DC_ERR_ARG, "dc_knn_recorded: workspace too small");
+  if (nq <= 0) return DC_OK;
+  dc_grid g;
+  int rc = dc_make_grid(spec, &g);
+  if (rc) return rc;
+  int max_ring = g.d[0] > g.d[1] ? g.d[0] : g.d[1];
+  max_ring = max_ring > g.d[2] ? max_ring : g.d[2];
+  const double ex = g.d[0] * g.cell, ey = g.d[1] * g.cell, ez = g.d[2] * g.cell;
+  double r2cap = 16.0 * (ex * ex + ey * ey + ez * ez) + 1.0;
+  if (r > 0.0) {
+    r2cap = r * r;
+    const int rr = (int)ceil(r / g.cell);
+    if (rr < max_ring) max_ring = rr;
+  }
+  if (max_ring < 1) max_ring = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* counters = (int32_t*)temp;
+  int2* fb = (int2*)((char*)temp + 64);
+  knn_record_init_kernel<<<1, 1, 0, st>>>(counters);
+  DC_LAUNCH_CHECK();
+  const int64_t n_slices = (nq + DC_SLICE - 1) / DC_SLICE;
+  const int blocks = dc_blocks(n_slices * DC_SLICE, KNN_THREADS);
+  knn_record_kernel<<<blocks, KNN_THREADS, 0, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq, g, cell_start, k,
+                                                    r2cap, max_ring, fb, counters, ell_idx);
+  DC_LAUNCH_CHECK();
+  int dev = 0, sms = 148;
+  DC_CUDA_CHECK(cudaGetDevice(&dev));
+  DC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  knn_thread_list_kernel<<<sms * 4, KNN_THREADS, 0, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, g, cell_start,
+                                                         k, r2cap, max_ring, fb, counters, ell_idx);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
 }
 
 struct kt_is_cell_start {

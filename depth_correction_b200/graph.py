@@ -401,7 +401,12 @@ def search(points, query=None, k=None, r=None, cell=None, stack_first=None):
         k = int(k)
         sp = torch.arange(ns + 1, dtype=torch.int64, device=dev) * (L.SLICE * k)
         idx = torch.empty(max(ns * L.SLICE * k, 1), dtype=torch.int32, device=dev)
-        if k <= 128 and os.environ.get('DC_KNN', 'thread') == 'cells':
+        knn_impl = os.environ.get('DC_KNN', 'thread')
+        if knn_impl == 'record':
+            # one distance pass: (index, bin) of the in-range candidates recorded during the histogram pass, emit from the record
+            L.call_with_temp('dc_knn_recorded', dev, L.ptr(smap.P), L.ptr(smap.keys), n, L.ptr(Q), L.ptr(qkeys), nq, spec,
+                             L.ptr(smap.cell_start), k, float(r) if r else 0.0, L.ptr(idx), after=(st,))
+        elif k <= 128 and knn_impl == 'cells':
             # second, independent implementation (one warp per occupied cell, fp32 classification + fp64 re-check):
             # bit-identical rows, not faster on lidar maps (profiles/r2_knn_cell_kernel.md) -- opt-in, used as a cross-check
             L.call_with_temp('dc_knn_cells', dev, L.ptr(smap.P), L.ptr(smap.keys), n, L.ptr(Q), L.ptr(qkeys), nq, spec,

@@ -130,6 +130,13 @@ int dc_knn(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const
 int dc_knn_cells(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
                  const dc_grid_spec* spec_host, const int32_t* cell_start, int k, double r, int32_t* ell_idx, void* temp,
                  size_t* temp_bytes, void* stream);
+/* The same search with ONE distance pass per query: the histogram pass records (index, bin) of every candidate inside the
+ * bound in a thread-private list and the emit pass replays the record, re-reading only the candidates of the boundary
+ * bin; queries with more than 256 candidates inside the bound (or > 8 exact ties at the k-th place) are finished by the
+ * kernel of dc_knn.  Same rows as dc_knn, entry by entry.  temp: 64 + 8 nq bytes (two-phase size query). */
+int dc_knn_recorded(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
+                    const dc_grid_spec* spec_host, const int32_t* cell_start, int k, double r, int32_t* ell_idx, void* temp,
+                    size_t* temp_bytes, void* stream);
 /* order every kNN row by (d^2, original index = tag of the map record) in place: cKDTree.query returns
  * distance-sorted rows (nearest_neighbors.py:48); needed only when the reference layout is exported */
 int dc_knn_sort_rows(const void* P, int64_t n, int k, int32_t* ell_idx, double* ell_d2, int64_t nq, void* stream);

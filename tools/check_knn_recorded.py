@@ -1,0 +1,71 @@
+"""dc_knn_recorded (one distance pass, emit from the record) against dc_knn on the GPU box: identical lists entry by entry,
+kernel times, share of the queries handed to the fallback list (developer tool).
+
+    python tools/check_knn_recorded.py [n_scans ...]
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, '.')
+import depth_correction_b200 as dc                      # noqa: E402,F401
+from depth_correction_b200 import _lib as L             # noqa: E402
+from depth_correction_b200.graph import search          # noqa: E402
+from depth_correction_b200.synthetic import make_sequence  # noqa: E402
+
+dev = torch.device('cuda:0')
+
+
+def world(scene, n_scans, pattern='os0-128', **kw):
+    scans, poses, _ = make_sequence(scene, n_scans=n_scans, pattern=pattern, seed=0, **kw)
+    return torch.as_tensor(np.concatenate([s['points'].astype(np.float64) @ T[:3, :3].T + T[:3, 3] for s, T in zip(scans, poses)]).astype(np.float32), device=dev)
+
+
+def timed(pts, k, r, path, reps=3):
+    os.environ['DC_KNN'] = path
+    names = {'record': ('init', 'dc_knn_recorded'), 'thread': ('dc_knn',)}[path]
+    best, g = None, None
+    for _ in range(reps):
+        del g
+        L.profile = {}
+        g = search(pts, k=k, r=r)
+        torch.cuda.synchronize()
+        prof = L.collect_profile()
+        L.profile = None
+        ms = prof[names[-1]]['ms_total']
+        best = ms if best is None else min(best, ms)
+    nfb = None
+    if path == 'record':
+        ws = L._workspace.get(('temp:dc_knn_recorded', str(pts.device)))
+        nfb = int(ws[:8].view(torch.int32)[1])
+    return g, best, nfb
+
+
+cases = []
+for a in sys.argv[1:] or ['16']:
+    cases.append(('corridor %s scans k=32 r=0.4' % a, world('corridor', int(a)), 32, 0.4))
+cases.append(('corridor 8 scans k=16', world('corridor', 8), 16, None))
+cases.append(('corridor 8 scans k=64 r=0.5', world('corridor', 8), 64, 0.5))
+cases.append(('street 8 HDL-64 scans k=32 r=0.4', world('street', 8, pattern='hdl-64', depth_clip=(5.0, 80.0)), 32, 0.4))
+rng = np.random.default_rng(3)
+c = rng.uniform(-10, 10, (200, 3))
+clu = (c[rng.integers(0, 200, 300000)] + rng.normal(0, 0.3, (300000, 3))).astype(np.float32)
+clu[500:900] = clu[:400]
+cases.append(('clustered + duplicates k=8', torch.as_tensor(clu, device=dev), 8, None))
+lat = np.stack(np.meshgrid(np.arange(40), np.arange(40), np.arange(10), indexing='ij'), -1).reshape(-1, 3).astype(np.float32) * 0.25
+cases.append(('lattice (exact ties) k=27 r=0.5', torch.as_tensor(lat, device=dev), 27, 0.5))
+ok = True
+for name, pts, k, r in cases:
+    gt, mt, _ = timed(pts, k, r, 'thread')
+    a = gt.ell_idx.clone()
+    del gt
+    gr, mr, nfb = timed(pts, k, r, 'record')
+    same = bool(torch.equal(a, gr.ell_idx))
+    ok &= same
+    print('%-36s n=%9d  dc_knn %.3f ms  dc_knn_recorded %.3f ms (%.2fx)  fallback %d (%.3f %%)  identical lists: %s' % (
+        name, len(pts), mt, mr, mt / mr, nfb, 100.0 * nfb / len(pts), same))
+    del gr, a
+print('OK' if ok else 'MISMATCH')
+sys.exit(0 if ok else 1)
