@@ -403,6 +403,7 @@ def algorithmic_bytes(job, ns):
     big = nr >= SCATTER_F32_MIN_POINTS
     return {
         'dc_knn': nr * (32 + 8) + idx_fwd + 4 * n_cells,                    # records + keys + cell table in, lists out
+        'dc_knn_recorded': nr * (32 + 8) + idx_fwd + 4 * n_cells,           # the same arrays (the record of bins stays in L1/L2)
         'dc_cell_keys': nr * (24 + 8 + 4),
         'dc_gather_points': nr * (24 + 4 + 32 + 4),
         'dc_cell_table': nr * 8 + 4 * n_cells,
@@ -681,7 +682,7 @@ def run_ours(args):
         roofline = {'bound': 'hbm', 'kernel': top, 'achieved': tab_timed[top]['GBps'], 'peak': peak, 'unit': 'GB/s',
                     'frac': tab_timed[top]['frac'], 'traffic': traffic.get(top), 'peak_source': peak_src,
                     'avg_kernel_ms': tab_timed[top]['ms'], 'algorithmic_bytes': alg[top],
-                    'note': 'dominant kernel of the timed region; dc_knn is bound by instruction issue and gather latency, not by '
+                    'note': 'dominant kernel of the timed region; the kNN kernel is bound by instruction issue and gather latency, not by '
                             'HBM (profiles/r2_knn_experiments.md); the HBM-side kernels are the fixed-graph step kernels below',
                     # the headline metric itself against the roofline, with SURVEY.md section 8(d)'s bytes per point
                     'headline': {'bytes_per_point': HEADLINE_BYTES_PER_POINT,

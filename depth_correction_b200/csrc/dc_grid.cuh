@@ -66,6 +66,19 @@ __device__ __forceinline__ void dc_row_range(const dc_grid& g, const uint64_t* _
   }
 }
 
+// The same range without branches around the loads (cell table only): an invalid row reads entry 0 twice and yields
+// lo = hi = 0.  Lets a caller issue the lookups of several rows back to back instead of one dependent pair per row.
+__device__ __forceinline__ void dc_row_range_nb(const dc_grid& g, const int32_t* __restrict__ cell_start, int c0lo, int c0hi,
+                                                int c1, int c2, int& lo, int& hi) {
+  c0lo = c0lo < 0 ? 0 : c0lo;
+  c0hi = c0hi >= g.d[0] ? g.d[0] - 1 : c0hi;
+  const bool ok = c1 >= 0 && c1 < g.d[1] && c2 >= 0 && c2 < g.d[2] && c0lo <= c0hi;
+  const uint64_t base = ((uint64_t)c2 * (uint64_t)g.d[1] + (uint64_t)c1) * (uint64_t)g.d[0];
+  const uint64_t k0 = ok ? base + (uint64_t)c0lo : 0, k1 = ok ? base + (uint64_t)c0hi + 1 : 0;
+  lo = __ldg(cell_start + k0);
+  hi = __ldg(cell_start + k1);
+}
+
 // Squared distance exactly as cKDTree's p=2 kernel accumulates it for m=3: ((dx*dx + dy*dy) + dz*dz)
 // with every product and sum rounded separately (no FMA contraction), so that `<= r*r` / `< r*r`
 // decide identically for boundary points.

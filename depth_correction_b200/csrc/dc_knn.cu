@@ -34,19 +34,47 @@ __device__ __forceinline__ int knn_bin(double d2, double scale) {
   return b > KNN_BINS - 1 ? KNN_BINS - 1 : b;
 }
 
+// Rows of the (2 rho + 1)^2 x [c0 - rho, c0 + rho] block in increasing key order, STEP candidates per callback f(j, hi).
+// The cell-table lookups of three consecutive rows are issued together: one dependent pair of loads per row left every
+// row waiting for the table (L2 latency once the block is larger than a few cells: the sparse queries that grow to 8+
+// rings walk hundreds of mostly empty rows).
+template <int STEP, typename F>
+__device__ __forceinline__ void knn_rows_t(const dc_grid& g, const uint64_t* __restrict__ pkeys, int64_t n,
+                                           const int32_t* __restrict__ cell_start, int c0, int c1, int c2, int rho, F&& f) {
+  if (!cell_start) {
+    for (int e2 = -rho; e2 <= rho; ++e2)
+      for (int e1 = -rho; e1 <= rho; ++e1) {
+        int lo, hi;
+        dc_row_range(g, pkeys, n, cell_start, c0 - rho, c0 + rho, c1 + e1, c2 + e2, lo, hi);
+        for (int j = lo; j < hi; j += STEP) f(j, hi);
+      }
+    return;
+  }
+  for (int e2 = -rho; e2 <= rho; ++e2) {
+    for (int e1 = -rho; e1 <= rho; e1 += 3) {
+      int lo0, hi0, lo1, hi1, lo2, hi2;
+      dc_row_range_nb(g, cell_start, c0 - rho, c0 + rho, c1 + e1, c2 + e2, lo0, hi0);
+      dc_row_range_nb(g, cell_start, c0 - rho, c0 + rho, e1 + 1 <= rho ? c1 + e1 + 1 : -1, c2 + e2, lo1, hi1);
+      dc_row_range_nb(g, cell_start, c0 - rho, c0 + rho, e1 + 2 <= rho ? c1 + e1 + 2 : -1, c2 + e2, lo2, hi2);
+      for (int u = 0; u < 3; ++u) {
+        const int lo = u == 0 ? lo0 : (u == 1 ? lo1 : lo2), hi = u == 0 ? hi0 : (u == 1 ? hi1 : hi2);
+        for (int j = lo; j < hi; j += STEP) f(j, hi);
+      }
+    }
+  }
+}
+
 template <typename F>
 __device__ __forceinline__ void knn_scan(const dc_grid& g, const uint64_t* __restrict__ pkeys, int64_t n,
                                          const int32_t* __restrict__ cell_start, const dc_point* __restrict__ P,
                                          const dc_point& pq, int c0, int c1, int c2, int rho, F&& f) {
-  for (int e2 = -rho; e2 <= rho; ++e2) {
-    for (int e1 = -rho; e1 <= rho; ++e1) {
-      int lo, hi;
-      dc_row_range(g, pkeys, n, cell_start, c0 - rho, c0 + rho, c1 + e1, c2 + e2, lo, hi);
+  knn_rows_t<4>(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int j, int hi) {
+    {
+      {
       // four independent candidate loads in flight per thread (the loop is latency bound otherwise; a software
       // pipeline with eight in flight cost registers / occupancy and was 30 % slower).  The tail of a row goes
       // through the same four-wide body with clamped addresses: a one-at-a-time tail loop exposed a full load
       // latency per candidate on up to three candidates of every row.
-      for (int j = lo; j < hi; j += 4) {
         const int last = hi - 1;
         const int j1 = j + 1 < last ? j + 1 : last, j2 = j + 2 < last ? j + 2 : last, j3 = j + 3 < last ? j + 3 : last;
         const dc_point p0 = dc_ld_point(P + j), p1 = dc_ld_point(P + j1);
@@ -58,7 +86,7 @@ __device__ __forceinline__ void knn_scan(const dc_grid& g, const uint64_t* __res
         if (j + 3 < hi) f(j + 3, d3);
       }
     }
-  }
+  });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -850,26 +878,14 @@ knn_thread_list_kernel(const dc_point* __restrict__ P, const uint64_t* __restric
 template <typename F>
 __device__ __forceinline__ void knn_rows(const dc_grid& g, const uint64_t* __restrict__ pkeys, int64_t n,
                                          const int32_t* __restrict__ cell_start, int c0, int c1, int c2, int rho, F&& f) {
-  for (int e2 = -rho; e2 <= rho; ++e2) {
-    for (int e1 = -rho; e1 <= rho; ++e1) {
-      int lo, hi;
-      dc_row_range(g, pkeys, n, cell_start, c0 - rho, c0 + rho, c1 + e1, c2 + e2, lo, hi);
-      for (int j = lo; j < hi; j += 4) f(j, hi);
-    }
-  }
+  knn_rows_t<4>(g, pkeys, n, cell_start, c0, c1, c2, rho, f);
 }
 
 // the same rows, sixteen candidates per callback
 template <typename F>
 __device__ __forceinline__ void knn_rows16(const dc_grid& g, const uint64_t* __restrict__ pkeys, int64_t n,
                                            const int32_t* __restrict__ cell_start, int c0, int c1, int c2, int rho, F&& f) {
-  for (int e2 = -rho; e2 <= rho; ++e2) {
-    for (int e1 = -rho; e1 <= rho; ++e1) {
-      int lo, hi;
-      dc_row_range(g, pkeys, n, cell_start, c0 - rho, c0 + rho, c1 + e1, c2 + e2, lo, hi);
-      for (int j = lo; j < hi; j += 16) f(j, hi);
-    }
-  }
+  knn_rows_t<16>(g, pkeys, n, cell_start, c0, c1, c2, rho, f);
 }
 
 // bins of the four candidates j .. j+3 of a row ending at hi (255 = outside the bound / past the end): what the first
@@ -1093,12 +1109,16 @@ knn_record_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
       const int slot = atomicAdd(counters + 1, 1);
       fb_list[slot] = make_int2((int)q, rho);
     }
+#ifdef DC_KNN_STATS
+    atomicAdd(counters + 2 + (rho < 9 ? rho : 9), 1);          // final ring of the query (tools/knn_ring_stats.py)
+    atomicAdd((unsigned long long*)(counters + 14), (unsigned long long)n_words);
+#endif
   }
   if (!fallback)
     for (int c = cnt; c < k; ++c) out_j[(int64_t)c * DC_SLICE] = -1;
 }
 
-__global__ void knn_record_init_kernel(int32_t* counters) { counters[0] = 0; counters[1] = 0; }
+__global__ void knn_record_init_kernel(int32_t* counters) { if (threadIdx.x < 16) counters[threadIdx.x] = 0; }
 
 extern "C" int dc_knn_recorded(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
                                const dc_grid_spec* spec, const int32_t* cell_start, int k, double r, int32_t* ell_idx,
@@ -1127,7 +1147,7 @@ extern "C" int dc_knn_recorded(const void* P, const uint64_t* pkeys, int64_t n, 
   cudaStream_t st = (cudaStream_t)stream;
   int32_t* counters = (int32_t*)temp;
   int2* fb = (int2*)((char*)temp + 64);
-  knn_record_init_kernel<<<1, 1, 0, st>>>(counters);
+  knn_record_init_kernel<<<1, 32, 0, st>>>(counters);
   DC_LAUNCH_CHECK();
   const int64_t n_slices = (nq + DC_SLICE - 1) / DC_SLICE;
   const int blocks = dc_blocks(n_slices * DC_SLICE, KNN_THREADS);

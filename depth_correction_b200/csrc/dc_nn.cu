@@ -94,7 +94,7 @@ radius_fill_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ 
   int32_t* out = ell_idx + base + lane;
   const bool live = q < nq;                                     // lanes past the end of the last slice only pad
   int cnt = 0, done = 0;                                        // matches found / already written (per lane)
-  dc_point pq = {0.0, 0.0, 0.0, 0.0};
+  dc_point pq = {0.0, 0.0, 0.0, 0};
   int c0 = 0, c1 = 0, c2 = 0;
   if (live) {
     pq = dc_ld_point(Q + q);

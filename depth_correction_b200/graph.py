@@ -401,9 +401,11 @@ def search(points, query=None, k=None, r=None, cell=None, stack_first=None):
         k = int(k)
         sp = torch.arange(ns + 1, dtype=torch.int64, device=dev) * (L.SLICE * k)
         idx = torch.empty(max(ns * L.SLICE * k, 1), dtype=torch.int32, device=dev)
-        knn_impl = os.environ.get('DC_KNN', 'thread')
+        # DC_KNN selects among three implementations that return identical rows (tests/test_gpu_round2.py): 'record'
+        # (default: one distance pass, the emit pass replays the recorded bins), 'thread' (dc_knn: re-walks the rows;
+        # also the one that can return distances), 'cells' (one warp per occupied cell)
+        knn_impl = os.environ.get('DC_KNN', 'record')
         if knn_impl == 'record':
-            # one distance pass: (index, bin) of the in-range candidates recorded during the histogram pass, emit from the record
             L.call_with_temp('dc_knn_recorded', dev, L.ptr(smap.P), L.ptr(smap.keys), n, L.ptr(Q), L.ptr(qkeys), nq, spec,
                              L.ptr(smap.cell_start), k, float(r) if r else 0.0, L.ptr(idx), after=(st,))
         elif k <= 128 and knn_impl == 'cells':

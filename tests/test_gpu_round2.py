@@ -35,8 +35,9 @@ def _street_points(n_scans, seed=0):
 
 @pytest.mark.parametrize('case', ['clustered', 'lattice', 'street', 'cross'])
 def test_knn_cell_kernel_equals_thread_kernel(dc, dev, monkeypatch, case):
-    """dc_knn (one query per thread, fp64) and dc_knn_cells (one warp per cell, fp32 classification + fp64 re-check)
-    are independent implementations of the same selection: identical neighbour SETS, row by row."""
+    """dc_knn (one query per thread, fp64), dc_knn_cells (one warp per cell, fp32 classification + fp64 re-check) and
+    dc_knn_recorded (one query per thread, one distance pass) are three implementations of the same selection:
+    identical neighbour SETS, row by row."""
     from depth_correction_b200.graph import search
     rng = np.random.default_rng(5)
     query = None
@@ -61,10 +62,15 @@ def test_knn_cell_kernel_equals_thread_kernel(dc, dev, monkeypatch, case):
     p = torch.as_tensor(pts, device=dev)
     for kw in kws:
         monkeypatch.setenv('DC_KNN', 'thread')
-        a = _rows_sorted(search(p, query, **kw))
+        g = search(p, query, **kw)
+        a, a_raw = _rows_sorted(g), g.ell_idx.clone()
         monkeypatch.setenv('DC_KNN', 'cells')
         b = _rows_sorted(search(p, query, **kw))
         assert torch.equal(a, b), (case, kw, int((a != b).any(dim=1).sum()))
+        # dc_knn_recorded (the default: one distance pass, emit from the recorded bins) walks the rows in the order of
+        # dc_knn: the lists are equal entry by entry, not only as sets
+        monkeypatch.setenv('DC_KNN', 'record')
+        assert torch.equal(search(p, query, **kw).ell_idx, a_raw), (case, kw)
 
 
 def test_knn_ties_do_not_depend_on_the_cell_size(dc, dev):
