@@ -94,6 +94,9 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        # started before the warm-up steps (NVML initialisation takes longer than a short timed region); rows are kept
+        # only while `armed`, i.e. inside the timed region
+        self.armed, self.ready = False, threading.Event()
 
     def run(self):
         # NVML in-process (the same counters nvidia-smi prints); spawning nvidia-smi every 100 ms
@@ -108,7 +111,12 @@ class ClockSampler(threading.Thread):
             mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
             bits = [(pynvml.nvmlClocksThrottleReasonHwSlowdown, 2), (pynvml.nvmlClocksThrottleReasonHwThermalSlowdown, 3),
                     (pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, 4), (pynvml.nvmlClocksThrottleReasonSwPowerCap, 5)]
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.ready.set()
             while not self.stop_flag:
+                if not self.armed:
+                    time.sleep(0.002)
+                    continue
                 sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
                 reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 row = [str(sm), str(mx), 'Not Active', 'Not Active', 'Not Active', 'Not Active']
@@ -116,11 +124,15 @@ class ClockSampler(threading.Thread):
                     if reasons & bit:
                         row[col] = 'Active'
                 self.rows.append(row)
-                time.sleep(0.02)
+                time.sleep(0.01)
             return
         except Exception:
             pass
+        self.ready.set()
         while not self.stop_flag:
+            if not self.armed:
+                time.sleep(0.002)
+                continue
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
@@ -130,7 +142,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.5)
 
     def summary(self):
-        self.stop_flag = True
+        self.armed, self.stop_flag = False, True
         rows = [r for r in self.rows if len(r) == 6 and r[0].isdigit()]
         if not rows:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
@@ -273,6 +285,8 @@ class Job(object):
 
     def timed(self, L, steps, warmup, profile_kernels=True, sampler=None, nvtx=False):
         """`warmup` untimed + `steps` timed steps (search + step every time) -> dict of max-over-ranks device times."""
+        if sampler is not None:
+            sampler.start()
         for _ in range(warmup):
             loss, ns = self.step()
         self.sync()
@@ -280,7 +294,8 @@ class Job(object):
         launches0 = L.launch_count
         L.profile = {} if profile_kernels else None
         if sampler is not None:
-            sampler.start()
+            sampler.ready.wait(10.0)
+            sampler.armed = True
         self.sync()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
@@ -297,6 +312,8 @@ class Job(object):
             torch.cuda.profiler.stop()
         t1.record()
         self.sync()
+        if sampler is not None:
+            sampler.armed = False
         kernel_ms = L.collect_profile()
         L.profile = None
         total_ms = t0.elapsed_time(t1)

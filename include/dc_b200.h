@@ -117,7 +117,8 @@ int dc_radius_fill(const void* P, const uint64_t* pkeys, int64_t n, const void* 
  * (slice_ptr[t] = 32*k*t) holding the k nearest of every query in NO particular order (the step kernels
  * only need the set); ell_d2 (optional) receives the squared distances.  Exact ties at the k-th distance
  * are broken by the smaller ORIGINAL index (the tag of the map record), so the result does not depend on
- * the cell size.  One query per thread: the general path (any k, any density); dc_knn_cells is the fast one. */
+ * the cell size.  One query per thread, rows re-walked by the emit pass; the only variant that can return distances.
+ * The host code calls dc_knn_recorded (below) when it needs the lists only. */
 int dc_knn(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
            const dc_grid_spec* spec_host, const int32_t* cell_start, int k, double r, int32_t* ell_idx, double* ell_d2,
            void* stream);
@@ -132,8 +133,9 @@ int dc_knn_cells(const void* P, const uint64_t* pkeys, int64_t n, const void* Q,
                  size_t* temp_bytes, void* stream);
 /* The same search with ONE distance pass per query: the histogram pass records (index, bin) of every candidate inside the
  * bound in a thread-private list and the emit pass replays the record, re-reading only the candidates of the boundary
- * bin; queries with more than 256 candidates inside the bound (or > 8 exact ties at the k-th place) are finished by the
- * kernel of dc_knn.  Same rows as dc_knn, entry by entry.  temp: 64 + 8 nq bytes (two-phase size query). */
+ * bin (one byte per visited candidate; iterations beyond the 256-word record are recomputed in place); queries with
+ * > 8 exact ties at the k-th place are finished by the kernel of dc_knn.  Same rows as dc_knn, entry by entry.
+ * Replaces cKDTree.query (nearest_neighbors.py:48-49).  temp: 64 + 8 nq bytes (two-phase size query). */
 int dc_knn_recorded(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
                     const dc_grid_spec* spec_host, const int32_t* cell_start, int k, double r, int32_t* ell_idx, void* temp,
                     size_t* temp_bytes, void* stream);

@@ -82,7 +82,7 @@ def main():
     if len(sys.argv) > 5:
         # per-launch DRAM traffic by C-ABI entry point -> profiles/traffic.json (bench.py fills roofline.traffic from it)
         import json
-        entry = {'knn_thread_kernel': 'dc_knn', 'step_points_kernel': 'dc_step_points', 'step_forward_kernel': 'dc_step_forward',
+        entry = {'knn_thread_kernel': 'dc_knn', 'knn_record_kernel': 'dc_knn_recorded', 'step_points_kernel': 'dc_step_points', 'step_forward_kernel': 'dc_step_forward',
                  'step_forward_scatter': 'dc_step_forward_scatter',
                  'step_backward_gather_kernel': 'dc_step_backward', 'step_backward_scatter_kernel': 'dc_step_backward_scatter',
                  'step_chain_kernel': 'dc_step_chain'}
