@@ -45,7 +45,11 @@ def timed(pts, k, r, path, reps=3):
 
 cases = []
 for a in sys.argv[1:] or ['16']:
-    cases.append(('corridor %s scans k=32 r=0.4' % a, world('corridor', int(a)), 32, 0.4))
+    if ',' in a:          # scans,k,r
+        sc, kk, rr = a.split(',')
+        cases.append(('corridor %s scans k=%s r=%s' % (sc, kk, rr), world('corridor', int(sc)), int(kk), float(rr) if float(rr) > 0 else None))
+    else:
+        cases.append(('corridor %s scans k=32 r=0.4' % a, world('corridor', int(a)), 32, 0.4))
 cases.append(('corridor 8 scans k=16', world('corridor', 8), 16, None))
 cases.append(('corridor 8 scans k=64 r=0.5', world('corridor', 8), 64, 0.5))
 cases.append(('street 8 HDL-64 scans k=32 r=0.4', world('street', 8, pattern='hdl-64', depth_clip=(5.0, 80.0)), 32, 0.4))
@@ -64,8 +68,8 @@ for name, pts, k, r in cases:
     gr, mr, nfb = timed(pts, k, r, 'record')
     same = bool(torch.equal(a, gr.ell_idx))
     ok &= same
-    print('%-36s n=%9d  dc_knn %.3f ms  dc_knn_recorded %.3f ms (%.2fx)  fallback %d (%.3f %%)  identical lists: %s' % (
-        name, len(pts), mt, mr, mt / mr, nfb, 100.0 * nfb / len(pts), same))
+    print('%-36s n=%9d cell %.4f  dc_knn %.3f ms  dc_knn_recorded %.3f ms (%.2fx)  fallback %d (%.3f %%)  identical lists: %s' % (
+        name, len(pts), gr.map.cell, mt, mr, mt / mr, nfb, 100.0 * nfb / len(pts), same))
     del gr, a
 print('OK' if ok else 'MISMATCH')
 sys.exit(0 if ok else 1)

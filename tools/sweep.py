@@ -38,7 +38,7 @@ def main():
              '', 'CUDA-event times, best of 3; step = `dc_step_points` + `dc_step_forward_scatter` (or the two-kernel forms below 2^19 points) + chain on a reused graph '
              '(ScaledPolynomial[2,4], min_eigval_loss(normalization), per-scan pose corrections); roofline fraction = '
              '(206 + 8K) B/point (SURVEY.md section 8(d)) / step time / %.1f GB/s.' % peak, '',
-             '| points | k | r [m] | mean valid neighbours | search ms | search Mpts/s | step ms | step Mpts/s | step frac of HBM roofline |', '|---|---|---|---|---|---|---|---|---|']
+             '| points | k | r [m] | mean valid neighbours | cell [m] | search ms | of which kNN kernel | search Mpts/s | step ms | step Mpts/s | step frac of HBM roofline |', '|---|---|---|---|---|---|---|---|---|---|---|']
     for n_scans in (8, 77, 763):
         if n_scans > max_scans:
             continue
@@ -63,6 +63,11 @@ def main():
                 cfg = dc.Config(nn_k=k, nn_r=r, pose_correction=dc.PoseCorrection.pose)
                 ms_search, ns = timed(lambda: dc.establish_neighborhoods(clouds=clouds, poses=poses, cfg=cfg))
                 deg = ns.graph.degrees().double().mean().item()
+                L.profile = {}
+                ns = dc.establish_neighborhoods(clouds=clouds, poses=poses, cfg=cfg)
+                torch.cuda.synchronize()
+                ms_knn = sum(v['ms_total'] for kk, v in L.collect_profile().items() if kk.startswith('dc_knn'))
+                L.profile = None
 
                 def step():
                     model.zero_grad(set_to_none=True)
@@ -75,8 +80,8 @@ def main():
                 step()
                 ms_step, _ = timed(step, reps=4)
                 frac = (206 + 8 * k) * n / (ms_step * 1e-3) / 1e9 / peak
-                lines.append('| %d | %d | %.1f | %.1f | %.2f | %.0f | %.2f | %.0f | %.3f |'
-                             % (n, k, r, deg, ms_search, n / ms_search / 1e3, ms_step, n / ms_step / 1e3, frac))
+                lines.append('| %d | %d | %.1f | %.1f | %.4f | %.2f | %.2f | %.0f | %.2f | %.0f | %.3f |'
+                             % (n, k, r, deg, ns.graph.map.cell, ms_search, ms_knn, n / ms_search / 1e3, ms_step, n / ms_step / 1e3, frac))
                 print(lines[-1], flush=True)
                 del ns
                 L.release_workspace()
