@@ -919,6 +919,9 @@ knn_record_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
   int cnt = 0;
   bool fallback = false;
   if (q < nq) {
+#ifdef DC_KNN_STATS
+    const long long stats_t0 = clock64();
+#endif
     unsigned short* h = &hist[0][threadIdx.x];
     const dc_point pq = dc_ld_point(Q + q);
     int c0, c1, c2;
@@ -1112,6 +1115,8 @@ knn_record_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
 #ifdef DC_KNN_STATS
     atomicAdd(counters + 2 + (rho < 9 ? rho : 9), 1);          // final ring of the query (tools/knn_ring_stats.py)
     atomicAdd((unsigned long long*)(counters + 14), (unsigned long long)n_words);
+    // thread cycles by final ring, in the last 128 bytes of the (otherwise unused) fallback list
+    atomicAdd((unsigned long long*)(fb_list + nq) - 16 + (rho < 9 ? rho : 9), (unsigned long long)(clock64() - stats_t0));
 #endif
   }
   if (!fallback)
@@ -1148,6 +1153,9 @@ extern "C" int dc_knn_recorded(const void* P, const uint64_t* pkeys, int64_t n, 
   int32_t* counters = (int32_t*)temp;
   int2* fb = (int2*)((char*)temp + 64);
   knn_record_init_kernel<<<1, 32, 0, st>>>(counters);
+#ifdef DC_KNN_STATS
+  DC_CUDA_CHECK(cudaMemsetAsync((char*)(fb + nq) - 128, 0, 128, st));
+#endif
   DC_LAUNCH_CHECK();
   const int64_t n_slices = (nq + DC_SLICE - 1) / DC_SLICE;
   const int blocks = dc_blocks(n_slices * DC_SLICE, KNN_THREADS);

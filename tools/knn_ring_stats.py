@@ -20,3 +20,5 @@ n = len(wp)
 print('n %d cell %.4f max_ring %d' % (n, g.map.cell, -(-NN_R // g.map.cell)))
 print('final ring histogram (1..8, 9+):', [round(int(c[2 + r]) / n, 4) for r in range(1, 10)])
 print('mean words / query: %.1f' % (int(ws[56:64].view(torch.int64)) / n))
+cyc = ws[64 + 8 * n - 128:64 + 8 * n].view(torch.int64).cpu().double()
+print('share of the thread cycles by final ring (1..8, 9+):', [round(float(cyc[r] / cyc.sum()), 4) for r in range(1, 10)])
