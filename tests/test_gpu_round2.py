@@ -293,3 +293,24 @@ def test_captured_iteration_follows_the_eager_loop(dc, dev, kw):
     assert rel_err_norm(model_c.w.detach().cpu(), model_e.w.detach().cpu()) < 1e-8
     assert rel_err_norm(deltas_c.detach().cpu(), deltas_e.detach().cpu()) < 1e-8
     assert step.replays == 6
+
+
+def test_radius_lists_longer_than_the_staging_tile_vs_ckdtree(dc, dev):
+    """Radius mode on a dense map (lists of several hundred entries, lanes of a warp with very different counts): the fill
+    pass stages 64 rows per lane in shared memory and flushes row by row (dc_nn.cu radius_fill_kernel); every flush
+    boundary has to land in the right row.  Reference layout against cKDTree.query_ball_point (nearest_neighbors.py:50-73)."""
+    from oracle import oracle
+    scans, poses = _street_points(2)
+    pts = np.concatenate([s['points'].astype(np.float64) @ T[:3, :3].T + T[:3, 3] for s, T in zip(scans, poses)]).astype(np.float32)
+    rng = np.random.default_rng(0)
+    pts = pts[rng.permutation(len(pts))[:60000]]
+    p = torch.as_tensor(pts, device=dev)
+    _, idx = dc.nearest_neighbors(p, p, r=0.6)
+    _, ref = oracle.nearest_neighbors(torch.as_tensor(pts.astype(np.float64)), r=0.6)
+    assert ref.shape[1] > 200                         # several flushes per slice
+    assert torch.equal(idx.cpu(), ref)
+    # cross query with a ragged last slice
+    q = torch.as_tensor(pts[:1000 + 13] + np.float32(0.01), device=dev)
+    _, idx = dc.nearest_neighbors(p, q, r=0.5)
+    _, ref = oracle.nearest_neighbors(torch.as_tensor(pts.astype(np.float64)), torch.as_tensor((pts[:1013] + np.float32(0.01)).astype(np.float64)), r=0.5)
+    assert torch.equal(idx.cpu(), ref)
