@@ -70,11 +70,15 @@ def test_step_matches_reference_golden(golden, tag):
     for sc in inp['scans']:
         sc.pop('points32')
     out = oracle.map_consistency_step(**inp)
-    assert rel_err(out['loss'], g['loss']) < 1e-12
-    assert rel_err_norm(out['per_point'], g['per_point']) < 1e-12
+    # sqrt of the smallest eigenvalue: LAPACK's eigenvalues carry an absolute error of eps * |C| that depends on the
+    # host's BLAS code path (the goldens were written on another CPU); on rank-deficient neighbourhoods lambda_0 IS that
+    # noise and sqrt turns 1e-18 into 1e-9 for the handful of points concerned
+    sqrt_loss = 'sqrt' in tag
+    assert rel_err(out['loss'], g['loss']) < (1e-9 if sqrt_loss else 1e-12)
+    assert rel_err_norm(out['per_point'], g['per_point']) < (1e-6 if sqrt_loss else 1e-12)
     assert rel_err_norm(out['eigvals'], g['eigvals']) < 1e-12
     assert rel_err_norm(out['w_grad'], g['w_grad']) < 1e-9
-    assert rel_err_norm(out['poses_grad'], g['poses_grad']) < 1e-9
+    assert rel_err_norm(out['poses_grad'], g['poses_grad']) < (1e-7 if sqrt_loss else 1e-9)
     if inp['pose_deltas'] is not None:
         assert rel_err_norm(out['pose_deltas_grad'], g['pose_deltas_grad']) < 1e-9
 
