@@ -73,8 +73,9 @@ __device__ __forceinline__ void dc_row_range_nb(const dc_grid& g, const int32_t*
   c0lo = c0lo < 0 ? 0 : c0lo;
   c0hi = c0hi >= g.d[0] ? g.d[0] - 1 : c0hi;
   const bool ok = c1 >= 0 && c1 < g.d[1] && c2 >= 0 && c2 < g.d[2] && c0lo <= c0hi;
-  const uint64_t base = ((uint64_t)c2 * (uint64_t)g.d[1] + (uint64_t)c1) * (uint64_t)g.d[0];
-  const uint64_t k0 = ok ? base + (uint64_t)c0lo : 0, k1 = ok ? base + (uint64_t)c0hi + 1 : 0;
+  // a dense cell table exists for at most 2^30 cells (graph.py: DENSE_TABLE_MAX_CELLS): 32-bit index arithmetic
+  const unsigned int base = ((unsigned int)c2 * (unsigned int)g.d[1] + (unsigned int)c1) * (unsigned int)g.d[0];
+  const unsigned int k0 = ok ? base + (unsigned int)c0lo : 0u, k1 = ok ? base + (unsigned int)c0hi + 1u : 0u;
   lo = __ldg(cell_start + k0);
   hi = __ldg(cell_start + k1);
 }

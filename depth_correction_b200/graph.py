@@ -17,6 +17,10 @@ from . import _lib as L
 __all__ = ['SortedMap', 'Graph', 'search']
 
 KNN_OCC_DEFAULT = '0.3'                # mean points per occupied cell / k the kNN cell size aims at
+KNN_SAMPLE = 8192                     # queries searched to model the cost of the kNN kernel against the cell size
+KNN_ROW_COST = 3.0                    # overhead of one row of cells, in candidates (fitted: tools/knn_cell_sweep.py)
+KNN_MODEL_MIN_POINTS = 1 << 17        # smaller maps are launch bound: the occupancy estimate is good enough
+KNN_PAD = 3                           # readable records dc_knn_recorded expects behind the n records of the map
 DENSE_TABLE_MAX_CELLS = 1 << 30      # 4 GB of int32 cell starts at most (a 100 M point, 760 m corridor needs 3e8 cells)
 
 
@@ -128,7 +132,11 @@ class SortedMap(object):
         ids = L.scratch('ids', n, torch.int32, dev)
         self.keys = torch.empty(n, dtype=torch.int64, device=dev)
         self.order = torch.empty(n, dtype=torch.int32, device=dev)
-        self.P = torch.empty((n, 4), dtype=torch.float64, device=dev)
+        # KNN_PAD records behind the map: the first pass of dc_knn_recorded reads four consecutive records per step without
+        # clamping the last ones to the end of the row (include/dc_b200.h); their content is never used
+        buf = torch.empty((n + KNN_PAD, 4), dtype=torch.float64, device=dev)
+        buf[n:].zero_()
+        self.P = buf[:n]
         if n > 0:
             if self.stack is None:
                 L.call('dc_cell_keys', L.ptr(points), code, n, ctypes.byref(self.spec), L.ptr(keys), L.ptr(ids), st)
@@ -351,8 +359,82 @@ def _knn_cell_size(points, k, r, bounds, use_hint=True):
         if r and c0 > r:
             c0 = float(r) * (1.0 + 1e-6)      # a hair above r: one ring always covers r
             break
+    if points.shape[0] >= KNN_MODEL_MIN_POINTS and os.environ.get('DC_KNN_CELL', 'model') == 'model':
+        c0 = _knn_cell_from_sample(points, int(k), r, bounds, c0)
     _cell_hint[hint_key] = (points.shape[0], c0, occ_env, ext)
     return c0
+
+
+def _ring_sequence(max_ring):
+    """Rings the kNN kernels try in turn (dc_knn.cu: 1, 2, 3, 4, 8, 16, ... capped at max_ring)."""
+    seq, rho = [], 1
+    while True:
+        seq.append(min(rho, max_ring))
+        if rho >= max_ring:
+            return seq
+        rho = rho + 1 if rho < 4 else rho * 2
+
+
+def _knn_cell_from_sample(points, k, r, bounds, c0):
+    """Cell edge that minimises a cost model of the kNN kernel on a SAMPLE of the map's own queries.
+
+    The mean occupancy the first estimate aims at says little about a map whose density varies by orders of magnitude
+    (lidar: ~1 / range^2): the best cell of the 64-scan corridor holds d_k (the distance of the k-th neighbour) of 75 %
+    of the queries, the best cell of a street map of HDL-64 scans only 50 % (tools/knn_cell_sweep.py).  So KNN_SAMPLE
+    random points are searched exactly (cell c0), which gives each one's d_k and, through it, the surface density
+    sigma = k / (pi d_k^2) around it; a query then costs, for every ring rho the kernel has to try,
+    (2 rho + 1)^2 rows of sigma c^2 candidates + KNN_ROW_COST candidates' worth of row overhead, and it is finished by
+    the first ring with d_k < rho c + c / 8 (mean distance to the nearest face of its cell).  The cell minimising the
+    mean cost over candidate sizes c0 / 2.5 ... 2 c0 is returned (c0 itself when it is within 5 % of the optimum)."""
+    n = points.shape[0]
+    dev = points.device
+    sample = points[torch.randint(0, n, (KNN_SAMPLE,), device=dev, generator=_sample_generator(dev))]
+    g = search(points, sample, k=k, r=r, cell=c0)
+    d = g.distances()                                     # fp64 [m, k], inf = fewer than k within r
+    del g
+    fin = torch.isfinite(d)
+    n_valid = fin.sum(dim=1).clamp_(min=1).double()
+    dk = d[:, -1]
+    have_k = fin[:, -1]
+    if float(have_k.double().mean().item()) < 0.1:
+        return c0                                          # hardly any query has k neighbours within r: nothing to model
+    far = torch.where(fin, d, torch.zeros_like(d)).amax(dim=1)
+    rad = torch.where(have_k, dk, torch.full_like(dk, float(r)) if r else far).clamp_(min=1e-12)
+    sigma = n_valid / (math.pi * rad * rad)               # points per unit area of the surface around the query
+    cells = c0 * torch.pow(2.0, torch.arange(-8, 7, dtype=torch.float64, device=dev) / 6.0)
+    if r:
+        cells = cells[cells <= float(r) * (1.0 + 1e-6)]
+    if cells.numel() == 0:
+        return c0
+    cost = torch.zeros((d.shape[0], cells.numel()), dtype=torch.float64, device=dev)
+    done = torch.zeros_like(cost, dtype=torch.bool)
+    unit = sigma[:, None] * (cells * cells)[None, :] + KNN_ROW_COST
+    max_ring = (torch.ceil(float(r) / cells) if r else torch.full_like(cells, 64.0))[None, :]
+    for rho in _ring_sequence(64):
+        rho_c = torch.clamp(torch.full_like(max_ring, float(rho)), max=max_ring)      # the kernel caps the ring at r / cell
+        last = rho_c >= max_ring
+        cost += torch.where(done, torch.zeros_like(cost), (2.0 * rho_c + 1.0) ** 2 * unit)
+        done |= (dk[:, None] < rho_c * cells[None, :] + 0.125 * cells[None, :]) | last
+        if bool(done.all()):
+            break
+    mean = cost.mean(dim=0)
+    best = int(torch.argmin(mean).item())
+    i0 = int(torch.argmin((cells - c0).abs()).item())
+    if float(mean[i0]) <= 1.05 * float(mean[best]):
+        return c0
+    return float(cells[best].item())
+
+
+_sample_generators = {}
+
+
+def _sample_generator(dev):
+    """Own seeded generator for the query sample: the cell size (speed only) does not consume the global RNG stream."""
+    key = str(dev)
+    if key not in _sample_generators:
+        _sample_generators[key] = torch.Generator(device=dev)
+    _sample_generators[key].manual_seed(12345)
+    return _sample_generators[key]
 
 
 def clear_cell_hints():

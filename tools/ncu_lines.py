@@ -46,7 +46,10 @@ def line_table(kernel):
 def main():
     rep, kernel = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '-k', 'regex:' + kernel], capture_output=True, text=True).stdout
+    # KERNEL_SUBSTR may be a mangled name (to pick one template instance in the cubin); ncu filters on the plain name
+    plain = re.sub(r'^_Z\d+', '', kernel)
+    plain = re.sub(r'I[A-Z].*$', '', plain)
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '-k', 'regex:' + plain], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
     hdr = rows[hdr_i]
