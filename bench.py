@@ -667,15 +667,18 @@ def run_ours(args):
                   'pose_grad_rel_err_vs_fp64_gather': rel(gd_fast, main_job.deltas.grad)}
     alg, idx_fwd, idx_bwd = algorithmic_bytes(main_job, ns)
     ns.graph._transposed = None          # (release the reverse lists again)
-    # ---- a cold search: no remembered cell size (the timed searches reuse the estimate of the first one)
-    clear_cell_hints()
-    main_job.sync()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record()
-    dc.establish_neighborhoods(clouds=main_job.clouds, poses=main_job.poses if main_job.local is None
-                               else main_job.poses[main_job.local.scan_ids], cfg=main_job.cfg)
-    c1.record()
-    main_job.sync()
+    # ---- a cold search: no remembered cell size (the timed searches reuse the estimate of the first one).  The second
+    # of two cold searches is the one reported: the first also pays the one-time module loads of the torch ops the
+    # estimate uses
+    for _ in range(2):
+        clear_cell_hints()
+        main_job.sync()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        dc.establish_neighborhoods(clouds=main_job.clouds, poses=main_job.poses if main_job.local is None
+                                   else main_job.poses[main_job.local.scan_ids], cfg=main_job.cfg)
+        c1.record()
+        main_job.sync()
     cold_search_ms = main_job.allmax([c0.elapsed_time(c1)])[0]
     e2e_s, h2d, d2h = main_job.e2e(args.steps)
     e2e_loss = main_job.e2e_loss

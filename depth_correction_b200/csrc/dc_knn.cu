@@ -919,11 +919,62 @@ __device__ __forceinline__ unsigned int knn_word(const dc_point* __restrict__ P,
   return w;
 }
 
+// How the first pass is kept lean (every step timed on the 8.37 M point bench map, profiles/r2_knn_experiments.md):
+//  * histogram columns at byte offset 4 lane + 2 warp: the 32 lanes of a warp sit in 32 different banks whatever their
+//    bins (a column at 2 tid puts two lanes into every bank: a 2-way conflict on every counter access);
+//  * no branch around the histogram update: the counter of the candidate's bin is read, incremented and stored under a
+//    predicate, the record byte is selected (`if (inside) {...}` around a shared-memory read-modify-write compiles to
+//    BSSY / BRA / BSYNC per candidate, with a third of the lanes inside on lidar maps).  Counters wrap instead of
+//    saturating: a query with more than 65535 candidates inside the bound goes to the list knn_thread_list_kernel
+//    finishes;
+//  * the four candidates of a step are read at pj, pj + 1, pj + 2, pj + 3 without clamping the last ones to the end of
+//    the row (one address computation): the caller provides KNN_PAD = 3 readable records behind the map, and slots
+//    past the end of the row are masked;
+//  * x, y, z are loaded without the tag (a 128-bit and a 64-bit load: six registers per candidate instead of the
+//    eight a 256-bit load pins), which lets all four loads of a step be in flight inside the 64-register budget;
+//  * the radius a block of rho rings is guaranteed to cover is measured from the QUERY (knn_face), so fewer queries
+//    need a second ring;
+//  * the emit pass stores with predicates and only collects the positions of the (<= 8) candidates of the boundary bin;
+//    their distances and tags are read afterwards, eight independent loads with the warp converged.
+// ---------------------------------------------------------------------------------------------
+
+// sub-bin (second histogram level) of candidate j of bin b1: out of line, rare
+__device__ __noinline__ int knn_sub_bin(const dc_point* __restrict__ P, int j, double qx, double qy, double qz, double scale1, int b1) {
+  const dc_point pj = dc_ld_point(P + j);
+  dc_point pq;
+  pq.x = qx; pq.y = qy; pq.z = qz; pq.tag = 0;
+  const double d2 = dc_dist2(pj, pq);
+  int bb = __double2int_rz((d2 * scale1 - (double)b1) * (double)KNN_BINS);
+  return bb < 0 ? 0 : (bb > KNN_BINS - 1 ? KNN_BINS - 1 : bb);
+}
+
+// x, y, z of a record without its tag
+__device__ __forceinline__ dc_point knn_ld_xyz(const dc_point* p) {
+  dc_point r;
+  asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  asm("ld.global.nc.f64 %0, [%1+16];" : "=d"(r.z) : "l"(p));
+  r.tag = 0;
+  return r;
+}
+
+// 16-bit shared-memory accesses at a 32-bit shared address (the kernel below keeps ONE opaque register with the address
+// of the thread's histogram column: a generic pointer to it was re-derived -- S2R, S2UR, ULEA, ... -- at every use)
+__device__ __forceinline__ unsigned int knn_lds16(unsigned int a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void knn_sts16(unsigned int a, unsigned int v) {
+  asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((unsigned short)v) : "memory");
+}
+#define KNN_COL (KNN_THREADS * 2u)      // bytes between two counters of a histogram column
+
 __global__ void __launch_bounds__(KNN_THREADS, KNN_BLOCKS)
 knn_record_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
                   const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
                   const int32_t* __restrict__ cell_start, int k, double r2cap, int max_ring,
                   int2* __restrict__ fb_list, int32_t* __restrict__ counters, int32_t* __restrict__ ell_idx) {
+  static_assert(KNN_THREADS == 64, "the interleaved histogram columns are laid out for two warps per block");
   __shared__ unsigned short hist[KNN_BINS][KNN_THREADS];
   unsigned int rec[KR_WORDS];
   const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -936,11 +987,14 @@ knn_record_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
 #ifdef DC_KNN_STATS
     const long long stats_t0 = clock64();
 #endif
-    unsigned short* h = &hist[0][threadIdx.x];
+    // shared address of this thread's histogram column (counter b at hs + b * KNN_COL)
+    unsigned int hs = (unsigned int)__cvta_generic_to_shared(&hist[0][2 * lane + (threadIdx.x >> 5)]);
+    asm volatile("" : "+r"(hs));      // opaque: kept in a register instead of being recomputed (8 instructions) in every step
     const dc_point pq = dc_ld_point(Q + q);
     int c0, c1, c2;
     dc_key_coords(g, qkeys[q], c0, c1, c2);
     const double slack_cell = g.cell * (1.0 - 1e-9);
+    const double face = knn_face(g, pq, c0, c1, c2);
     // ---- 1. ring growth + level-1 histogram + record
     int rho = 1;
     double bound2, scale1;
@@ -949,40 +1003,42 @@ knn_record_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
     for (;;) {
       if (rho > max_ring) rho = max_ring;
       const bool last = rho >= max_ring;
-      const double reach = rho * slack_cell;
+      const double reach = rho * slack_cell + face;
       bound2 = last ? r2cap : fmin(reach * reach, r2cap);
       scale1 = (double)KNN_BINS / bound2;
 #pragma unroll
-      for (int b = 0; b < KNN_BINS; ++b) h[b * KNN_THREADS] = (unsigned short)0;
-      n_in = 0u;
+      for (int b = 0; b < KNN_BINS; ++b) knn_sts16(hs + b * KNN_COL, 0u);
       n_words = 0;
+      unsigned int n_out = 0u;
       knn_rows(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int j, int hi) {
-        const int lastj = hi - 1;
-        const int j1 = j + 1 < lastj ? j + 1 : lastj, j2 = j + 2 < lastj ? j + 2 : lastj, j3 = j + 3 < lastj ? j + 3 : lastj;
-        const dc_point p0 = dc_ld_point(P + j), p1 = dc_ld_point(P + j1);
-        const dc_point p2 = dc_ld_point(P + j2), p3 = dc_ld_point(P + j3);
+        const dc_point* pj = P + j;
+        const dc_point p0 = knn_ld_xyz(pj), p1 = knn_ld_xyz(pj + 1), p2 = knn_ld_xyz(pj + 2), p3 = knn_ld_xyz(pj + 3);
         const double d0 = dc_dist2(p0, pq), d1 = dc_dist2(p1, pq), d2 = dc_dist2(p2, pq), d3 = dc_dist2(p3, pq);
-        unsigned int w = 0xffffffffu;
-        auto visit = [&](double dd, int slot) {
-          if (dd < bound2) {
-            const int b = knn_bin(dd, scale1);
-            const unsigned short v = h[b * KNN_THREADS];
-            h[b * KNN_THREADS] = v == 65535 ? v : (unsigned short)(v + 1);
-            ++n_in;
-            w ^= (unsigned int)(b ^ 255) << (8 * slot);
-          }
+        unsigned int w = 0u;
+        auto visit = [&](double dd, bool valid, unsigned int sel) {
+          const bool in = valid && dd < bound2;
+          const int b = knn_bin(dd, scale1);
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t.reg .b16 v;\n\tsetp.ne.s32 p, %1, 0;\n\tld.shared.u16 v, [%0];\n\t"
+              "add.u16 v, v, 1;\n\t@p st.shared.u16 [%0], v;\n\t}"
+              :: "r"(hs + (unsigned int)b * KNN_COL), "r"((int)in) : "memory");
+          w = __byte_perm(w, (unsigned int)(in ? b : 255), sel);
         };
-        visit(d0, 0);
-        if (j + 1 < hi) visit(d1, 1);
-        if (j + 2 < hi) visit(d2, 2);
-        if (j + 3 < hi) visit(d3, 3);
+        visit(d0, true, 0x3214u);
+        visit(d1, j + 1 < hi, 0x3240u);
+        visit(d2, j + 2 < hi, 0x3410u);
+        visit(d3, j + 3 < hi, 0x4210u);
+        n_out += (unsigned int)__popc(w & 0x80808080u);      // bit 7 of a record byte = outside the bound / past the row
         if (n_words < KR_WORDS) rec[n_words] = w;
         ++n_words;
       });
+      n_in = 4u * (unsigned int)n_words - n_out;
       if (n_in >= (unsigned int)k || last) break;
       rho = rho < 4 ? rho + 1 : rho * 2;
     }
-    if (n_in <= (unsigned int)k) {
+    if (n_in > 65535u) {
+      fallback = true;                       // a 16-bit counter may have wrapped
+    } else if (n_in <= (unsigned int)k) {
       // everything inside the bound is a neighbour (fewer than k exist within r / in the map)
       int it = 0;
       knn_rows(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int j, int hi) {
@@ -995,12 +1051,20 @@ knn_record_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
       });
     } else {
       // ---- level 1: bin of the k-th distance
+      // (four counters per step: one dependent shared-memory load per bin was 3 % of the kernel; n_in > k, so the
+      // scan always ends inside the histogram)
       unsigned int c_lo = 0u, cnt1 = 0u;
       int b1 = 0;
-      for (; b1 < KNN_BINS; ++b1) {
-        cnt1 = h[b1 * KNN_THREADS];
-        if (c_lo + cnt1 >= (unsigned int)k) break;
-        c_lo += cnt1;
+      for (; b1 < KNN_BINS; b1 += 4) {
+        const unsigned int v0 = knn_lds16(hs + b1 * KNN_COL), v1 = knn_lds16(hs + (b1 + 1) * KNN_COL),
+                           v2 = knn_lds16(hs + (b1 + 2) * KNN_COL), v3 = knn_lds16(hs + (b1 + 3) * KNN_COL);
+        const unsigned int s1 = c_lo + v0, s2 = s1 + v1, s3 = s2 + v2, s4 = s3 + v3;
+        if (s4 < (unsigned int)k) { c_lo = s4; continue; }
+        if (s1 >= (unsigned int)k) { cnt1 = v0; }
+        else if (s2 >= (unsigned int)k) { c_lo = s1; cnt1 = v1; b1 += 1; }
+        else if (s3 >= (unsigned int)k) { c_lo = s2; cnt1 = v2; b1 += 2; }
+        else { c_lo = s3; cnt1 = v3; b1 += 3; }
+        break;
       }
       int b2 = KNN_BINS;
       unsigned int cnt2 = cnt1;
@@ -1008,24 +1072,22 @@ knn_record_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
       if (lvl2) {
         // ---- 2. level-2 histogram over the recorded candidates of bin b1
 #pragma unroll
-        for (int b = 0; b < KNN_BINS; ++b) h[b * KNN_THREADS] = (unsigned short)0;
+        for (int b = 0; b < KNN_BINS; ++b) knn_sts16(hs + b * KNN_COL, 0u);
         int it = 0;
         knn_rows(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int j, int hi) {
           const unsigned int w = it < KR_WORDS ? rec[it] : knn_word(P, pq, j, hi, bound2, scale1);
-        ++it;
+          ++it;
           if (w == 0xffffffffu) return;
 #pragma unroll
           for (int s_ = 0; s_ < 4; ++s_) {
             if ((int)((w >> (8 * s_)) & 255u) != b1) continue;
-            const double s = dc_dist2(dc_ld_point(P + j + s_), pq) * scale1;
-            int bb = __double2int_rz((s - (double)b1) * (double)KNN_BINS);
-            bb = bb < 0 ? 0 : (bb > KNN_BINS - 1 ? KNN_BINS - 1 : bb);
-            const unsigned short v = h[bb * KNN_THREADS];
-            h[bb * KNN_THREADS] = v == 65535 ? v : (unsigned short)(v + 1);
+            const int bb = knn_sub_bin(P, j + s_, pq.x, pq.y, pq.z, scale1, b1);
+            const unsigned int v = knn_lds16(hs + bb * KNN_COL);
+            knn_sts16(hs + bb * KNN_COL, v == 65535u ? v : v + 1u);
           }
         });
         for (b2 = 0; b2 < KNN_BINS; ++b2) {
-          cnt2 = h[b2 * KNN_THREADS];
+          cnt2 = knn_lds16(hs + b2 * KNN_COL);
           if (c_lo + cnt2 >= (unsigned int)k) break;
           c_lo += cnt2;
         }
@@ -1035,11 +1097,16 @@ knn_record_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
       if (!take_all && cnt2 > 8u) {
         fallback = true;                     // more than 8 candidates tied in the boundary sub-bin: repeated selection, rare
       } else {
-        // ---- 3. emit from the record
+        // ---- 3. emit from the record.  Bins below `thr` are neighbours outright; candidates of bin b1 that need a
+        // second look (sub-bin under the second level, rank among the boundary candidates) only leave their position
+        // in the thread's dead histogram column (two counters per entry)
+        const bool plain_b1 = take_all && !lvl2;
+        int thr = plain_b1 ? b1 + 1 : b1;
+        asm volatile("" : "+r"(thr));        // opaque: one register instead of a select at every use
         int nb = 0;
         int it = 0;
         // four words of the record per step, loaded together: the record comes back from L2 (480 KB per SM do not
-        // stay in L1) and one dependent load per word left the pass waiting on it for 12 % of the kernel
+        // stay in L1) and one dependent load per word left the pass waiting on it
         knn_rows16(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int jg, int hi) {
           const int left = hi - jg;
           const int nw = left >= 16 ? 4 : (left + 3) >> 2;
@@ -1054,63 +1121,65 @@ knn_record_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
           }
           it += nw;
           for (int i = 0; i < nw; ++i) {
-          const unsigned int w = i == 0 ? w0 : (i == 1 ? w1 : (i == 2 ? w2 : w3));
-          if (w == 0xffffffffu) continue;
-          const int j0 = jg + 4 * i;
-#pragma unroll
-          for (int s_ = 0; s_ < 4; ++s_) {
-            const int b = (int)((w >> (8 * s_)) & 255u);
-            const int j = j0 + s_;
-            if (b < b1) {
-              out_j[(int64_t)(cnt++) * DC_SLICE] = j;
-            } else if (b == b1) {
-              if (take_all && !lvl2) {
-                out_j[(int64_t)(cnt++) * DC_SLICE] = j;
-              } else {
-                const dc_point pj = dc_ld_point(P + j);
-                const double d2 = dc_dist2(pj, pq);
-                bool boundary = true;
-                if (lvl2) {
-                  int bb = __double2int_rz((d2 * scale1 - (double)b1) * (double)KNN_BINS);
-                  bb = bb < 0 ? 0 : (bb > KNN_BINS - 1 ? KNN_BINS - 1 : bb);
-                  if (bb < b2) out_j[(int64_t)(cnt++) * DC_SLICE] = j;
-                  boundary = (bb == b2);
-                }
-                if (boundary) {
-                  if (take_all) {
+            const unsigned int w = i == 0 ? w0 : (i == 1 ? w1 : (i == 2 ? w2 : w3));
+            if (w == 0xffffffffu) continue;
+            const int j0 = jg + 4 * i;
+            const int e0 = (int)(w & 255u), e1 = (int)((w >> 8) & 255u), e2 = (int)((w >> 16) & 255u), e3 = (int)(w >> 24);
+            const bool has_b1 = !plain_b1 && (e0 == b1 || e1 == b1 || e2 == b1 || e3 == b1);
+            if (lvl2 && has_b1) {
+              // second level (rare): slot by slot, so that the row keeps the order of the walk
+#pragma unroll 1
+              for (int s_ = 0; s_ < 4; ++s_) {
+                const int b = (int)((w >> (8 * s_)) & 255u);
+                const int j = j0 + s_;
+                if (b < b1) {
+                  out_j[(int64_t)(cnt++) * DC_SLICE] = j;
+                } else if (b == b1) {
+                  const int bb = knn_sub_bin(P, j, pq.x, pq.y, pq.z, scale1, b1);
+                  if (bb < b2 || (bb == b2 && take_all)) {
                     out_j[(int64_t)(cnt++) * DC_SLICE] = j;
-                  } else if (nb < 8) {
-                    const int tag = (int)pj.tag;
-                    const unsigned long long u = (unsigned long long)__double_as_longlong(d2);
-                    unsigned short* e = h + 8 * nb * KNN_THREADS;
-                    e[0] = (unsigned short)u;
-                    e[KNN_THREADS] = (unsigned short)(u >> 16);
-                    e[2 * KNN_THREADS] = (unsigned short)(u >> 32);
-                    e[3 * KNN_THREADS] = (unsigned short)(u >> 48);
-                    e[4 * KNN_THREADS] = (unsigned short)j;
-                    e[5 * KNN_THREADS] = (unsigned short)((unsigned int)j >> 16);
-                    e[6 * KNN_THREADS] = (unsigned short)tag;
-                    e[7 * KNN_THREADS] = (unsigned short)((unsigned int)tag >> 16);
+                  } else if (bb == b2 && nb < 8) {
+                    knn_sts16(hs + 2 * nb * KNN_COL, (unsigned int)j);
+                    knn_sts16(hs + (2 * nb + 1) * KNN_COL, (unsigned int)j >> 16);
+                    ++nb;
+                  }
+                }
+              }
+            } else {
+              if (e0 < thr) out_j[(int64_t)cnt * DC_SLICE] = j0;
+              cnt += e0 < thr ? 1 : 0;
+              if (e1 < thr) out_j[(int64_t)cnt * DC_SLICE] = j0 + 1;
+              cnt += e1 < thr ? 1 : 0;
+              if (e2 < thr) out_j[(int64_t)cnt * DC_SLICE] = j0 + 2;
+              cnt += e2 < thr ? 1 : 0;
+              if (e3 < thr) out_j[(int64_t)cnt * DC_SLICE] = j0 + 3;
+              cnt += e3 < thr ? 1 : 0;
+              if (has_b1) {
+                // the (<= 8) candidates of the boundary bin: positions only, ranked after the walk
+#pragma unroll
+                for (int s_ = 0; s_ < 4; ++s_) {
+                  if ((int)((w >> (8 * s_)) & 255u) == b1 && nb < 8) {
+                    knn_sts16(hs + 2 * nb * KNN_COL, (unsigned int)(j0 + s_));
+                    knn_sts16(hs + (2 * nb + 1) * KNN_COL, (unsigned int)(j0 + s_) >> 16);
                     ++nb;
                   }
                 }
               }
             }
           }
-          }
         });
         if (!take_all) {
+          // rank the boundary candidates by (d2, original index): eight independent loads, the warp converged
           double bd[8];
           int bj[8], bt[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const unsigned short* e = h + 8 * i * KNN_THREADS;
-            const unsigned long long u = (unsigned long long)e[0] | ((unsigned long long)e[KNN_THREADS] << 16) |
-                                         ((unsigned long long)e[2 * KNN_THREADS] << 32) | ((unsigned long long)e[3 * KNN_THREADS] << 48);
-            const int j = (int)((unsigned int)e[4 * KNN_THREADS] | ((unsigned int)e[5 * KNN_THREADS] << 16));
-            bd[i] = i < nb ? __longlong_as_double((long long)u) : INFINITY;
-            bj[i] = i < nb ? j : 0x7fffffff;
-            bt[i] = i < nb ? (int)((unsigned int)e[6 * KNN_THREADS] | ((unsigned int)e[7 * KNN_THREADS] << 16)) : 0x7fffffff;
+            const bool have = i < nb;
+            const int j = have ? (int)(knn_lds16(hs + 2 * i * KNN_COL) | (knn_lds16(hs + (2 * i + 1) * KNN_COL) << 16)) : 0;
+            const dc_point pj = dc_ld_point(P + j);
+            bd[i] = have ? dc_dist2(pj, pq) : INFINITY;
+            bj[i] = have ? j : 0x7fffffff;
+            bt[i] = have ? (int)pj.tag : 0x7fffffff;
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -1132,409 +1201,6 @@ knn_record_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ p
     // thread cycles by final ring, in the last 128 bytes of the (otherwise unused) fallback list
     atomicAdd((unsigned long long*)(fb_list + nq) - 16 + (rho < 9 ? rho : 9), (unsigned long long)(clock64() - stats_t0));
 #endif
-  }
-  if (!fallback)
-    for (int c = cnt; c < k; ++c) out_j[(int64_t)c * DC_SLICE] = -1;
-}
-
-// ---------------------------------------------------------------------------------------------
-// knn_record2_kernel: the recorded kernel, leaner per candidate.  Same lists as knn_record_kernel entry by entry (same
-// order inside a row).  What differs (template flags so that every step can be timed on its own):
-//  * histogram columns at byte offset 4 lane + 2 warp instead of 2 tid: the 32 lanes of a warp sit in 32 different
-//    banks whatever their bins (at 2 tid two lanes share every bank: a 2-way conflict on every counter access);
-//  * KR2_BRANCHFREE: the first pass updates the histogram without a branch -- the counter of the candidate's bin is
-//    rewritten with + (inside the bound ? 1 : 0), the record byte is selected -- instead of `if (inside) {...}` around
-//    a shared-memory read-modify-write, which ptxas compiles to BSSY / BRA / BSYNC per candidate with (on lidar maps)
-//    a third of the lanes inside.  Counters wrap instead of saturating; a query with more than 65535 candidates inside
-//    the bound (never on a sane cell size) is handed to the list knn_thread_list_kernel finishes;
-//  * KR2_MINFACE: the radius a block of rho rings is guaranteed to cover is measured from the QUERY, not from its
-//    cell: rho cells + the distance to the nearest face of the query's own cell (fewer queries need a second ring);
-//  * KR2_EMIT: the emit pass stores with predicates and only collects the positions of the (<= 8) candidates of the
-//    boundary bin; their distances and tags are read afterwards, eight independent loads with the warp converged,
-//    instead of one lane at a time inside the replay.
-// ---------------------------------------------------------------------------------------------
-#define KR2_BRANCHFREE 1
-#define KR2_MINFACE 2
-#define KR2_EMIT 4
-#define KR2_FASTLD 8
-#define KR2_PREFETCH 16
-#define KR2_XYZ 32
-#define KR2_PIPE 64
-#define KR2_DEFAULT (-1)
-
-// sub-bin (second histogram level) of candidate j of bin b1: out of line, rare
-__device__ __noinline__ int knn_sub_bin(const dc_point* __restrict__ P, int j, double qx, double qy, double qz, double scale1, int b1) {
-  const dc_point pj = dc_ld_point(P + j);
-  dc_point pq;
-  pq.x = qx; pq.y = qy; pq.z = qz; pq.tag = 0.0;
-  const double d2 = dc_dist2(pj, pq);
-  int bb = __double2int_rz((d2 * scale1 - (double)b1) * (double)KNN_BINS);
-  return bb < 0 ? 0 : (bb > KNN_BINS - 1 ? KNN_BINS - 1 : bb);
-}
-
-// x, y, z of a record without its tag: a 128-bit and a 64-bit load, six registers instead of the eight a 256-bit load
-// pins (the first pass keeps four candidates in flight inside a 64-register budget)
-__device__ __forceinline__ dc_point knn_ld_xyz(const dc_point* p) {
-  dc_point r;
-  asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
-  asm("ld.global.nc.f64 %0, [%1+16];" : "=d"(r.z) : "l"(p));
-  r.tag = 0;
-  return r;
-}
-
-template <int F>
-__global__ void __launch_bounds__(KNN_THREADS, KNN_BLOCKS)
-knn_record2_kernel(const dc_point* __restrict__ P, const uint64_t* __restrict__ pkeys, int64_t n,
-                   const dc_point* __restrict__ Q, const uint64_t* __restrict__ qkeys, int64_t nq, dc_grid g,
-                   const int32_t* __restrict__ cell_start, int k, double r2cap, int max_ring,
-                   int2* __restrict__ fb_list, int32_t* __restrict__ counters, int32_t* __restrict__ ell_idx) {
-  static_assert(KNN_THREADS == 64, "the interleaved histogram columns are laid out for two warps per block");
-  __shared__ unsigned short hist[KNN_BINS][KNN_THREADS];
-  unsigned int rec[KR_WORDS];
-  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  if (nq <= 0 || (q >> 5) > ((nq - 1) >> 5)) return;
-  int32_t* out_j = ell_idx + (q >> 5) * (int64_t)k * DC_SLICE + lane;
-  int cnt = 0;
-  bool fallback = false;
-  if (q < nq) {
-    unsigned short* h = &hist[0][2 * lane + (threadIdx.x >> 5)];
-    unsigned int hs = (unsigned int)__cvta_generic_to_shared(h);
-    asm volatile("" : "+r"(hs));      // opaque: kept in a register instead of being recomputed (8 instructions) in every iteration
-    const int n_map = (int)n;
-    const dc_point pq = dc_ld_point(Q + q);
-    int c0, c1, c2;
-    dc_key_coords(g, qkeys[q], c0, c1, c2);
-    const double slack_cell = g.cell * (1.0 - 1e-9);
-    double face = 0.0;
-    if (F & KR2_MINFACE) {
-      face = knn_face(g, pq, c0, c1, c2);
-    }
-    // ---- 1. ring growth + level-1 histogram + record
-    int rho = 1;
-    double bound2, scale1;
-    unsigned int n_in;
-    int n_words;
-    for (;;) {
-      if (rho > max_ring) rho = max_ring;
-      const bool last = rho >= max_ring;
-      const double reach = rho * slack_cell + face;
-      bound2 = last ? r2cap : fmin(reach * reach, r2cap);
-      scale1 = (double)KNN_BINS / bound2;
-#pragma unroll
-      for (int b = 0; b < KNN_BINS; ++b) h[b * KNN_THREADS] = (unsigned short)0;
-      n_in = 0u;
-      n_words = 0;
-      unsigned int n_out = 0u;
-      knn_rows(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int j, int hi) {
-        dc_point p0, p1, p2, p3;
-        if (F & KR2_FASTLD) {   // EXPERIMENT: assumes three readable records behind the map
-          // slots past the end of the row read the first candidates of the next row (they exist: j + 3 < n) and are
-          // masked below: one address computation, three immediate offsets
-          const dc_point* pj = P + j;
-          if (F & KR2_PREFETCH) {
-            if (j + 8 < hi) asm volatile("prefetch.global.L1 [%0];" :: "l"(pj + 8));
-          }
-          if (F & KR2_XYZ) {
-            p0 = knn_ld_xyz(pj); p1 = knn_ld_xyz(pj + 1); p2 = knn_ld_xyz(pj + 2); p3 = knn_ld_xyz(pj + 3);
-          } else {
-            p0 = dc_ld_point(pj); p1 = dc_ld_point(pj + 1); p2 = dc_ld_point(pj + 2); p3 = dc_ld_point(pj + 3);
-          }
-        } else {
-          const int lastj = hi - 1;
-          const int j1 = j + 1 < lastj ? j + 1 : lastj, j2 = j + 2 < lastj ? j + 2 : lastj, j3 = j + 3 < lastj ? j + 3 : lastj;
-          p0 = dc_ld_point(P + j); p1 = dc_ld_point(P + j1); p2 = dc_ld_point(P + j2); p3 = dc_ld_point(P + j3);
-        }
-        const double d0 = dc_dist2(p0, pq), d1 = dc_dist2(p1, pq), d2 = dc_dist2(p2, pq), d3 = dc_dist2(p3, pq);
-        unsigned int w;
-        if (F & KR2_BRANCHFREE) {
-          w = 0u;
-          auto visit = [&](double dd, bool valid, unsigned int sel) {
-            const bool in = valid && dd < bound2;
-            const int b = knn_bin(dd, scale1);
-            // counter of bin b: read, + 1, stored under the predicate (one instruction less than storing a selected value)
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t.reg .b16 v;\n\tsetp.ne.s32 p, %1, 0;\n\tld.shared.u16 v, [%0];\n\t"
-                "add.u16 v, v, 1;\n\t@p st.shared.u16 [%0], v;\n\t}"
-                :: "r"(hs + (unsigned int)b * (KNN_THREADS * 2u)), "r"((int)in) : "memory");
-            w = __byte_perm(w, (unsigned int)(in ? b : 255), sel);
-          };
-          visit(d0, true, 0x3214u);
-          visit(d1, j + 1 < hi, 0x3240u);
-          visit(d2, j + 2 < hi, 0x3410u);
-          visit(d3, j + 3 < hi, 0x4210u);
-          n_out += (unsigned int)__popc(w & 0x80808080u);      // bit 7 of a record byte = outside the bound
-        } else {
-          w = 0xffffffffu;
-          auto visit = [&](double dd, int slot) {
-            if (dd < bound2) {
-              const int b = knn_bin(dd, scale1);
-              const unsigned short v = h[b * KNN_THREADS];
-              h[b * KNN_THREADS] = (unsigned short)(v + 1);
-              ++n_in;
-              w ^= (unsigned int)(b ^ 255) << (8 * slot);
-            }
-          };
-          visit(d0, 0);
-          if (j + 1 < hi) visit(d1, 1);
-          if (j + 2 < hi) visit(d2, 2);
-          if (j + 3 < hi) visit(d3, 3);
-        }
-        if (n_words < KR_WORDS) rec[n_words] = w;
-        ++n_words;
-      });
-      if (F & KR2_BRANCHFREE) n_in = 4u * (unsigned int)n_words - n_out;
-      if (n_in >= (unsigned int)k || last) break;
-      rho = rho < 4 ? rho + 1 : rho * 2;
-    }
-    if (n_in > 65535u) {
-      fallback = true;                       // a 16-bit counter may have wrapped
-    } else if (n_in <= (unsigned int)k) {
-      // everything inside the bound is a neighbour (fewer than k exist within r / in the map)
-      int it = 0;
-      knn_rows(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int j, int hi) {
-        const unsigned int w = it < KR_WORDS ? rec[it] : knn_word(P, pq, j, hi, bound2, scale1);
-        ++it;
-        if (w == 0xffffffffu) return;
-#pragma unroll
-        for (int s_ = 0; s_ < 4; ++s_)
-          if (((w >> (8 * s_)) & 255u) != 255u) out_j[(int64_t)(cnt++) * DC_SLICE] = j + s_;
-      });
-    } else {
-      // ---- level 1: bin of the k-th distance
-      unsigned int c_lo = 0u, cnt1 = 0u;
-      int b1 = 0;
-      for (; b1 < KNN_BINS; ++b1) {
-        cnt1 = h[b1 * KNN_THREADS];
-        if (c_lo + cnt1 >= (unsigned int)k) break;
-        c_lo += cnt1;
-      }
-      int b2 = KNN_BINS;
-      unsigned int cnt2 = cnt1;
-      const bool lvl2 = cnt1 > 8u && c_lo + cnt1 > (unsigned int)k;
-      if (lvl2) {
-        // ---- 2. level-2 histogram over the recorded candidates of bin b1
-#pragma unroll
-        for (int b = 0; b < KNN_BINS; ++b) h[b * KNN_THREADS] = (unsigned short)0;
-        int it = 0;
-        knn_rows(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int j, int hi) {
-          const unsigned int w = it < KR_WORDS ? rec[it] : knn_word(P, pq, j, hi, bound2, scale1);
-          ++it;
-          if (w == 0xffffffffu) return;
-#pragma unroll
-          for (int s_ = 0; s_ < 4; ++s_) {
-            if ((int)((w >> (8 * s_)) & 255u) != b1) continue;
-            const int bb = knn_sub_bin(P, j + s_, pq.x, pq.y, pq.z, scale1, b1);
-            const unsigned short v = h[bb * KNN_THREADS];
-            h[bb * KNN_THREADS] = v == 65535 ? v : (unsigned short)(v + 1);
-          }
-        });
-        for (b2 = 0; b2 < KNN_BINS; ++b2) {
-          cnt2 = h[b2 * KNN_THREADS];
-          if (c_lo + cnt2 >= (unsigned int)k) break;
-          c_lo += cnt2;
-        }
-      }
-      const unsigned int t = (unsigned int)k - c_lo;
-      const bool take_all = (t == cnt2);
-      if (!take_all && cnt2 > 8u) {
-        fallback = true;                     // more than 8 candidates tied in the boundary sub-bin: repeated selection, rare
-      } else {
-        if (F & KR2_EMIT) {
-          // ---- 3. emit from the record.  Bins below `thr` are neighbours outright; candidates of bin b1 that need a
-          // second look (sub-bin under the second level, rank among the boundary candidates) only leave their position
-          // in the thread's dead histogram column (two counters per entry)
-          const bool plain_b1 = take_all && !lvl2;
-          int thr = plain_b1 ? b1 + 1 : b1;
-          asm volatile("" : "+r"(thr));        // opaque: one register instead of a select at every use
-          int nb = 0;
-          int it = 0;
-          unsigned int pre0 = rec[0], pre1 = rec[1], pre2 = rec[2], pre3 = rec[3];
-          knn_rows16(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int jg, int hi) {
-            const int left = hi - jg;
-            const int nw = left >= 16 ? 4 : (left + 3) >> 2;
-            unsigned int w0, w1 = 0xffffffffu, w2 = 0xffffffffu, w3 = 0xffffffffu;
-            if (it + 3 < KR_WORDS) {
-              if (F & KR2_PIPE) {
-                // the record is one linear stream over the iterations of the walk: the words of this step were loaded
-                // during the previous one (they come back from L2), the words of the next step are requested now
-                w0 = pre0; w1 = pre1; w2 = pre2; w3 = pre3;
-                const int nx = it + nw < KR_WORDS - 4 ? it + nw : KR_WORDS - 4;
-                pre0 = rec[nx]; pre1 = rec[nx + 1]; pre2 = rec[nx + 2]; pre3 = rec[nx + 3];
-              } else {
-                w0 = rec[it]; w1 = rec[it + 1]; w2 = rec[it + 2]; w3 = rec[it + 3];      // words past nw: ignored below
-              }
-            } else {
-              w0 = it < KR_WORDS ? rec[it] : knn_word(P, pq, jg, hi, bound2, scale1);
-              if (nw > 1) w1 = it + 1 < KR_WORDS ? rec[it + 1] : knn_word(P, pq, jg + 4, hi, bound2, scale1);
-              if (nw > 2) w2 = it + 2 < KR_WORDS ? rec[it + 2] : knn_word(P, pq, jg + 8, hi, bound2, scale1);
-              if (nw > 3) w3 = it + 3 < KR_WORDS ? rec[it + 3] : knn_word(P, pq, jg + 12, hi, bound2, scale1);
-            }
-            it += nw;
-            for (int i = 0; i < nw; ++i) {
-              const unsigned int w = i == 0 ? w0 : (i == 1 ? w1 : (i == 2 ? w2 : w3));
-              if (w == 0xffffffffu) continue;
-              const int j0 = jg + 4 * i;
-              const int e0 = (int)(w & 255u), e1 = (int)((w >> 8) & 255u), e2 = (int)((w >> 16) & 255u), e3 = (int)(w >> 24);
-              const bool has_b1 = !plain_b1 && (e0 == b1 || e1 == b1 || e2 == b1 || e3 == b1);
-              if (lvl2 && has_b1) {
-                // second level (rare): slot by slot, so that the row keeps the order of the walk
-  #pragma unroll 1
-                for (int s_ = 0; s_ < 4; ++s_) {
-                  const int b = (int)((w >> (8 * s_)) & 255u);
-                  const int j = j0 + s_;
-                  if (b < b1) {
-                    out_j[(int64_t)(cnt++) * DC_SLICE] = j;
-                  } else if (b == b1) {
-                    const int bb = knn_sub_bin(P, j, pq.x, pq.y, pq.z, scale1, b1);
-                    if (bb < b2 || (bb == b2 && take_all)) {
-                      out_j[(int64_t)(cnt++) * DC_SLICE] = j;
-                    } else if (bb == b2 && nb < 8) {
-                      unsigned short* e = h + 2 * nb * KNN_THREADS;
-                      e[0] = (unsigned short)j;
-                      e[KNN_THREADS] = (unsigned short)((unsigned int)j >> 16);
-                      ++nb;
-                    }
-                  }
-                }
-              } else {
-                if (e0 < thr) out_j[(int64_t)cnt * DC_SLICE] = j0;
-                cnt += e0 < thr ? 1 : 0;
-                if (e1 < thr) out_j[(int64_t)cnt * DC_SLICE] = j0 + 1;
-                cnt += e1 < thr ? 1 : 0;
-                if (e2 < thr) out_j[(int64_t)cnt * DC_SLICE] = j0 + 2;
-                cnt += e2 < thr ? 1 : 0;
-                if (e3 < thr) out_j[(int64_t)cnt * DC_SLICE] = j0 + 3;
-                cnt += e3 < thr ? 1 : 0;
-                if (has_b1) {
-                  // the (<= 8) candidates of the boundary bin: positions only, ranked after the walk
-  #pragma unroll
-                  for (int s_ = 0; s_ < 4; ++s_) {
-                    if ((int)((w >> (8 * s_)) & 255u) == b1 && nb < 8) {
-                      unsigned short* e = h + 2 * nb * KNN_THREADS;
-                      e[0] = (unsigned short)(j0 + s_);
-                      e[KNN_THREADS] = (unsigned short)((unsigned int)(j0 + s_) >> 16);
-                      ++nb;
-                    }
-                  }
-                }
-              }
-            }
-          });
-          if (!take_all) {
-            double bd[8];
-            int bj[8], bt[8];
-  #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const unsigned short* e = h + 2 * i * KNN_THREADS;
-              const bool have = i < nb;
-              const int j = have ? (int)((unsigned int)e[0] | ((unsigned int)e[KNN_THREADS] << 16)) : 0;
-              const dc_point pj = dc_ld_point(P + j);
-              bd[i] = have ? dc_dist2(pj, pq) : INFINITY;
-              bj[i] = have ? j : 0x7fffffff;
-              bt[i] = have ? (int)pj.tag : 0x7fffffff;
-            }
-  #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              unsigned int rank = 0u;
-  #pragma unroll
-              for (int m = 0; m < 8; ++m) rank += knn_less(bd[m], bt[m], bd[i], bt[i]) ? 1u : 0u;
-              if (i < nb && rank < t) out_j[(int64_t)(cnt++) * DC_SLICE] = bj[i];
-            }
-          }
-        } else {
-          // ---- 3. emit from the record
-          int nb = 0;
-          int it = 0;
-          // four words of the record per step, loaded together: the record comes back from L2 (480 KB per SM do not
-          // stay in L1) and one dependent load per word left the pass waiting on it for 12 % of the kernel
-          knn_rows16(g, pkeys, n, cell_start, c0, c1, c2, rho, [&](int jg, int hi) {
-            const int left = hi - jg;
-            const int nw = left >= 16 ? 4 : (left + 3) >> 2;
-            unsigned int w0, w1 = 0xffffffffu, w2 = 0xffffffffu, w3 = 0xffffffffu;
-            if (it + 3 < KR_WORDS) {
-              w0 = rec[it]; w1 = rec[it + 1]; w2 = rec[it + 2]; w3 = rec[it + 3];      // words past nw: ignored below
-            } else {
-              w0 = it < KR_WORDS ? rec[it] : knn_word(P, pq, jg, hi, bound2, scale1);
-              if (nw > 1) w1 = it + 1 < KR_WORDS ? rec[it + 1] : knn_word(P, pq, jg + 4, hi, bound2, scale1);
-              if (nw > 2) w2 = it + 2 < KR_WORDS ? rec[it + 2] : knn_word(P, pq, jg + 8, hi, bound2, scale1);
-              if (nw > 3) w3 = it + 3 < KR_WORDS ? rec[it + 3] : knn_word(P, pq, jg + 12, hi, bound2, scale1);
-            }
-            it += nw;
-            for (int i = 0; i < nw; ++i) {
-            const unsigned int w = i == 0 ? w0 : (i == 1 ? w1 : (i == 2 ? w2 : w3));
-            if (w == 0xffffffffu) continue;
-            const int j0 = jg + 4 * i;
-  #pragma unroll
-            for (int s_ = 0; s_ < 4; ++s_) {
-              const int b = (int)((w >> (8 * s_)) & 255u);
-              const int j = j0 + s_;
-              if (b < b1) {
-                out_j[(int64_t)(cnt++) * DC_SLICE] = j;
-              } else if (b == b1) {
-                if (take_all && !lvl2) {
-                  out_j[(int64_t)(cnt++) * DC_SLICE] = j;
-                } else {
-                  const dc_point pj = dc_ld_point(P + j);
-                  const double d2 = dc_dist2(pj, pq);
-                  bool boundary = true;
-                  if (lvl2) {
-                    int bb = __double2int_rz((d2 * scale1 - (double)b1) * (double)KNN_BINS);
-                    bb = bb < 0 ? 0 : (bb > KNN_BINS - 1 ? KNN_BINS - 1 : bb);
-                    if (bb < b2) out_j[(int64_t)(cnt++) * DC_SLICE] = j;
-                    boundary = (bb == b2);
-                  }
-                  if (boundary) {
-                    if (take_all) {
-                      out_j[(int64_t)(cnt++) * DC_SLICE] = j;
-                    } else if (nb < 8) {
-                      const int tag = (int)pj.tag;
-                      const unsigned long long u = (unsigned long long)__double_as_longlong(d2);
-                      unsigned short* e = h + 8 * nb * KNN_THREADS;
-                      e[0] = (unsigned short)u;
-                      e[KNN_THREADS] = (unsigned short)(u >> 16);
-                      e[2 * KNN_THREADS] = (unsigned short)(u >> 32);
-                      e[3 * KNN_THREADS] = (unsigned short)(u >> 48);
-                      e[4 * KNN_THREADS] = (unsigned short)j;
-                      e[5 * KNN_THREADS] = (unsigned short)((unsigned int)j >> 16);
-                      e[6 * KNN_THREADS] = (unsigned short)tag;
-                      e[7 * KNN_THREADS] = (unsigned short)((unsigned int)tag >> 16);
-                      ++nb;
-                    }
-                  }
-                }
-              }
-            }
-            }
-          });
-          if (!take_all) {
-            double bd[8];
-            int bj[8], bt[8];
-  #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const unsigned short* e = h + 8 * i * KNN_THREADS;
-              const unsigned long long u = (unsigned long long)e[0] | ((unsigned long long)e[KNN_THREADS] << 16) |
-                                           ((unsigned long long)e[2 * KNN_THREADS] << 32) | ((unsigned long long)e[3 * KNN_THREADS] << 48);
-              const int j = (int)((unsigned int)e[4 * KNN_THREADS] | ((unsigned int)e[5 * KNN_THREADS] << 16));
-              bd[i] = i < nb ? __longlong_as_double((long long)u) : INFINITY;
-              bj[i] = i < nb ? j : 0x7fffffff;
-              bt[i] = i < nb ? (int)((unsigned int)e[6 * KNN_THREADS] | ((unsigned int)e[7 * KNN_THREADS] << 16)) : 0x7fffffff;
-            }
-  #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              unsigned int rank = 0u;
-  #pragma unroll
-              for (int m = 0; m < 8; ++m) rank += knn_less(bd[m], bt[m], bd[i], bt[i]) ? 1u : 0u;
-              if (i < nb && rank < t) out_j[(int64_t)(cnt++) * DC_SLICE] = bj[i];
-            }
-          }
-        }
-      }
-    }
-    if (fallback) {
-      const int slot = atomicAdd(counters + 1, 1);
-      fb_list[slot] = make_int2((int)q, rho);
-    }
   }
   if (!fallback)
     for (int c = cnt; c < k; ++c) out_j[(int64_t)c * DC_SLICE] = -1;
@@ -1576,25 +1242,8 @@ extern "C" int dc_knn_recorded(const void* P, const uint64_t* pkeys, int64_t n, 
   DC_LAUNCH_CHECK();
   const int64_t n_slices = (nq + DC_SLICE - 1) / DC_SLICE;
   const int blocks = dc_blocks(n_slices * DC_SLICE, KNN_THREADS);
-  // DC_KNN_REC: -1 = knn_record_kernel, 0..7 = knn_record2_kernel with that combination of KR2_* flags (all return the
-  // same lists; tools/check_knn_recorded.py times them side by side)
-  const char* env = getenv("DC_KNN_REC");
-  const int variant = env ? atoi(env) : KR2_DEFAULT;
-#define KR2_LAUNCH(F)                                                                                                      \
-  knn_record2_kernel<F><<<blocks, KNN_THREADS, 0, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq, g,  \
-                                                        cell_start, k, r2cap, max_ring, fb, counters, ell_idx)
-  switch (variant) {
-    case 7: KR2_LAUNCH(7); break;
-    case 15: KR2_LAUNCH(15); break;
-    case 31: KR2_LAUNCH(31); break;
-    case 47: KR2_LAUNCH(47); break;
-    case 79: KR2_LAUNCH(79); break;
-    case 127: KR2_LAUNCH(127); break;
-    default:
-      knn_record_kernel<<<blocks, KNN_THREADS, 0, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq, g, cell_start,
-                                                        k, r2cap, max_ring, fb, counters, ell_idx);
-  }
-#undef KR2_LAUNCH
+  knn_record_kernel<<<blocks, KNN_THREADS, 0, st>>>((const dc_point*)P, pkeys, n, (const dc_point*)Q, qkeys, nq, g, cell_start, k,
+                                                    r2cap, max_ring, fb, counters, ell_idx);
   DC_LAUNCH_CHECK();
   int dev = 0, sms = 148;
   DC_CUDA_CHECK(cudaGetDevice(&dev));

@@ -18,7 +18,7 @@ __all__ = ['SortedMap', 'Graph', 'search']
 
 KNN_OCC_DEFAULT = '0.3'                # mean points per occupied cell / k the kNN cell size aims at
 KNN_SAMPLE = 8192                     # queries searched to model the cost of the kNN kernel against the cell size
-KNN_ROW_COST = 3.0                    # overhead of one row of cells, in candidates (fitted: tools/knn_cell_sweep.py)
+KNN_ROW_COST = 4.0                    # overhead of one row of cells, in candidates (fitted: tools/knn_cell_sweep.py)
 KNN_MODEL_MIN_POINTS = 1 << 17        # smaller maps are launch bound: the occupancy estimate is good enough
 KNN_PAD = 3                           # readable records dc_knn_recorded expects behind the n records of the map
 DENSE_TABLE_MAX_CELLS = 1 << 30      # 4 GB of int32 cell starts at most (a 100 M point, 760 m corridor needs 3e8 cells)
@@ -330,7 +330,9 @@ _cell_hint = {}
 
 
 def _knn_cell_size(points, k, r, bounds, use_hint=True):
-    """Cell edge for kNN search: aim at ~DC_KNN_OCC * k points per occupied cell, estimated from key-only sorts.
+    """Cell edge for kNN search: ~DC_KNN_OCC * k points per occupied cell (estimated from key-only sorts), refined on
+    maps of >= KNN_MODEL_MIN_POINTS points by a cost model of the kernel evaluated on a sample of queries
+    (_knn_cell_from_sample; DC_KNN_CELL=occ keeps the occupancy estimate).
 
     The estimate of the previous search is reused (no sort at all) only for a map of the same size (+-5 %) AND the
     same extent (+-10 % per axis): an unrelated map of similar size but different scale gets its own estimate."""
@@ -351,18 +353,28 @@ def _knn_cell_size(points, k, r, bounds, use_hint=True):
     # a disc of radius c on a surface with `occ` points per c^2 holds pi * occ points; the mean occupancy is dominated
     # by sparse cells (a typical QUERY sits in a cell 2x as full)
     target = max(float(occ_env) * k, 2.0)
+    use_model = points.shape[0] >= KNN_MODEL_MIN_POINTS and os.environ.get('DC_KNN_CELL', 'model') == 'model'
+    band = (0.6, 1.7) if use_model else (0.9, 1.11)       # the sample model refines a rough estimate: fewer sorts
     for _ in range(5):
         occ = SortedMap.occupancy_of(points, lo, hi, c0)
-        if 0.9 * target <= occ <= 1.11 * target:
+        if band[0] * target <= occ <= band[1] * target:
             break
         c0 = c0 * min(max(math.sqrt(target / occ), 1.0 / 8.0), 8.0)
         if r and c0 > r:
             c0 = float(r) * (1.0 + 1e-6)      # a hair above r: one ring always covers r
             break
-    if points.shape[0] >= KNN_MODEL_MIN_POINTS and os.environ.get('DC_KNN_CELL', 'model') == 'model':
+    if use_model:
         c0 = _knn_cell_from_sample(points, int(k), r, bounds, c0)
     _cell_hint[hint_key] = (points.shape[0], c0, occ_env, ext)
     return c0
+
+
+def _grid_cells(bounds, cell):
+    """Number of cells of the search grid SortedMap.make_spec lays over `bounds` (no overflow check)."""
+    n = 1
+    for lo, hi in zip(*bounds):
+        n *= int(math.floor((hi - (lo - 1e-3 * cell)) / cell)) + 1
+    return n
 
 
 def _ring_sequence(max_ring):
@@ -391,6 +403,8 @@ def _knn_cell_from_sample(points, k, r, bounds, c0):
     sample = points[torch.randint(0, n, (KNN_SAMPLE,), device=dev, generator=_sample_generator(dev))]
     g = search(points, sample, k=k, r=r, cell=c0)
     d = g.distances()                                     # fp64 [m, k], inf = fewer than k within r
+    # the sorted map of this search is the one the caller builds next when c0 stands: keep it for search()
+    _sample_map[0] = (points.data_ptr(), points._version, tuple(points.shape), points.dtype, c0, bounds, g.map)
     del g
     fin = torch.isfinite(d)
     n_valid = fin.sum(dim=1).clamp_(min=1).double()
@@ -401,11 +415,18 @@ def _knn_cell_from_sample(points, k, r, bounds, c0):
     far = torch.where(fin, d, torch.zeros_like(d)).amax(dim=1)
     rad = torch.where(have_k, dk, torch.full_like(dk, float(r)) if r else far).clamp_(min=1e-12)
     sigma = n_valid / (math.pi * rad * rad)               # points per unit area of the surface around the query
-    cells = c0 * torch.pow(2.0, torch.arange(-8, 7, dtype=torch.float64, device=dev) / 6.0)
+    cand = [c0 * 2.0 ** (e / 6.0) for e in range(-8, 7)]
     if r:
-        cells = cells[cells <= float(r) * (1.0 + 1e-6)]
-    if cells.numel() == 0:
+        cand = [c for c in cand if c <= float(r) * (1.0 + 1e-6)]
+    # a grid too fine for the dense cell table (binary searches for every row of cells: 6x slower on the 57 M point street
+    # map) is only considered when no candidate fits
+    fits = [c for c in cand if _grid_cells(bounds, c) <= DENSE_TABLE_MAX_CELLS]
+    if fits:
+        cand = fits
+        c0 = min(cand, key=lambda c: abs(c - c0))          # c0 itself may not fit
+    if not cand:
         return c0
+    cells = torch.tensor(cand, dtype=torch.float64, device=dev)
     cost = torch.zeros((d.shape[0], cells.numel()), dtype=torch.float64, device=dev)
     done = torch.zeros_like(cost, dtype=torch.bool)
     unit = sigma[:, None] * (cells * cells)[None, :] + KNN_ROW_COST
@@ -423,6 +444,17 @@ def _knn_cell_from_sample(points, k, r, bounds, c0):
     if float(mean[i0]) <= 1.05 * float(mean[best]):
         return c0
     return float(cells[best].item())
+
+
+_sample_map = [None]                   # (data_ptr, version, shape, dtype, cell, bounds, SortedMap) of the last sample search
+
+
+def _take_sample_map(points, cell, bounds):
+    """The map the cell-size estimate has just built for these very points, cell and bounds (used once), else None."""
+    e, _sample_map[0] = _sample_map[0], None
+    if e is not None and e[:6] == (points.data_ptr(), points._version, tuple(points.shape), points.dtype, cell, bounds):
+        return e[6]
+    return None
 
 
 _sample_generators = {}
@@ -470,7 +502,10 @@ def search(points, query=None, k=None, r=None, cell=None, stack_first=None):
             cell = float(r) * (1.0 + 1e-6)   # a hair above r: one ring of cells is always enough
     if stack_first is not None:
         stack = (stack_first, n_clouds, int(math.ceil(float(r) / cell)))
-    smap = SortedMap(points, cell, bounds=bounds, stack=stack)
+    smap = _take_sample_map(points, cell, bounds) if (stack is None and self_query) else None
+    _sample_map[0] = None
+    if smap is None:
+        smap = SortedMap(points, cell, bounds=bounds, stack=stack)
     st = L.stream()
     if self_query:
         Q, qkeys, qorder, nq = smap.P, smap.keys, None, n

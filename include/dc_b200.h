@@ -135,7 +135,10 @@ int dc_knn_cells(const void* P, const uint64_t* pkeys, int64_t n, const void* Q,
  * bound in a thread-private list and the emit pass replays the record, re-reading only the candidates of the boundary
  * bin (one byte per visited candidate; iterations beyond the 256-word record are recomputed in place); queries with
  * > 8 exact ties at the k-th place are finished by the kernel of dc_knn.  Same rows as dc_knn, entry by entry.
+ * PRECONDITION: the n records of P are followed by DC_KNN_PAD (3) more READABLE records (content ignored): the first
+ * pass reads four consecutive records per step without clamping the last ones to the end of a row.
  * Replaces cKDTree.query (nearest_neighbors.py:48-49).  temp: 64 + 8 nq bytes (two-phase size query). */
+#define DC_KNN_PAD 3
 int dc_knn_recorded(const void* P, const uint64_t* pkeys, int64_t n, const void* Q, const uint64_t* qkeys, int64_t nq,
                     const dc_grid_spec* spec_host, const int32_t* cell_start, int k, double r, int32_t* ell_idx, void* temp,
                     size_t* temp_bytes, void* stream);

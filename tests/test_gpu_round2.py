@@ -73,6 +73,35 @@ def test_knn_cell_kernel_equals_thread_kernel(dc, dev, monkeypatch, case):
         assert torch.equal(search(p, query, **kw).ell_idx, a_raw), (case, kw)
 
 
+def test_knn_cell_model_changes_speed_not_results(dc, dev, monkeypatch):
+    """The cell size of a kNN search comes from a cost model evaluated on a sample of queries (graph._knn_cell_from_sample):
+    it may differ from the occupancy estimate, the neighbour lists may not; the map carries the KNN_PAD records the first
+    pass of dc_knn_recorded may read behind its last row."""
+    from depth_correction_b200 import graph
+    scans, poses = _street_points(3)
+    pts = np.concatenate([s['points'].astype(np.float64) @ T[:3, :3].T + T[:3, 3] for s, T in zip(scans, poses)]).astype(np.float32)
+    p = torch.as_tensor(pts, device=dev)
+    assert len(p) >= graph.KNN_MODEL_MIN_POINTS
+    cells, rows = {}, {}
+    for mode in ('occ', 'model'):
+        monkeypatch.setenv('DC_KNN_CELL', mode)
+        graph.clear_cell_hints()
+        g = graph.search(p, k=32, r=0.4)
+        cells[mode] = g.map.cell
+        rows[mode] = g.neighbors()
+        assert g.map.P.untyped_storage().nbytes() >= (len(p) + graph.KNN_PAD) * 32
+        # a second search of the same map takes the remembered cell: no estimate at all
+        assert graph.search(p, k=32, r=0.4).map.cell == g.map.cell
+    graph.clear_cell_hints()
+    assert torch.equal(rows['occ'], rows['model'])
+    assert cells['occ'] / 2.6 <= cells['model'] <= 2.1 * cells['occ']
+    tree_d, tree_i = __import__('scipy.spatial', fromlist=['cKDTree']).cKDTree(pts.astype(np.float64)).query(
+        pts[:2000].astype(np.float64), k=32, distance_upper_bound=0.4)
+    ref = np.where(np.isfinite(tree_d), tree_i, -1)
+    got = rows['model'][:2000].cpu().numpy()
+    assert np.array_equal(np.sort(got, axis=1), np.sort(ref, axis=1))
+
+
 def test_knn_ties_do_not_depend_on_the_cell_size(dc, dev):
     """Exact ties at the k-th place are broken by the ORIGINAL index, so the index matrix is the same for every cell
     size (round 1 broke them by the position in the cell-sorted map)."""

@@ -61,32 +61,23 @@ cases.append(('clustered + duplicates k=8', torch.as_tensor(clu, device=dev), 8,
 lat = np.stack(np.meshgrid(np.arange(40), np.arange(40), np.arange(10), indexing='ij'), -1).reshape(-1, 3).astype(np.float32) * 0.25
 cases.append(('lattice (exact ties) k=27 r=0.5', torch.as_tensor(lat, device=dev), 27, 0.5))
 ok = True
-# DC_KNN_REC: -1 = knn_record_kernel, 0..7 = knn_record2_kernel<flags> (1 branch-free histogram, 2 reach from the query,
-# 4 predicated emit); every variant must return the lists of dc_knn entry by entry
-variants = [int(v) for v in os.environ.get('KNN_REC_VARIANTS', '-1,0,1,2,4,7').split(',')]
 for name, pts, k, r in cases:
     gt, mt, _ = timed(pts, k, r, 'thread')
     a = gt.ell_idx.clone()
     cell = gt.map.cell
     del gt
-    line = '%-36s n=%9d cell %.4f  dc_knn %.3f ms |' % (name, len(pts), cell, mt)
-    for v in variants:
-        os.environ['DC_KNN_REC'] = str(v)
-        gr, mr, nfb = timed(pts, k, r, 'record')
-        same = bool(torch.equal(a, gr.ell_idx))
-        note = ''
-        if not same:
-            # same neighbour SETS in another order inside the rows?  (ELL slices: [slice, column, lane])
-            sa = a.view(-1, k, 32).sort(dim=1).values
-            sb = gr.ell_idx.view(-1, k, 32).sort(dim=1).values
-            same = bool(torch.equal(sa, sb))
-            note = ' (order differs)' if same else ' MISMATCH'
-            del sa, sb
-        ok &= same
-        line += '  rec[%d] %.3f ms (%.2fx) fb %d%s' % (v, mr, mt / mr, nfb, note)
-        del gr
-    os.environ.pop('DC_KNN_REC', None)
-    print(line, flush=True)
-    del a
+    gr, mr, nfb = timed(pts, k, r, 'record')
+    same = bool(torch.equal(a, gr.ell_idx))
+    note = ''
+    if not same:
+        # same neighbour SETS in another order inside the rows?  (ELL slices: [slice, column, lane])
+        sa = a.view(-1, k, 32).sort(dim=1).values
+        sb = gr.ell_idx.view(-1, k, 32).sort(dim=1).values
+        note = ' (same sets, order differs)' if bool(torch.equal(sa, sb)) else ' MISMATCH'
+        del sa, sb
+    ok &= same
+    print('%-36s n=%9d cell %.4f  dc_knn %.3f ms  dc_knn_recorded %.3f ms (%.2fx)  fallback %d (%.3f %%)  identical lists: %s%s' % (
+        name, len(pts), cell, mt, mr, mt / mr, nfb, 100.0 * nfb / len(pts), same, note), flush=True)
+    del gr, a
 print('OK' if ok else 'MISMATCH')
 sys.exit(0 if ok else 1)

@@ -38,18 +38,23 @@ def kernel_ms(pts, k, r, cell, reps=3):
 
 
 n_scans = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+n_street = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+only = os.environ.get('SWEEP_ONLY')           # substring of the case names to run
 cases = [('corridor %d scans k=32 r=0.4' % n_scans, world('corridor', n_scans), 32, 0.4),
          ('corridor 8 scans k=32 r=0.4', world('corridor', 8), 32, 0.4),
          ('corridor 8 scans k=16', world('corridor', 8), 16, None),
          ('corridor 8 scans k=64 r=0.5', world('corridor', 8), 64, 0.5),
          ('street 8 HDL-64 scans k=32 r=0.4', world('street', 8, pattern='hdl-64', depth_clip=(5.0, 80.0)), 32, 0.4),
-         ('street 60 HDL-64 scans k=32 r=0.4', world('street', 60, pattern='hdl-64', depth_clip=(5.0, 80.0)), 32, 0.4)]
+         ('street %d HDL-64 scans k=32 r=0.4' % n_street, (lambda: world('street', n_street, pattern='hdl-64', depth_clip=(5.0, 80.0))), 32, 0.4)]
 rng = np.random.default_rng(3)
 c = rng.uniform(-10, 10, (200, 3))
 clu = (c[rng.integers(0, 200, 300000)] + rng.normal(0, 0.3, (300000, 3))).astype(np.float32)
 cases.append(('clustered k=8', torch.as_tensor(clu, device=dev), 8, None))
-variants = os.environ.get('KNN_REC_VARIANTS', '5,7').split(',')
 for name, pts, k, r in cases:
+    if only and only not in name:
+        continue
+    if callable(pts):
+        pts = pts()
     g = search(pts, k=k, r=r)
     cell0 = g.map.cell
     dk = g.distances()[:, k - 1]
@@ -67,12 +72,8 @@ for name, pts, k, r in cases:
         if r and cell > r:
             continue
         share = (sample < cell).double().mean().item()
-        line = '   cell %.4f (%.2f x)  d_k < cell for %.1f %% of the queries |' % (cell, f, 100.0 * share)
-        for v in variants:
-            os.environ['DC_KNN_REC'] = v
-            line += '  rec[%s] %.3f ms' % (v, kernel_ms(pts, k, r, cell))
-        print(line, flush=True)
-    os.environ.pop('DC_KNN_REC', None)
+        print('   cell %.4f (%.2f x)  d_k < cell for %.1f %% of the queries | dc_knn_recorded %.3f ms' % (
+            cell, f, 100.0 * share, kernel_ms(pts, k, r, cell)), flush=True)
     del dk, dkc, sample
     # what the estimate of graph._knn_cell_size picks (cost model on a sample of queries), and the cold search it costs
     from depth_correction_b200.graph import clear_cell_hints
@@ -87,10 +88,6 @@ for name, pts, k, r in cases:
         torch.cuda.synchronize()
         cell = g.map.cell
         del g
-        line = '   estimate %-5s -> cell %.4f  cold search %.2f ms |' % (mode, cell, e0.elapsed_time(e1))
-        for v in variants:
-            os.environ['DC_KNN_REC'] = v
-            line += '  rec[%s] %.3f ms' % (v, kernel_ms(pts, k, r, cell))
-        os.environ.pop('DC_KNN_REC', None)
-        print(line, flush=True)
+        print('   estimate %-5s -> cell %.4f  cold search %.2f ms | dc_knn_recorded %.3f ms' % (
+            mode, cell, e0.elapsed_time(e1), kernel_ms(pts, k, r, cell)), flush=True)
     os.environ.pop('DC_KNN_CELL', None)
