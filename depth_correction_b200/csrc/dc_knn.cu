@@ -21,7 +21,9 @@
 
 #define KNN_THREADS 64
 #define KNN_WARPS (KNN_THREADS / 32)
+#ifndef KNN_BLOCKS
 #define KNN_BLOCKS (1024 / KNN_THREADS)   // resident blocks per SM the register allocation is held to (64 registers)
+#endif
 #define KNN_BINS 64
 
 // (d2, original index) lexicographic order.  The original index (dc_point.tag) -- not the position in the cell-sorted

@@ -11,6 +11,6 @@ ncu --profile-from-start off --set full --clock-control none --import-source on 
 tail -2 gpurun_out/r2_ncu_full.log
 python tools/ncu_summary.py gpurun_out/r2_timed.ncu-rep gpurun_out/r2_timed_region_kernels.md "Round 2 final: kernels of the timed region of bench.py (64 scans, 8.37 M points, k=32)" gpurun_out/r2_traffic.json 8366086
 python tools/ncu_lines.py gpurun_out/r2_timed.ncu-rep knn_record_kernel 50 > gpurun_out/r2_knn_record_lines.txt 2>&1
-python tools/ncu_lines.py gpurun_out/r2_timed.ncu-rep step_forward_kernel 30 > gpurun_out/r2_step_forward_lines.txt 2>&1
+python tools/ncu_lines.py gpurun_out/r2_timed.ncu-rep step_forward_kernelILi0ELb1E 30 > gpurun_out/r2_step_forward_lines.txt 2>&1
 ls -la gpurun_out/
 sz=$(stat -c %s gpurun_out/r2_timed.ncu-rep); if [ "$sz" -gt 40000000 ]; then rm gpurun_out/r2_timed.ncu-rep; fi
