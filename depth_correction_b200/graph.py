@@ -19,6 +19,7 @@ __all__ = ['SortedMap', 'Graph', 'search']
 KNN_OCC_DEFAULT = '0.3'                # mean points per occupied cell / k the kNN cell size aims at
 KNN_SAMPLE = 8192                     # queries searched to model the cost of the kNN kernel against the cell size
 KNN_ROW_COST = 4.0                    # overhead of one row of cells, in candidates (fitted: tools/knn_cell_sweep.py)
+KNN_TABLE_COST = 0.55                 # one entry of the dense cell table, in candidates of one query (0.83 ms per 2^30 cells)
 KNN_MODEL_MIN_POINTS = 1 << 17        # smaller maps are launch bound: the occupancy estimate is good enough
 KNN_PAD = 3                           # readable records dc_knn_recorded expects behind the n records of the map
 DENSE_TABLE_MAX_CELLS = 1 << 30      # 4 GB of int32 cell starts at most (a 100 M point, 760 m corridor needs 3e8 cells)
@@ -438,7 +439,11 @@ def _knn_cell_from_sample(points, k, r, bounds, c0):
         done |= (dk[:, None] < rho_c * cells[None, :] + 0.125 * cells[None, :]) | last
         if bool(done.all()):
             break
-    mean = cost.mean(dim=0)
+    # + the dense cell table the search builds (n_cells + 1 int32 starts: a fill and a scan at HBM speed), per query and in
+    # the model's unit (one candidate ~ 1.8 ps of kernel time per query of the map, one table entry ~ 1 ps)
+    table = torch.tensor([_grid_cells(bounds, c) for c in cand], dtype=torch.float64, device=dev)
+    table = torch.where(table <= DENSE_TABLE_MAX_CELLS, table, torch.zeros_like(table))
+    mean = cost.mean(dim=0) + KNN_TABLE_COST * table / float(n)
     best = int(torch.argmin(mean).item())
     i0 = int(torch.argmin((cells - c0).abs()).item())
     if float(mean[i0]) <= 1.05 * float(mean[best]):
