@@ -407,6 +407,13 @@ def _knn_cell_from_sample(points, k, r, bounds, c0):
     # the sorted map of this search is the one the caller builds next when c0 stands: keep it for search()
     _sample_map[0] = (points.data_ptr(), points._version, tuple(points.shape), points.dtype, c0, bounds, g.map)
     del g
+    return _knn_cell_of_distances(d, n, r, bounds, c0)
+
+
+def _knn_cell_of_distances(d, n, r, bounds, c0):
+    """The cost model of _knn_cell_from_sample on the sorted neighbour distances d (fp64 [m, k], inf = missing) of m sample
+    queries of a map of n points (pure torch: runs on any device, tests/test_host_graph.py)."""
+    dev = d.device
     fin = torch.isfinite(d)
     n_valid = fin.sum(dim=1).clamp_(min=1).double()
     dk = d[:, -1]
