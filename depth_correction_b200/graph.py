@@ -18,7 +18,7 @@ __all__ = ['SortedMap', 'Graph', 'search']
 
 KNN_OCC_DEFAULT = '0.3'                # mean points per occupied cell / k the kNN cell size aims at
 KNN_SAMPLE = 8192                     # queries searched to model the cost of the kNN kernel against the cell size
-KNN_ROW_COST = 4.0                    # overhead of one row of cells, in candidates (fitted: tools/knn_cell_sweep.py)
+KNN_ROW_COST = 3.0                    # overhead of one row of cells, in candidates (fitted: tools/knn_cell_sweep.py)
 KNN_TABLE_COST = 0.55                 # one entry of the dense cell table, in candidates of one query (0.83 ms per 2^30 cells)
 KNN_MODEL_MIN_POINTS = 1 << 17        # smaller maps are launch bound: the occupancy estimate is good enough
 KNN_PAD = 3                           # readable records dc_knn_recorded expects behind the n records of the map
@@ -397,8 +397,12 @@ def _knn_cell_from_sample(points, k, r, bounds, c0):
     random points are searched exactly (cell c0), which gives each one's d_k and, through it, the surface density
     sigma = k / (pi d_k^2) around it; a query then costs, for every ring rho the kernel has to try,
     (2 rho + 1)^2 rows of sigma c^2 candidates + KNN_ROW_COST candidates' worth of row overhead, and it is finished by
-    the first ring with d_k < rho c + c / 8 (mean distance to the nearest face of its cell).  The cell minimising the
-    mean cost over candidate sizes c0 / 2.5 ... 2 c0 is returned (c0 itself when it is within 5 % of the optimum)."""
+    the first ring with d_k < rho c.  (The kernel's reach is rho c + the distance of the query to the nearest face of its
+    cell, but a WARP goes on to the next ring as soon as one of its 32 queries does, and one of them always sits next to a
+    face: fitted against the measured sweeps of seven maps, profiles/r2_knn_cell_sweep.log, the plain rho c criterion with
+    three candidates per row picks a cell within 2 % of the best of every sweep; crediting the mean face distance c / 8, or
+    its exact expectation, up to 17 % off.)  The cell minimising the mean cost over candidate sizes c0 / 2.5 ... 2 c0 is
+    returned."""
     n = points.shape[0]
     dev = points.device
     sample = points[torch.randint(0, n, (KNN_SAMPLE,), device=dev, generator=_sample_generator(dev))]
@@ -443,7 +447,7 @@ def _knn_cell_of_distances(d, n, r, bounds, c0):
         rho_c = torch.clamp(torch.full_like(max_ring, float(rho)), max=max_ring)      # the kernel caps the ring at r / cell
         last = rho_c >= max_ring
         cost += torch.where(done, torch.zeros_like(cost), (2.0 * rho_c + 1.0) ** 2 * unit)
-        done |= (dk[:, None] < rho_c * cells[None, :] + 0.125 * cells[None, :]) | last
+        done |= (dk[:, None] < rho_c * cells[None, :]) | last
         if bool(done.all()):
             break
     # + the dense cell table the search builds (n_cells + 1 int32 starts: a fill and a scan at HBM speed), per query and in
@@ -453,9 +457,10 @@ def _knn_cell_of_distances(d, n, r, bounds, c0):
     mean = cost.mean(dim=0) + KNN_TABLE_COST * table / float(n)
     best = int(torch.argmin(mean).item())
     i0 = int(torch.argmin((cells - c0).abs()).item())
-    if float(mean[i0]) <= 1.05 * float(mean[best]):
-        return c0
-    return float(cells[best].item())
+    # candidates are 12 % apart; c0 stands (and the map of the sample search is reused) only when it is the minimum itself:
+    # the model's curve is flatter than the kernel's, "within 5 % of the model's minimum" kept cells 12-20 % slower than
+    # the best of the sweep on mid-size street maps
+    return c0 if best == i0 else float(cells[best].item())
 
 
 _sample_map = [None]                   # (data_ptr, version, shape, dtype, cell, bounds, SortedMap) of the last sample search

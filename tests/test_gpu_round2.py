@@ -94,7 +94,8 @@ def test_knn_cell_model_changes_speed_not_results(dc, dev, monkeypatch):
         assert graph.search(p, k=32, r=0.4).map.cell == g.map.cell
     graph.clear_cell_hints()
     assert torch.equal(rows['occ'], rows['model'])
-    assert cells['occ'] / 2.6 <= cells['model'] <= 2.1 * cells['occ']
+    # the model looks at cells within 2^(-8/6) .. 2 of a first estimate that is itself within 0.77 .. 1.3 of the occupancy cell
+    assert cells['occ'] / 3.4 <= cells['model'] <= 2.7 * cells['occ']
     tree_d, tree_i = __import__('scipy.spatial', fromlist=['cKDTree']).cKDTree(pts.astype(np.float64)).query(
         pts[:2000].astype(np.float64), k=32, distance_upper_bound=0.4)
     ref = np.where(np.isfinite(tree_d), tree_i, -1)
