@@ -3,7 +3,7 @@
 //
 // The k nearest of a query are selected, not sorted: a histogram of the squared distances finds the bin that
 // holds the k-th distance, everything below that bin is a neighbour, and only the few candidates inside the
-// boundary bin are ranked (by (d2, sorted index)).  Every d2 is computed with the identical non-fused
+// boundary bin are ranked (by (d2, original index)).  Every d2 is computed with the identical non-fused
 // instruction sequence wherever it is needed, so the classification of a candidate never changes between
 // passes and the selection is exact.  Rows are emitted UNSORTED (the step kernels only need the set);
 // dc_knn_sort_rows orders them by distance when the reference layout is exported.
