@@ -427,7 +427,7 @@ def _knn_cell_of_distances(d, n, r, bounds, c0):
     far = torch.where(fin, d, torch.zeros_like(d)).amax(dim=1)
     rad = torch.where(have_k, dk, torch.full_like(dk, float(r)) if r else far).clamp_(min=1e-12)
     sigma = n_valid / (math.pi * rad * rad)               # points per unit area of the surface around the query
-    cand = [c0 * 2.0 ** (e / 6.0) for e in range(-8, 7)]
+    cand = [c0 * 2.0 ** (e / 12.0) for e in range(-16, 13)]          # c0 / 2.5 ... 2 c0, 6 % apart
     if r:
         cand = [c for c in cand if c <= float(r) * (1.0 + 1e-6)]
     # a grid too fine for the dense cell table (binary searches for every row of cells: 6x slower on the 57 M point street
@@ -457,10 +457,10 @@ def _knn_cell_of_distances(d, n, r, bounds, c0):
     mean = cost.mean(dim=0) + KNN_TABLE_COST * table / float(n)
     best = int(torch.argmin(mean).item())
     i0 = int(torch.argmin((cells - c0).abs()).item())
-    # candidates are 12 % apart; c0 stands (and the map of the sample search is reused) only when it is the minimum itself:
-    # the model's curve is flatter than the kernel's, "within 5 % of the model's minimum" kept cells 12-20 % slower than
-    # the best of the sweep on mid-size street maps
-    return c0 if best == i0 else float(cells[best].item())
+    # c0 stands (and the map of the sample search is reused) only when the minimum is c0 or one of its direct neighbours
+    # (6 % apart): the model's curve is flatter than the kernel's, "within 5 % of the model's minimum" kept cells 12-20 %
+    # slower than the best of the sweep on mid-size street maps
+    return c0 if abs(best - i0) <= 1 else float(cells[best].item())
 
 
 _sample_map = [None]                   # (data_ptr, version, shape, dtype, cell, bounds, SortedMap) of the last sample search
