@@ -271,8 +271,13 @@ extern "C" int dc_gather_points(const void* pts, int dtype, const int32_t* order
 // cell_start[c] = first sorted position with key >= c, for c = 0 .. n_cells.  Position s "owns" the cells
 // (key[s-1], key[s]] (and position n the cells above the last key); a warp fills the gaps of its 32 positions
 // cooperatively, so a long run of empty cells costs one coalesced sweep instead of one thread's serial loop
-// (the previous version did a 23-step binary search for each of the ~14 M cells of the bench grid).
-__global__ void cell_table_positions_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t n_cells, int sub_bits, int32_t* __restrict__ cell_start) {
+// (the previous version did a 23-step binary search for each of the ~14 M cells of the bench grid).  On SPARSE grids (street
+// maps: 20-40 cells per point) the gaps are 10^5 .. 10^6 cells long and each is filled by one warp: 1.4 TB/s, 0.83 ms for
+// the 2.8e8-cell grid of one of eight slabs of the 57 M point map.  A kernel with one warp per 2048 CELLS (one coalesced store
+// per 32 cells, keys searched only where a step holds any) was written and is correct, but its searches cost ~20 k cycles per
+// occupied step (0.50 vs 0.11 ms on the dense bench grid) and it was never measured on a sparse grid: not adopted
+// (profiles/r2_knn_experiments.md).
+__global__ void cell_table_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t n_cells, int sub_bits, int32_t* __restrict__ cell_start) {
   const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;     // 0 .. n (inclusive), rounded up to a warp
   const int lane = threadIdx.x & 31;
   int64_t first = 0, last = -1;      // cells first .. last get the value s
@@ -294,66 +299,10 @@ __global__ void cell_table_positions_kernel(const uint64_t* __restrict__ keys, i
   }
 }
 
-// The same table for SPARSE grids (many more cells than points: the street maps, every slab of a partitioned map).
-// One warp per CT_CHUNK consecutive cells, 32 cells per step, lane = cell: a coalesced 128-byte store per step.  The warp
-// keeps pos = the first position whose cell is >= the first cell of the step (one binary search per chunk, then carried
-// along); a step whose 32 cells hold no key -- almost every step of a sparse grid -- stores pos from every lane, a step
-// with keys finds the end of its keys by galloping from pos and lets every lane search its own cell in that short range.
-// Every entry is written exactly once and the work per warp is bounded by the chunk, whereas the kernel above hands the gap
-// of empty cells in front of a sorted position to that position's warp: the empty remainder of a row of a street grid
-// (10^5 .. 10^6 cells) is filled by ONE warp, 128 bytes at a time (1.4 TB/s: 0.83 ms for the 2.8e8-cell grid of one of eight
-// slabs of the 57 M point map).  On a dense grid (the 64-scan corridor: two cells per point, most steps hold keys) the
-// searches of this kernel are the slower way (0.50 vs 0.11 ms), so dc_cell_table picks by n_cells / n.
-#define CT_CHUNK 2048
-#define CT_THREADS 256
-#define CT_SPARSE 8          // cells per point from which the chunked kernel is used
-
-__global__ void __launch_bounds__(CT_THREADS)
-cell_table_chunks_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t n_cells, int sub_bits, int32_t* __restrict__ cell_start) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t c_begin = warp * CT_CHUNK;
-  if (c_begin > n_cells) return;
-  const int64_t c_end = c_begin + CT_CHUNK < n_cells + 1 ? c_begin + CT_CHUNK : n_cells + 1;
-  int64_t pos = dc_lower_bound(keys, n, (uint64_t)c_begin, sub_bits);        // the same search in every lane: broadcast loads
-  for (int64_t cg = c_begin; cg < c_end; cg += 32) {
-    const int64_t ge = cg + 32 < c_end ? cg + 32 : c_end;                    // this step: cells cg .. ge - 1
-    const int64_t kc = pos < n ? (int64_t)(__ldg(keys + pos) >> sub_bits) : INT64_MAX;
-    const int64_t c = cg + lane;
-    if (kc >= ge) {
-      if (c < ge) cell_start[c] = (int32_t)pos;
-      continue;
-    }
-    // keys of this step's cells start at pos; hi = a position at or behind their end
-    int64_t hi = pos + 1, stride = 32;
-    while (hi < n && (int64_t)(__ldg(keys + hi) >> sub_bits) < ge) {
-      hi = hi + stride < n ? hi + stride : n;
-      stride *= 2;
-    }
-    int64_t lo = pos, up = hi;                                                // first position in [pos, hi] with cell >= c
-    while (lo < up) {
-      const int64_t mid = (lo + up) >> 1;
-      if ((int64_t)(__ldg(keys + mid) >> sub_bits) < c) lo = mid + 1; else up = mid;
-    }
-    if (c < ge) cell_start[c] = (int32_t)lo;
-    lo = pos; up = hi;                                                        // ... with cell >= ge: pos of the next step
-    while (lo < up) {
-      const int64_t mid = (lo + up) >> 1;
-      if ((int64_t)(__ldg(keys + mid) >> sub_bits) < ge) lo = mid + 1; else up = mid;
-    }
-    pos = lo;
-  }
-}
-
 extern "C" int dc_cell_table(const uint64_t* keys_sorted, int64_t n, int64_t n_cells, int sub_bits, int32_t* cell_start, void* stream) {
   if (n_cells < 0 || n < 0) return dc_set_error(DC_ERR_ARG, "dc_cell_table: negative size");
-  if (n_cells > CT_SPARSE * (n + 1)) {
-    const int64_t warps = (n_cells + 1 + CT_CHUNK - 1) / CT_CHUNK;
-    cell_table_chunks_kernel<<<dc_blocks(warps * 32, CT_THREADS), CT_THREADS, 0, (cudaStream_t)stream>>>(keys_sorted, n, n_cells, sub_bits, cell_start);
-  } else {
-    const int64_t threads = ((n + 1 + 31) / 32) * 32;
-    cell_table_positions_kernel<<<dc_blocks(threads, 256), 256, 0, (cudaStream_t)stream>>>(keys_sorted, n, n_cells, sub_bits, cell_start);
-  }
+  const int64_t threads = ((n + 1 + 31) / 32) * 32;
+  cell_table_kernel<<<dc_blocks(threads, 256), 256, 0, (cudaStream_t)stream>>>(keys_sorted, n, n_cells, sub_bits, cell_start);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

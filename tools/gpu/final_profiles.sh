@@ -6,7 +6,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_ref.
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-strong-anchor > gpurun_out/r2_ncu_launch.log 2>&1
 ncu --profile-from-start off --set full --clock-control none --import-source on \
-    -k regex:'knn_record_kernel|knn_thread_list_kernel|step_forward_kernel|step_chain_kernel|step_points_kernel|pack_records_batched_kernel|gather_points_kernel|cell_table_positions_kernel|cell_table_chunks_kernel|cell_keys_kernel|world_points_batched_kernel' \
+    -k regex:'knn_record_kernel|knn_thread_list_kernel|step_forward_kernel|step_chain_kernel|step_points_kernel|pack_records_batched_kernel|gather_points_kernel|cell_table_kernel|cell_keys_kernel|world_points_batched_kernel' \
     -o gpurun_out/r2_timed -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-strong-anchor > gpurun_out/r2_ncu_full.log 2>&1
 tail -2 gpurun_out/r2_ncu_full.log
 python tools/ncu_summary.py gpurun_out/r2_timed.ncu-rep gpurun_out/r2_timed_region_kernels.md "Round 2 final: kernels of the timed region of bench.py (64 scans, 8.37 M points, k=32)" gpurun_out/r2_traffic.json 8366086
